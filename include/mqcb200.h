@@ -1,0 +1,159 @@
+/* mqcb200.h -- C ABI of the B200-native density-fitted J/K Fock-build engine.
+ *
+ * This is the drop-in boundary for ONE hot path of JorgeG94/metalquicha: the
+ * CPU routine `build_fock_df` and the tensor it consumes.  Every entry point
+ * below names the reference interface it replaces (paths relative to the
+ * reference tree).  The Fortran side binds these with ISO_C_BINDING
+ * (metalquicha_b200/fortran/mqc_b200_iface.f90); INTEGRATION.md shows the
+ * patch a maintainer applies.
+ *
+ * Conventions (reference: backends/cuest/bindings/cublas.f90:20-44,
+ * src/interface/mqc_capi_status.f90:21-23):
+ *   - every function returns int: MQCB200_OK=0, MQCB200_FAIL=1, MQCB200_BAD_HANDLE=2;
+ *     after a non-zero return mqcb200_last_error() gives the message (per thread);
+ *   - handles are opaque `void*`; one handle per host thread per GPU; calls block
+ *     (results are valid on return);
+ *   - all matrices are float64, COLUMN-major (Fortran order), contiguous;
+ *   - the caller owns every host array; the engine owns its device copies.
+ * There is no CPU fallback: without a CUDA device mqcb200_create fails.
+ */
+#ifndef MQCB200_H
+#define MQCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQCB200_OK 0
+#define MQCB200_FAIL 1
+#define MQCB200_BAD_HANDLE 2
+
+#define MQCB200_SLOT_FULL_RANGE 0 /* bmat    (mqc_libcint_rhf.f90:420,486-491) */
+#define MQCB200_SLOT_ATTENUATED 1 /* bmat_lr (mqc_libcint_rhf.f90:421,493-497) */
+#define MQCB200_NUM_SLOTS 2
+
+/* Number of per-phase timers returned by mqcb200_last_timings. */
+#define MQCB200_NUM_TIMERS 8
+/* indices: 0 upload(H2D+prep) 1 J pass 1 (gamma) 2 J pass 2 3 K half-transform
+ *          4 K accumulation 5 finalize/assemble 6 all-reduce 7 download(D2H) */
+
+/* ---- lifetime ------------------------------------------------------------
+ * Replaces the lazily created per-rank device context of the reference's GPU
+ * backend (backends/cuest/backend/mqc_cuest_context.f90:166-233, :285-299):
+ * binds device `mod(device_rank, device_count)` and owns grow-only pools. */
+int mqcb200_create(int device_rank, void **handle);
+int mqcb200_destroy(void *handle);
+/* Message of the last failure on this thread (cf. mqc_run_last_error,
+ * src/interface/mqc_capi_run.f90:147). Always NUL-terminated. */
+void mqcb200_last_error(int buffer_len, char *buffer);
+int mqcb200_version(void);
+/* CUDA stream the engine launches on (a cudaStream_t), for callers that want to
+ * bracket calls with their own events. */
+int mqcb200_get_stream(void *handle, void **stream);
+/* Upper bound (bytes) of the K half-transform scratch (cf. DF_EXCHANGE_BUFFER_BYTES,
+ * backends/cuest/backend/mqc_cuest_integrals.f90:122). Default 4 GiB. */
+int mqcb200_set_workspace_limit(void *handle, size_t bytes);
+
+/* ---- the fitted tensor ---------------------------------------------------
+ * Replaces the host array `bmat(nao*nao, naux)` that run_libcint_rhf receives
+ * from build_df_tensor (mqc_libcint_integrals.F90:913-990; layout :985-986,
+ * :1425-1437).  B is packed on the device into lower-triangular 16x16 tiles; only
+ * the lower triangle mu >= nu of each slab is read (slabs are symmetric by
+ * construction).  The tensor stays resident until the next set on that slot.
+ *
+ * The *_shard form holds only auxiliary functions [q_begin, q_begin+q_count) of a
+ * tensor with naux_total of them (whole-molecule builds sharded over GPUs);
+ * `b` then points at the first slab of the shard. */
+int mqcb200_set_tensor(void *handle, int slot, int n, int naux, const double *b);
+int mqcb200_set_tensor_shard(void *handle, int slot, int n, int naux_total,
+                             int q_begin, int q_count, const double *b_shard);
+/* b = three . metric^(-1/2) on the device (build_df_tensor's last two stages,
+ * mqc_libcint_integrals.F90:981-987, :992-1038): `half` is the caller's
+ * metric^(-1/2) (naux x naux, symmetric). */
+int mqcb200_set_tensor_from_3c(void *handle, int slot, int n, int naux,
+                               const double *three, const double *half);
+/* Synthetic tensor generated on the device from a counter-based generator that
+ * metalquicha_b200/synth.py reproduces bit-for-bit on the host (benchmarks at
+ * sizes whose full-square host tensor does not fit in RAM). */
+int mqcb200_synth_tensor(void *handle, int slot, int n, int naux_total,
+                         int q_begin, int q_count, uint64_t seed, double scale);
+int mqcb200_clear_tensor(void *handle, int slot);
+/* Packed device bytes held by a slot (0 when empty). */
+int mqcb200_tensor_bytes(void *handle, int slot, size_t *bytes);
+
+/* ---- the Fock build ------------------------------------------------------
+ * mqcb200_build_fock == build_fock_df(h, b, density, coeff, n_occ, fock, k_scale, j_scale)
+ * (mqc_libcint_rhf.f90:1576-1646):  F = H + j_scale*J - (0.5*k_scale)*K with
+ * J = sum_P (B_P.D) B_P and K = 2 sum_P (B_P C_occ)(B_P C_occ)^T.  `coeff` has
+ * leading dimension ldc >= n and at least n_occ columns; only (:,1:n_occ) is
+ * read (:1618).  The optional Fortran arguments become plain doubles: pass 1.0
+ * for an absent k_scale / j_scale.  n_occ may equal n (pseudo-orbital guess
+ * build, mqc_libcint_rhf.f90:1402-1405).  With n_occ == 0 K is zero. */
+int mqcb200_build_fock(void *handle, int slot, const double *h, const double *density,
+                       const double *coeff, int ldc, int n_occ,
+                       double k_scale, double j_scale, double *fock);
+/* The two contractions alone (either output may be NULL to skip it). K carries
+ * the restricted factor 2 of mqc_libcint_rhf.f90:1637. */
+int mqcb200_build_jk(void *handle, int slot, const double *density,
+                     const double *coeff, int ldc, int n_occ, double *j, double *k);
+/* Two-spin build (conventions of
+ * backends/cuest/backend/mqc_cuest_scf.f90:48-57, :826-838): J from the total
+ * density, K_sigma = sum_P (B_P C_sigma)(B_P C_sigma)^T with no factor 2.  A
+ * channel with n_sigma == 0 is skipped and its output left untouched
+ * (mqc_cuest_integrals.f90:1694-1701). */
+int mqcb200_build_jk_uhf(void *handle, int slot, const double *density_total,
+                         const double *coeff_a, int lda, int n_alpha,
+                         const double *coeff_b, int ldb, int n_beta,
+                         double *j, double *k_alpha, double *k_beta);
+/* F_sigma = H + J[Da+Db] - k_scale*K[C_sigma]  (shape of build_fock_uhf,
+ * mqc_libcint_rhf.f90:1648-1681, with the fitted K). */
+int mqcb200_build_fock_uhf(void *handle, int slot, const double *h,
+                           const double *density_total,
+                           const double *coeff_a, int lda, int n_alpha,
+                           const double *coeff_b, int ldb, int n_beta,
+                           double k_scale, double *fock_a, double *fock_b);
+/* E = 1/2 sum D (H + F)  (electronic_energy, mqc_libcint_rhf.f90:1691-1697),
+ * evaluated on the device from the operands of the last mqcb200_build_fock. */
+int mqcb200_last_energy(void *handle, double *e_elec);
+
+/* Device-resident variant: all pointers are DEVICE pointers on the engine's
+ * GPU (n x n, ld == n; coeff n x n_occ with ld == n).  No host<->device copies;
+ * the call is asynchronous on the engine's stream unless `sync` is non-zero. */
+int mqcb200_build_fock_device(void *handle, int slot, const double *d_h,
+                              const double *d_density, const double *d_coeff, int n_occ,
+                              double k_scale, double j_scale, double *d_fock, int sync);
+
+/* ---- multi-GPU (whole-molecule builds sharded by auxiliary index) ---------
+ * New behaviour relative to the reference, which never splits one Fock build
+ * (SURVEY 2.2).  One process per GPU; each holds a shard set with
+ * mqcb200_set_tensor_shard; every build ends in one sum all-reduce of [J;K]
+ * over NCCL.  The 128-byte id is created on rank 0 and carried to the other
+ * ranks by the host program's own transport (MPI bcast in the reference,
+ * src/parallel/mqc_bcast.f90). */
+int mqcb200_comm_unique_id(char id[128]);
+int mqcb200_comm_init(void *handle, int n_ranks, int rank, const char id[128]);
+int mqcb200_comm_destroy(void *handle);
+
+/* ---- fragment FIFO (fragmented MBE/GMBE runs, one fragment per GPU) -------
+ * Same semantics as queue_t (src/fragmentation/common/mqc_work_queue.f90:10-57):
+ * a FIFO of int64 ids, pop returns has_item=0 and id=-1 when drained.  Thread
+ * safe, so one host thread per GPU can pull from it. */
+int mqcb200_queue_create(const int64_t *ids, int64_t count, void **queue);
+int mqcb200_queue_pop(void *queue, int64_t *id, int *has_item);
+int mqcb200_queue_is_empty(void *queue, int *is_empty);
+int mqcb200_queue_destroy(void *queue);
+
+/* ---- instrumentation -------------------------------------------------------
+ * Per-phase device times (ms, CUDA events on the engine's stream) of the last
+ * build when profiling is on; kernels launched by the last build. */
+int mqcb200_set_profiling(void *handle, int on);
+int mqcb200_last_timings(void *handle, double ms[MQCB200_NUM_TIMERS]);
+int mqcb200_last_launches(void *handle, int *n_kernels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MQCB200_H */

@@ -1,0 +1,115 @@
+// common.cuh -- packed-tensor layout arithmetic and sm_100a PTX wrappers shared
+// by the kernels of the DF-J/K engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mqcb200 {
+
+// ---------------------------------------------------------------------------
+// Packed layout of one auxiliary slab B_Q (symmetric n x n), see DESIGN.md:
+//   * the matrix is cut into 16x16 tiles; only tiles (tr, tc) with tr >= tc are
+//     stored, ordered column by column:  idx(tr,tc) = tc*nt - tc*(tc-1)/2 + (tr-tc);
+//   * diagonal tiles are stored as full symmetric 16x16 blocks, rows/cols >= n are 0;
+//   * inside a tile the 256 doubles are in "DMMA fragment order": eight 8x4
+//     blocks, element (r,c) at ((r>>3)*4 + (c>>2))*32 + (r&7)*4 + (c&3), so that a
+//     warp's m8n8k4 A-fragment (and its transpose) is 256 contiguous bytes.
+// One slab is L = ntl*256 doubles; slabs are contiguous (row stride L).
+// ---------------------------------------------------------------------------
+constexpr int TILE = 16;
+constexpr int TILE_ELEMS = TILE * TILE;  // 256 doubles = 2 KiB
+
+__host__ __device__ inline int num_tiles(int n) { return (n + TILE - 1) / TILE; }
+__host__ __device__ inline long long num_lower_tiles(int nt) { return (long long)nt * (nt + 1) / 2; }
+__host__ __device__ inline long long packed_row_len(int n) {
+  return num_lower_tiles(num_tiles(n)) * TILE_ELEMS;
+}
+__host__ __device__ inline int tile_index(int tr, int tc, int nt) {  // tr >= tc
+  return tc * nt - (tc * (tc - 1)) / 2 + (tr - tc);
+}
+__host__ __device__ inline int in_tile_offset(int r, int c) {
+  return (((r >> 3) << 2) + (c >> 2)) * 32 + ((r & 7) << 2) + (c & 3);
+}
+
+#ifdef __CUDACC__
+// --------------------------- PTX wrappers ----------------------------------
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double2 ld_stream_f64x2(const double *p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); bytes % 16 == 0,
+// both addresses 16-byte aligned; completion is signalled on `bar` (complete_tx).
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// Same with an L2 eviction-priority hint (createpolicy result in `policy`).
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                                 uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, "
+      "[%3], %4;" ::"r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+#endif  // __CUDACC__
+
+}  // namespace mqcb200

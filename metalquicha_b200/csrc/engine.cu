@@ -1,0 +1,785 @@
+// engine.cu -- the context behind the C ABI of include/mqcb200.h: device binding,
+// grow-only pools, tensor slots, the build sequence, NCCL (loaded lazily), the
+// fragment FIFO.  No CPU fallback exists anywhere in this file: every entry point
+// either runs the CUDA path or fails with a message.
+#include "../../include/mqcb200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace mqcb200 {
+
+static thread_local std::string g_last_error;
+
+struct Failure : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define CUDA_CHECK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t err__ = (expr);                                                                   \
+    if (err__ != cudaSuccess)                                                                     \
+      throw Failure(std::string("mqcb200: CUDA error '") + cudaGetErrorString(err__) + "' in " + \
+                    #expr + " (" __FILE__ ":" + std::to_string(__LINE__) + ")");                  \
+  } while (0)
+
+// ---- grow-only device buffer (cf. device_pool_t of the reference's GPU backend,
+// backends/cuest/backend/mqc_cuest_context.f90:40-53) -------------------------------
+struct DevBuf {
+  void *ptr = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes) {
+    if (bytes <= cap) return;
+    if (ptr) CUDA_CHECK(cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    CUDA_CHECK(cudaMalloc(&ptr, bytes));
+    cap = bytes;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+  double *d() const { return static_cast<double *>(ptr); }
+};
+
+struct TensorSlot {
+  DevBuf packed;
+  int n = 0;
+  int naux_total = 0;
+  int q_begin = 0;
+  int q_count = 0;
+  long long L = 0;
+  bool set = false;
+};
+
+// ---- NCCL through dlopen: the library must load on a box without NCCL ----------------
+struct Id128 {
+  char bytes[128];
+};
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, Id128 /* ncclUniqueId, passed by value */, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mutex;
+
+static void load_nccl() {
+  std::lock_guard<std::mutex> lock(g_nccl_mutex);
+  if (g_nccl.lib) return;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *lib = nullptr;
+  for (const char *nm : names) {
+    lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) throw Failure("mqcb200: NCCL is required for a multi-GPU build but libnccl.so.2 could not be loaded");
+  auto sym = [&](const char *nm) {
+    void *p = dlsym(lib, nm);
+    if (!p) throw Failure(std::string("mqcb200: NCCL symbol missing: ") + nm);
+    return p;
+  };
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(sym("ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(sym("ncclCommInitRank"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(sym("ncclAllReduce"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(sym("ncclCommDestroy"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
+  g_nccl.lib = lib;
+}
+#define NCCL_CHECK(expr)                                                                   \
+  do {                                                                                     \
+    int rc__ = (expr);                                                                     \
+    if (rc__ != 0)                                                                         \
+      throw Failure(std::string("mqcb200: NCCL error '") + g_nccl.GetErrorString(rc__) + \
+                    "' in " + #expr);                                                      \
+  } while (0)
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclSum = 0;
+
+// ---- the engine ------------------------------------------------------------------------
+constexpr uint32_t kMagic = 0x4D51B200u;
+
+struct Engine {
+  uint32_t magic = kMagic;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  TensorSlot slots[MQCB200_NUM_SLOTS];
+  size_t workspace_limit = (size_t)4 << 30;
+
+  // per-build device operands and scratch (grow-only)
+  DevBuf d_h, d_density, d_coeff, d_coeff_b, d_w, d_ctf, d_gamma_partial, d_gamma, d_jpart, d_x, d_kpart;
+  DevBuf d_jk;       // [J | K | K_beta] contiguous so one all-reduce covers them
+  DevBuf d_fock, d_fock_b, d_scalar, d_stage;
+  int last_n = 0;    // shape of the operands of the last build_fock (for last_energy)
+  bool have_last_fock = false;
+
+  // multi-GPU
+  void *comm = nullptr;
+  int n_ranks = 1, rank = 0;
+
+  // instrumentation: every occurrence of a phase gets its own event pair; a build's
+  // per-phase time is the sum over its occurrences (K runs once per Q-chunk and spin)
+  bool profiling = false;
+  struct Span { int idx; cudaEvent_t a, b; };
+  std::vector<Span> spans;          // spans[0..n_spans) are live for the last build
+  size_t n_spans = 0;
+  double last_ms[MQCB200_NUM_TIMERS] = {};
+  int launches = 0;
+
+  void bind() { CUDA_CHECK(cudaSetDevice(device)); }
+
+  void phase_begin(int idx) {
+    if (!profiling) return;
+    if (n_spans == spans.size()) {
+      Span sp{idx, nullptr, nullptr};
+      CUDA_CHECK(cudaEventCreate(&sp.a));
+      CUDA_CHECK(cudaEventCreate(&sp.b));
+      spans.push_back(sp);
+    }
+    spans[n_spans].idx = idx;
+    CUDA_CHECK(cudaEventRecord(spans[n_spans].a, stream));
+    ++n_spans;
+  }
+  void phase_end(int idx) {
+    if (!profiling) return;
+    for (size_t i = n_spans; i-- > 0;)
+      if (spans[i].idx == idx) {
+        CUDA_CHECK(cudaEventRecord(spans[i].b, stream));
+        return;
+      }
+  }
+  void reset_timers() {
+    n_spans = 0;
+    for (int i = 0; i < MQCB200_NUM_TIMERS; ++i) last_ms[i] = 0.0;
+    launches = 0;
+  }
+  void collect_timers() {
+    if (!profiling) return;
+    for (size_t i = 0; i < n_spans; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, spans[i].a, spans[i].b) == cudaSuccess) last_ms[spans[i].idx] += ms;
+    }
+  }
+};
+
+static Engine *as_engine(void *h) {
+  Engine *e = static_cast<Engine *>(h);
+  if (!e || e->magic != kMagic) return nullptr;
+  return e;
+}
+
+enum { T_UPLOAD = 0, T_J1, T_J2, T_K1, T_K2, T_FINAL, T_ALLREDUCE, T_DOWNLOAD };
+
+// ------------------------------- tensor set-up ------------------------------------------
+static void slot_prepare(Engine *e, TensorSlot &sl, int n, int naux_total, int q_begin, int q_count) {
+  if (n <= 0) throw Failure("mqcb200: the orbital dimension n must be positive");
+  if (naux_total <= 0 || q_count < 0 || q_begin < 0 || q_begin + q_count > naux_total)
+    throw Failure("mqcb200: auxiliary range [q_begin, q_begin+q_count) does not fit naux_total");
+  sl.set = false;
+  sl.n = n;
+  sl.naux_total = naux_total;
+  sl.q_begin = q_begin;
+  sl.q_count = q_count;
+  sl.L = packed_row_len(n);
+  sl.packed.ensure(std::max<size_t>(16, (size_t)sl.L * (size_t)q_count * sizeof(double)));
+  (void)e;
+}
+
+static void set_tensor_host(Engine *e, int slot, int n, int naux_total, int q_begin, int q_count,
+                            const double *b) {
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  if (!b && q_count > 0) throw Failure("mqcb200: null tensor pointer");
+  e->bind();
+  TensorSlot &sl = e->slots[slot];
+  slot_prepare(e, sl, n, naux_total, q_begin, q_count);
+  const size_t slab = (size_t)n * n;
+  // stage full-square slabs through a bounded device buffer, pack chunk by chunk
+  size_t chunk = std::max<size_t>(1, ((size_t)512 << 20) / (slab * sizeof(double)));
+  chunk = std::min<size_t>(chunk, (size_t)std::max(q_count, 1));
+  e->d_stage.ensure(chunk * slab * sizeof(double));
+  for (size_t q0 = 0; q0 < (size_t)q_count; q0 += chunk) {
+    const size_t qc = std::min(chunk, (size_t)q_count - q0);
+    CUDA_CHECK(cudaMemcpyAsync(e->d_stage.ptr, b + q0 * slab, qc * slab * sizeof(double), cudaMemcpyHostToDevice,
+                               e->stream));
+    launch_pack_tensor(e->d_stage.d(), n, (int)qc, sl.packed.d() + q0 * (size_t)sl.L, e->stream);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));  // the staging buffer is reused
+  }
+  sl.set = true;
+}
+
+// ------------------------------- the build ------------------------------------------------
+struct BuildArgs {
+  int slot = 0;
+  // exactly one of host/device operand sets is used
+  bool device_operands = false;
+  const double *h = nullptr, *density = nullptr;
+  const double *coeff_a = nullptr, *coeff_b = nullptr;
+  int lda = 0, ldb = 0, n_a = 0, n_b = 0;
+  bool two_spin = false;          // K per spin with factor 1 instead of one K with factor 2
+  bool want_j = true, want_k = true;
+  // outputs (host pointers unless device_operands)
+  double *j = nullptr, *k_a = nullptr, *k_b = nullptr, *fock_a = nullptr, *fock_b = nullptr;
+  double k_scale = 1.0, j_scale = 1.0;
+  bool assemble = false;
+  bool sync = true;
+};
+
+static void upload_matrix(Engine *e, DevBuf &dst, const double *src, int rows, int cols, int ld) {
+  dst.ensure(std::max<size_t>(16, (size_t)rows * cols * sizeof(double)));
+  if (cols == 0) return;
+  if (ld == rows)
+    CUDA_CHECK(cudaMemcpyAsync(dst.ptr, src, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  else
+    CUDA_CHECK(cudaMemcpy2DAsync(dst.ptr, (size_t)rows * sizeof(double), src, (size_t)ld * sizeof(double),
+                                 (size_t)rows * sizeof(double), cols, cudaMemcpyHostToDevice, e->stream));
+}
+
+static void run_k(Engine *e, const TensorSlot &sl, const double *d_coeff, int ldc, int n_occ, double *d_kpart_out,
+                  KPlan &plan) {
+  const int n = sl.n;
+  plan = plan_k(n, n_occ, sl.q_count, e->workspace_limit, e->sm_count);
+  e->d_ctf.ensure((size_t)num_tiles(n) * plan.nib * 128 * sizeof(double));
+  e->d_x.ensure(plan.x_elems_per_q * (size_t)plan.q_chunk * sizeof(double));
+  launch_pack_coeff(d_coeff, ldc, n, n_occ, plan.nib, e->d_ctf.d(), e->stream);
+  e->launches += 1;
+  for (int q0 = 0, chunk = 0; q0 < sl.q_count; q0 += plan.q_chunk, ++chunk) {
+    const int qc = std::min(plan.q_chunk, sl.q_count - q0);
+    e->phase_begin(T_K1);
+    launch_k_half_transform(sl.packed.d() + (size_t)q0 * sl.L, sl.L, n, qc, e->d_ctf.d(), plan, e->d_x.d(),
+                            e->stream);
+    e->phase_end(T_K1);
+    e->phase_begin(T_K2);
+    launch_k_accumulate(e->d_x.d(), qc, plan, d_kpart_out, chunk > 0, e->stream);
+    e->phase_end(T_K2);
+    e->launches += 2;
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+static void build(Engine *e, const BuildArgs &a) {
+  if (a.slot < 0 || a.slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  TensorSlot &sl = e->slots[a.slot];
+  if (!sl.set) throw Failure("mqcb200: no fitted tensor has been set on this slot (call mqcb200_set_tensor first)");
+  if (!a.density && a.want_j) throw Failure("mqcb200: null density");
+  if (a.n_a < 0 || a.n_b < 0) throw Failure("mqcb200: negative occupied count");
+  if (a.want_k && a.n_a > 0 && (!a.coeff_a || a.lda < sl.n)) throw Failure("mqcb200: bad coefficient matrix / leading dimension");
+  if (a.want_k && a.two_spin && a.n_b > 0 && (!a.coeff_b || a.ldb < sl.n)) throw Failure("mqcb200: bad beta coefficient matrix / leading dimension");
+  e->bind();
+  e->reset_timers();
+  const int n = sl.n;
+  const size_t nn = (size_t)n * n;
+  const bool sharded = e->comm != nullptr;
+  if (sharded && sl.naux_total == sl.q_count && e->n_ranks > 1)
+    throw Failure("mqcb200: a communicator is active but this slot holds the whole tensor; use mqcb200_set_tensor_shard");
+
+  // ---- operands on the device
+  const double *d_h = nullptr, *d_density = nullptr, *d_ca = nullptr, *d_cb = nullptr;
+  int lda = n, ldb = n;
+  {
+    e->phase_begin(T_UPLOAD);
+    if (a.device_operands) {
+      d_h = a.h; d_density = a.density; d_ca = a.coeff_a; d_cb = a.coeff_b;
+      lda = a.lda; ldb = a.ldb;
+    } else {
+      if (a.h) { upload_matrix(e, e->d_h, a.h, n, n, n); d_h = e->d_h.d(); }
+      if (a.density) { upload_matrix(e, e->d_density, a.density, n, n, n); d_density = e->d_density.d(); }
+      if (a.want_k && a.n_a > 0) { upload_matrix(e, e->d_coeff, a.coeff_a, n, a.n_a, a.lda); d_ca = e->d_coeff.d(); }
+      if (a.want_k && a.two_spin && a.n_b > 0) { upload_matrix(e, e->d_coeff_b, a.coeff_b, n, a.n_b, a.ldb); d_cb = e->d_coeff_b.d(); }
+    }
+    e->phase_end(T_UPLOAD);
+  }
+
+  const bool do_j = a.want_j;
+  const bool do_ka = a.want_k && a.n_a > 0;
+  const bool do_kb = a.want_k && a.two_spin && a.n_b > 0;
+  // [J | K_a | K_b] in one buffer: a single all-reduce covers whatever was built
+  e->d_jk.ensure(3 * nn * sizeof(double));
+  double *d_j = e->d_jk.d(), *d_ka = d_j + nn, *d_kb = d_j + 2 * nn;
+
+  // ---- J
+  JPlan jp = plan_j(n, sl.q_count);
+  if (do_j) {
+    if (sl.q_count > 0) {
+      e->d_w.ensure((size_t)sl.L * sizeof(double));
+      e->d_gamma_partial.ensure(jp.gamma_partial_elems * sizeof(double));
+      e->d_gamma.ensure((size_t)sl.q_count * sizeof(double));
+      e->d_jpart.ensure(jp.j_partial_elems * sizeof(double));
+      e->phase_begin(T_J1);
+      launch_pack_density(d_density, n, e->d_w.d(), e->stream);
+      launch_j_gamma(sl.packed.d(), sl.L, sl.q_count, e->d_w.d(), jp, e->d_gamma_partial.d(), e->d_gamma.d(), e->stream);
+      e->phase_end(T_J1);
+      e->phase_begin(T_J2);
+      launch_j_accumulate(sl.packed.d(), sl.L, sl.q_count, e->d_gamma.d(), jp, e->d_jpart.d(), e->stream);
+      e->phase_end(T_J2);
+      e->launches += 4;
+      CUDA_CHECK(cudaGetLastError());
+    }
+  }
+
+  // ---- K (alpha / closed shell), then finalize; K (beta) reuses the scratch afterwards
+  const double kfac = a.two_spin ? 1.0 : 2.0;
+  KPlan kp{};
+  if (do_ka && sl.q_count > 0) {
+    KPlan probe = plan_k(n, a.n_a, sl.q_count, e->workspace_limit, e->sm_count);
+    e->d_kpart.ensure(probe.kpart_elems * sizeof(double));
+    run_k(e, sl, d_ca, lda, a.n_a, e->d_kpart.d(), kp);
+  }
+  e->phase_begin(T_FINAL);
+  if (sl.q_count > 0) {
+    launch_finalize_jk(do_j ? e->d_jpart.d() : nullptr, jp.n_slices, do_ka ? e->d_kpart.d() : nullptr, kp.n_splits, n,
+                       kfac, do_j ? d_j : nullptr, do_ka ? d_ka : nullptr, e->stream);
+    e->launches += 1;
+  } else {
+    if (do_j) CUDA_CHECK(cudaMemsetAsync(d_j, 0, nn * sizeof(double), e->stream));
+    if (do_ka) CUDA_CHECK(cudaMemsetAsync(d_ka, 0, nn * sizeof(double), e->stream));
+  }
+  e->phase_end(T_FINAL);
+  if (do_kb) {
+    if (sl.q_count > 0) {
+      KPlan probe = plan_k(n, a.n_b, sl.q_count, e->workspace_limit, e->sm_count);
+      e->d_kpart.ensure(probe.kpart_elems * sizeof(double));  // stream-ordered: finalize above has consumed it
+      KPlan kpb{};
+      run_k(e, sl, d_cb, ldb, a.n_b, e->d_kpart.d(), kpb);
+      launch_finalize_jk(nullptr, 0, e->d_kpart.d(), kpb.n_splits, n, kfac, nullptr, d_kb, e->stream);
+      e->launches += 1;
+    } else {
+      CUDA_CHECK(cudaMemsetAsync(d_kb, 0, nn * sizeof(double), e->stream));
+    }
+  }
+  CUDA_CHECK(cudaGetLastError());
+
+  // ---- multi-GPU: one sum all-reduce over whatever was built
+  if (sharded && e->n_ranks > 1) {
+    e->phase_begin(T_ALLREDUCE);
+    // J, K_a, K_b are adjacent; reduce the smallest contiguous span that covers the built ones
+    size_t first = do_j ? 0 : (do_ka ? 1 : 2);
+    size_t last = do_kb ? 3 : (do_ka ? 2 : 1);
+    if (!do_j && !do_ka && !do_kb) { first = 0; last = 0; }
+    if (last > first) {
+      if (!do_ka && do_kb && do_j) CUDA_CHECK(cudaMemsetAsync(d_ka, 0, nn * sizeof(double), e->stream));
+      NCCL_CHECK(g_nccl.AllReduce(d_j + first * nn, d_j + first * nn, (last - first) * nn, kNcclFloat64, kNcclSum,
+                                  e->comm, e->stream));
+    }
+    e->phase_end(T_ALLREDUCE);
+  }
+
+  // ---- assemble and return
+  e->have_last_fock = false;
+  if (a.assemble) {
+    e->phase_begin(T_FINAL);
+    const double kf_a = a.two_spin ? a.k_scale : 0.5 * a.k_scale;
+    double *d_fa = a.device_operands ? a.fock_a : (e->d_fock.ensure(nn * sizeof(double)), e->d_fock.d());
+    launch_assemble_fock(d_h, do_j ? d_j : nullptr, do_ka ? d_ka : nullptr, a.j_scale, kf_a, n, d_fa, e->stream);
+    e->launches += 1;
+    double *d_fb = nullptr;
+    if (a.two_spin && a.fock_b) {
+      d_fb = a.device_operands ? a.fock_b : (e->d_fock_b.ensure(nn * sizeof(double)), e->d_fock_b.d());
+      launch_assemble_fock(d_h, do_j ? d_j : nullptr, do_kb ? d_kb : nullptr, a.j_scale, a.k_scale, n, d_fb, e->stream);
+      e->launches += 1;
+    }
+    e->phase_end(T_FINAL);
+    if (!a.device_operands) {
+      e->phase_begin(T_DOWNLOAD);
+      CUDA_CHECK(cudaMemcpyAsync(a.fock_a, d_fa, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      if (d_fb) CUDA_CHECK(cudaMemcpyAsync(a.fock_b, d_fb, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      e->phase_end(T_DOWNLOAD);
+      if (!a.two_spin && d_h && d_density) { e->last_n = n; e->have_last_fock = true; }
+    }
+  } else if (!a.device_operands) {
+    e->phase_begin(T_DOWNLOAD);
+    if (a.j && do_j) CUDA_CHECK(cudaMemcpyAsync(a.j, d_j, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (a.k_a && do_ka) CUDA_CHECK(cudaMemcpyAsync(a.k_a, d_ka, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (a.k_b && do_kb) CUDA_CHECK(cudaMemcpyAsync(a.k_b, d_kb, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    // K of an empty closed-shell / alpha channel is zero, not "untouched": only the two-spin
+    // beta channel has skip semantics (mqc_cuest_integrals.f90:1694-1701)
+    e->phase_end(T_DOWNLOAD);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  if (a.sync) {
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (!a.device_operands && !a.assemble && a.k_a && a.want_k && !do_ka) std::memset(a.k_a, 0, nn * sizeof(double));
+    e->collect_timers();
+  }
+}
+
+// ------------------------------- fragment FIFO -------------------------------------------
+struct Fifo {
+  uint32_t magic = 0x4D51F1F0u;
+  std::vector<int64_t> ids;
+  size_t head = 0;
+  std::mutex m;
+};
+
+}  // namespace mqcb200
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace mqcb200;
+
+#define API_BEGIN try {
+#define API_END                                   \
+  }                                               \
+  catch (const std::exception &ex) {              \
+    g_last_error = ex.what();                     \
+    return MQCB200_FAIL;                          \
+  }                                               \
+  catch (...) {                                   \
+    g_last_error = "mqcb200: unknown failure";    \
+    return MQCB200_FAIL;                          \
+  }                                               \
+  return MQCB200_OK;
+
+#define GET_ENGINE(h)                                                   \
+  Engine *e = as_engine(h);                                             \
+  if (!e) {                                                             \
+    g_last_error = "mqcb200: the handle names no engine";               \
+    return MQCB200_BAD_HANDLE;                                          \
+  }
+
+extern "C" {
+
+int mqcb200_version(void) { return 100; }
+
+void mqcb200_last_error(int buffer_len, char *buffer) {
+  if (!buffer || buffer_len <= 0) return;
+  std::snprintf(buffer, (size_t)buffer_len, "%s", g_last_error.c_str());
+}
+
+int mqcb200_create(int device_rank, void **handle) {
+  if (!handle) {
+    g_last_error = "mqcb200: null handle pointer";
+    return MQCB200_FAIL;
+  }
+  *handle = nullptr;
+  API_BEGIN
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count <= 0)
+    throw Failure(std::string("mqcb200: no CUDA device is visible (") + cudaGetErrorString(err) +
+                  "); this engine has no CPU fallback");
+  if (device_rank < 0) throw Failure("mqcb200: negative device rank");
+  Engine *e = new Engine();
+  try {
+    e->device = device_rank % count;  // cf. mqc_cuest_context.f90:188
+    e->bind();
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, e->device));
+    if (prop.major < 10)
+      throw Failure(std::string("mqcb200: device '") + prop.name + "' is not sm_100-class; the kernels are built for sm_100a only");
+    e->sm_count = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->d_scalar.ensure(64);
+    configure_kernels();
+    CUDA_CHECK(cudaGetLastError());
+  } catch (...) {
+    delete e;
+    throw;
+  }
+  *handle = e;
+  API_END
+}
+
+int mqcb200_destroy(void *handle) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  for (auto &sl : e->slots) sl.packed.release();
+  DevBuf *bufs[] = {&e->d_h, &e->d_density, &e->d_coeff, &e->d_coeff_b, &e->d_w, &e->d_ctf, &e->d_gamma_partial,
+                    &e->d_gamma, &e->d_jpart, &e->d_x, &e->d_kpart, &e->d_jk, &e->d_fock, &e->d_fock_b,
+                    &e->d_scalar, &e->d_stage};
+  for (DevBuf *b : bufs) b->release();
+  for (auto &sp : e->spans) {
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  if (e->stream) cudaStreamDestroy(e->stream);
+  e->magic = 0;
+  delete e;
+  API_END
+}
+
+int mqcb200_get_stream(void *handle, void **stream) {
+  GET_ENGINE(handle)
+  if (!stream) { g_last_error = "mqcb200: null stream pointer"; return MQCB200_FAIL; }
+  *stream = e->stream;
+  return MQCB200_OK;
+}
+
+int mqcb200_set_workspace_limit(void *handle, size_t bytes) {
+  GET_ENGINE(handle)
+  if (bytes < ((size_t)1 << 20)) { g_last_error = "mqcb200: workspace limit below 1 MiB"; return MQCB200_FAIL; }
+  e->workspace_limit = bytes;
+  return MQCB200_OK;
+}
+
+int mqcb200_set_tensor(void *handle, int slot, int n, int naux, const double *b) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  set_tensor_host(e, slot, n, naux, 0, naux, b);
+  API_END
+}
+
+int mqcb200_set_tensor_shard(void *handle, int slot, int n, int naux_total, int q_begin, int q_count,
+                             const double *b_shard) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  set_tensor_host(e, slot, n, naux_total, q_begin, q_count, b_shard);
+  API_END
+}
+
+int mqcb200_set_tensor_from_3c(void *handle, int slot, int n, int naux, const double *three, const double *half) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  (void)slot; (void)n; (void)naux; (void)three; (void)half;
+  throw Failure("mqcb200: device whitening (set_tensor_from_3c) is not built yet; whiten on the host and call mqcb200_set_tensor");
+  API_END
+}
+
+int mqcb200_synth_tensor(void *handle, int slot, int n, int naux_total, int q_begin, int q_count, uint64_t seed,
+                         double scale) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  e->bind();
+  TensorSlot &sl = e->slots[slot];
+  slot_prepare(e, sl, n, naux_total, q_begin, q_count);
+  if (q_count > 0) launch_synth_tensor(sl.packed.d(), n, q_begin, q_count, seed, scale, e->stream);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  sl.set = true;
+  API_END
+}
+
+int mqcb200_clear_tensor(void *handle, int slot) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  e->bind();
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  e->slots[slot].packed.release();
+  e->slots[slot].set = false;
+  API_END
+}
+
+int mqcb200_tensor_bytes(void *handle, int slot, size_t *bytes) {
+  GET_ENGINE(handle)
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS || !bytes) { g_last_error = "mqcb200: bad slot or null output"; return MQCB200_FAIL; }
+  const TensorSlot &sl = e->slots[slot];
+  *bytes = sl.set ? (size_t)sl.L * (size_t)sl.q_count * sizeof(double) : 0;
+  return MQCB200_OK;
+}
+
+int mqcb200_build_fock(void *handle, int slot, const double *h, const double *density, const double *coeff, int ldc,
+                       int n_occ, double k_scale, double j_scale, double *fock) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!h || !density || !fock) throw Failure("mqcb200: null matrix argument to build_fock");
+  BuildArgs a;
+  a.slot = slot; a.h = h; a.density = density; a.coeff_a = coeff; a.lda = ldc; a.n_a = n_occ;
+  a.k_scale = k_scale; a.j_scale = j_scale; a.fock_a = fock; a.assemble = true;
+  // j_scale == 0 is the attenuated second pass (rhf.f90:1100): J is not needed at all
+  a.want_j = j_scale != 0.0;
+  a.want_k = k_scale != 0.0;
+  build(e, a);
+  API_END
+}
+
+int mqcb200_build_jk(void *handle, int slot, const double *density, const double *coeff, int ldc, int n_occ,
+                     double *j, double *k) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  BuildArgs a;
+  a.slot = slot; a.density = density; a.coeff_a = coeff; a.lda = ldc; a.n_a = n_occ;
+  a.j = j; a.k_a = k; a.want_j = j != nullptr; a.want_k = k != nullptr;
+  if (a.want_j && !density) throw Failure("mqcb200: J was requested without a density");
+  build(e, a);
+  API_END
+}
+
+int mqcb200_build_jk_uhf(void *handle, int slot, const double *density_total, const double *coeff_a, int lda,
+                         int n_alpha, const double *coeff_b, int ldb, int n_beta, double *j, double *k_alpha,
+                         double *k_beta) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  BuildArgs a;
+  a.slot = slot; a.density = density_total; a.two_spin = true;
+  a.coeff_a = coeff_a; a.lda = lda; a.n_a = n_alpha; a.coeff_b = coeff_b; a.ldb = ldb; a.n_b = n_beta;
+  a.j = j; a.k_a = k_alpha; a.k_b = k_beta; a.want_j = j != nullptr; a.want_k = (k_alpha != nullptr) || (k_beta != nullptr);
+  if (a.want_j && !density_total) throw Failure("mqcb200: J was requested without a density");
+  build(e, a);
+  API_END
+}
+
+int mqcb200_build_fock_uhf(void *handle, int slot, const double *h, const double *density_total,
+                           const double *coeff_a, int lda, int n_alpha, const double *coeff_b, int ldb, int n_beta,
+                           double k_scale, double *fock_a, double *fock_b) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!h || !density_total || !fock_a || !fock_b) throw Failure("mqcb200: null matrix argument to build_fock_uhf");
+  BuildArgs a;
+  a.slot = slot; a.h = h; a.density = density_total; a.two_spin = true;
+  a.coeff_a = coeff_a; a.lda = lda; a.n_a = n_alpha; a.coeff_b = coeff_b; a.ldb = ldb; a.n_b = n_beta;
+  a.k_scale = k_scale; a.j_scale = 1.0; a.fock_a = fock_a; a.fock_b = fock_b; a.assemble = true;
+  a.want_k = k_scale != 0.0;
+  build(e, a);
+  API_END
+}
+
+int mqcb200_build_fock_device(void *handle, int slot, const double *d_h, const double *d_density,
+                              const double *d_coeff, int n_occ, double k_scale, double j_scale, double *d_fock,
+                              int sync) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!d_h || !d_density || !d_fock) throw Failure("mqcb200: null device pointer argument to build_fock_device");
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  BuildArgs a;
+  a.slot = slot; a.device_operands = true; a.h = d_h; a.density = d_density; a.coeff_a = d_coeff;
+  a.lda = e->slots[slot].n; a.n_a = n_occ; a.k_scale = k_scale; a.j_scale = j_scale; a.fock_a = d_fock;
+  a.assemble = true; a.sync = sync != 0;
+  a.want_j = j_scale != 0.0;
+  a.want_k = k_scale != 0.0;
+  build(e, a);
+  API_END
+}
+
+int mqcb200_last_energy(void *handle, double *e_elec) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!e_elec) throw Failure("mqcb200: null energy pointer");
+  if (!e->have_last_fock) throw Failure("mqcb200: no closed-shell build_fock has run on this handle yet");
+  e->bind();
+  launch_energy(e->d_density.d(), e->d_h.d(), e->d_fock.d(), e->last_n, e->d_scalar.d(), e->stream);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpyAsync(e_elec, e->d_scalar.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  API_END
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------
+int mqcb200_comm_unique_id(char id[128]) {
+  API_BEGIN
+  if (!id) throw Failure("mqcb200: null id buffer");
+  load_nccl();
+  NCCL_CHECK(g_nccl.GetUniqueId(id));
+  API_END
+}
+
+int mqcb200_comm_init(void *handle, int n_ranks, int rank, const char id[128]) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) throw Failure("mqcb200: bad communicator arguments");
+  if (e->comm) throw Failure("mqcb200: a communicator is already active on this handle");
+  load_nccl();
+  e->bind();
+  Id128 uid;
+  std::memcpy(uid.bytes, id, 128);
+  void *comm = nullptr;
+  NCCL_CHECK(g_nccl.CommInitRank(&comm, n_ranks, uid, rank));
+  e->comm = comm;
+  e->n_ranks = n_ranks;
+  e->rank = rank;
+  API_END
+}
+
+int mqcb200_comm_destroy(void *handle) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (e->comm) {
+    e->bind();
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    NCCL_CHECK(g_nccl.CommDestroy(e->comm));
+    e->comm = nullptr;
+    e->n_ranks = 1;
+    e->rank = 0;
+  }
+  API_END
+}
+
+// ---- fragment FIFO ------------------------------------------------------------------------
+int mqcb200_queue_create(const int64_t *ids, int64_t count, void **queue) {
+  API_BEGIN
+  if (!queue || count < 0 || (count > 0 && !ids)) throw Failure("mqcb200: bad queue arguments");
+  Fifo *f = new Fifo();
+  f->ids.assign(ids, ids + count);
+  *queue = f;
+  API_END
+}
+
+static Fifo *as_fifo(void *q) {
+  Fifo *f = static_cast<Fifo *>(q);
+  return (f && f->magic == 0x4D51F1F0u) ? f : nullptr;
+}
+
+int mqcb200_queue_pop(void *queue, int64_t *id, int *has_item) {
+  Fifo *f = as_fifo(queue);
+  if (!f) { g_last_error = "mqcb200: the handle names no queue"; return MQCB200_BAD_HANDLE; }
+  if (!id || !has_item) { g_last_error = "mqcb200: null output pointer"; return MQCB200_FAIL; }
+  std::lock_guard<std::mutex> lock(f->m);
+  if (f->head >= f->ids.size()) {  // queue_pop, mqc_work_queue.f90:36-40
+    *id = -1;
+    *has_item = 0;
+  } else {
+    *id = f->ids[f->head++];
+    *has_item = 1;
+  }
+  return MQCB200_OK;
+}
+
+int mqcb200_queue_is_empty(void *queue, int *is_empty) {
+  Fifo *f = as_fifo(queue);
+  if (!f) { g_last_error = "mqcb200: the handle names no queue"; return MQCB200_BAD_HANDLE; }
+  if (!is_empty) { g_last_error = "mqcb200: null output pointer"; return MQCB200_FAIL; }
+  std::lock_guard<std::mutex> lock(f->m);
+  *is_empty = f->head >= f->ids.size() ? 1 : 0;
+  return MQCB200_OK;
+}
+
+int mqcb200_queue_destroy(void *queue) {
+  Fifo *f = as_fifo(queue);
+  if (!f) { g_last_error = "mqcb200: the handle names no queue"; return MQCB200_BAD_HANDLE; }
+  f->magic = 0;
+  delete f;
+  return MQCB200_OK;
+}
+
+// ---- instrumentation ----------------------------------------------------------------------
+int mqcb200_set_profiling(void *handle, int on) {
+  GET_ENGINE(handle)
+  e->profiling = on != 0;
+  return MQCB200_OK;
+}
+
+int mqcb200_last_timings(void *handle, double ms[MQCB200_NUM_TIMERS]) {
+  GET_ENGINE(handle)
+  if (!ms) { g_last_error = "mqcb200: null output pointer"; return MQCB200_FAIL; }
+  for (int i = 0; i < MQCB200_NUM_TIMERS; ++i) ms[i] = e->last_ms[i];
+  return MQCB200_OK;
+}
+
+int mqcb200_last_launches(void *handle, int *n_kernels) {
+  GET_ENGINE(handle)
+  if (!n_kernels) { g_last_error = "mqcb200: null output pointer"; return MQCB200_FAIL; }
+  *n_kernels = e->launches;
+  return MQCB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+// j_kernels.cu -- the Coulomb half of build_fock_df on the packed tensor.
+//
+//   pass 1   gamma_Q = sum_p Bp[Q][p] * w[p]        (reference rhf.f90:1620-1622)
+//   pass 2   Jp[p]   = sum_Q gamma_Q * Bp[Q][p]     (reference rhf.f90:1624-1627)
+//
+// Both passes stream the whole packed tensor once: algorithmic traffic is
+// 8*L*Q bytes per pass (L = packed row length), i.e. 16*npair*Q per build up to the
+// tile padding.  They are HBM-bound; the design goals are 128-bit coalesced
+// streaming loads that bypass L1, enough loads in flight per SM to cover the HBM
+// latency, and fixed-order reductions (no floating-point atomics) so that repeated
+// builds are bit-identical.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mqcb200 {
+
+constexpr int J_THREADS = 256;
+constexpr int J_ROWS = 8;               // auxiliary rows per CTA in pass 1
+constexpr int J_STEP = J_THREADS * 2;   // doubles covered by one CTA-wide 128-bit load
+
+__global__ void __launch_bounds__(J_THREADS) j_gamma_kernel(const double *__restrict__ packed, long long L,
+                                                            int q_count, const double *__restrict__ w,
+                                                            long long seg_len, int qblk0,
+                                                            double *__restrict__ gamma_partial) {
+  const int seg = blockIdx.x;
+  const int q0 = (qblk0 + blockIdx.y) * J_ROWS;
+  const long long start = (long long)seg * seg_len;
+  long long end = start + seg_len;
+  if (end > L) end = L;
+
+  const double *row[J_ROWS];
+#pragma unroll
+  for (int r = 0; r < J_ROWS; ++r) {
+    int q = q0 + r;
+    if (q > q_count - 1) q = q_count - 1;  // tail rows re-read the last slab; their sums are dropped
+    row[r] = packed + (size_t)q * L;
+  }
+  double acc[J_ROWS];
+#pragma unroll
+  for (int r = 0; r < J_ROWS; ++r) acc[r] = 0.0;
+
+  long long i = start + 2 * threadIdx.x;
+  // two steps per trip: 16 independent 128-bit tensor loads in flight per thread
+  for (; i + J_STEP < end; i += 2 * J_STEP) {
+    const double2 w0 = *reinterpret_cast<const double2 *>(w + i);
+    const double2 w1 = *reinterpret_cast<const double2 *>(w + i + J_STEP);
+    double2 v0[J_ROWS], v1[J_ROWS];
+#pragma unroll
+    for (int r = 0; r < J_ROWS; ++r) v0[r] = ld_stream_f64x2(row[r] + i);
+#pragma unroll
+    for (int r = 0; r < J_ROWS; ++r) v1[r] = ld_stream_f64x2(row[r] + i + J_STEP);
+#pragma unroll
+    for (int r = 0; r < J_ROWS; ++r) {
+      acc[r] = fma(v0[r].x, w0.x, acc[r]);
+      acc[r] = fma(v0[r].y, w0.y, acc[r]);
+      acc[r] = fma(v1[r].x, w1.x, acc[r]);
+      acc[r] = fma(v1[r].y, w1.y, acc[r]);
+    }
+  }
+  if (i < end) {
+    const double2 w0 = *reinterpret_cast<const double2 *>(w + i);
+    double2 v0[J_ROWS];
+#pragma unroll
+    for (int r = 0; r < J_ROWS; ++r) v0[r] = ld_stream_f64x2(row[r] + i);
+#pragma unroll
+    for (int r = 0; r < J_ROWS; ++r) {
+      acc[r] = fma(v0[r].x, w0.x, acc[r]);
+      acc[r] = fma(v0[r].y, w0.y, acc[r]);
+    }
+  }
+
+  __shared__ double red[J_THREADS / 32][J_ROWS];
+#pragma unroll
+  for (int r = 0; r < J_ROWS; ++r) {
+    double s = acc[r];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][r] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < J_ROWS && q0 + threadIdx.x < q_count) {
+    double s = 0.0;
+#pragma unroll
+    for (int wp = 0; wp < J_THREADS / 32; ++wp) s += red[wp][threadIdx.x];
+    gamma_partial[(size_t)seg * q_count + q0 + threadIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) j_gamma_reduce_kernel(const double *__restrict__ gamma_partial,
+                                                             int n_seg, int q_count,
+                                                             double *__restrict__ gamma) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= q_count) return;
+  double s = 0.0;
+  for (int seg = 0; seg < n_seg; ++seg) s += gamma_partial[(size_t)seg * q_count + q];
+  gamma[q] = s;
+}
+
+constexpr int J2_QCHUNK = 1024;
+
+__global__ void __launch_bounds__(J_THREADS) j_accumulate_kernel(const double *__restrict__ packed, long long L,
+                                                                 int q_count, const double *__restrict__ gamma,
+                                                                 int n_slices, double *__restrict__ jpart) {
+  __shared__ double g_s[J2_QCHUNK];
+  const int slice = blockIdx.y;
+  const int qa = (int)((long long)slice * q_count / n_slices);
+  const int qb = (int)((long long)(slice + 1) * q_count / n_slices);
+  const long long col = (long long)blockIdx.x * J_STEP + 2 * threadIdx.x;
+  const bool live = col < L;
+  const double *base = packed + (live ? col : 0);
+  double ax = 0.0, ay = 0.0;
+
+  for (int qc = qa; qc < qb; qc += J2_QCHUNK) {
+    const int cnt = qb - qc < J2_QCHUNK ? qb - qc : J2_QCHUNK;
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt; t += J_THREADS) g_s[t] = gamma[qc + t];
+    __syncthreads();
+    if (live) {
+      int t = 0;
+      for (; t + 8 <= cnt; t += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ld_stream_f64x2(base + (size_t)(qc + t + u) * L);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double g = g_s[t + u];
+          ax = fma(g, v[u].x, ax);
+          ay = fma(g, v[u].y, ay);
+        }
+      }
+      for (; t < cnt; ++t) {
+        const double2 v = ld_stream_f64x2(base + (size_t)(qc + t) * L);
+        const double g = g_s[t];
+        ax = fma(g, v.x, ax);
+        ay = fma(g, v.y, ay);
+      }
+    }
+  }
+  if (live) *reinterpret_cast<double2 *>(jpart + (size_t)slice * L + col) = make_double2(ax, ay);
+}
+
+JPlan plan_j(int n, int q_count) {
+  JPlan p;
+  const long long L = packed_row_len(n);
+  const int target = 148 * 8;
+  const int nqblk = (q_count + J_ROWS - 1) / J_ROWS;
+  long long max_seg = L / 4096;
+  if (max_seg < 1) max_seg = 1;
+  long long ns = (target + nqblk - 1) / (nqblk > 0 ? nqblk : 1);
+  if (ns > max_seg) ns = max_seg;
+  if (ns < 1) ns = 1;
+  p.n_seg = (int)ns;
+  const long long ncolblk = (L + J_STEP - 1) / J_STEP;
+  long long sl = (target + ncolblk - 1) / ncolblk;
+  long long max_sl = q_count / 64;
+  if (max_sl < 1) max_sl = 1;
+  if (sl > max_sl) sl = max_sl;
+  if (sl < 1) sl = 1;
+  p.n_slices = (int)sl;
+  p.gamma_partial_elems = (size_t)p.n_seg * (size_t)(q_count > 0 ? q_count : 1);
+  p.j_partial_elems = (size_t)p.n_slices * (size_t)L;
+  return p;
+}
+
+void launch_j_gamma(const double *d_packed, long long L, int q_count, const double *d_w, const JPlan &plan,
+                    double *d_gamma_partial, double *d_gamma, cudaStream_t s) {
+  long long seg_len = (L + plan.n_seg - 1) / plan.n_seg;
+  seg_len = (seg_len + J_STEP - 1) / J_STEP * J_STEP;
+  const int nqblk = (q_count + J_ROWS - 1) / J_ROWS;
+  for (int b0 = 0; b0 < nqblk; b0 += 65535) {
+    const int nb = nqblk - b0 < 65535 ? nqblk - b0 : 65535;
+    dim3 grid((unsigned)plan.n_seg, (unsigned)nb);
+    j_gamma_kernel<<<grid, J_THREADS, 0, s>>>(d_packed, L, q_count, d_w, seg_len, b0, d_gamma_partial);
+  }
+  j_gamma_reduce_kernel<<<(q_count + 255) / 256, 256, 0, s>>>(d_gamma_partial, plan.n_seg, q_count, d_gamma);
+}
+
+void launch_j_accumulate(const double *d_packed, long long L, int q_count, const double *d_gamma,
+                         const JPlan &plan, double *d_jpart, cudaStream_t s) {
+  const long long ncolblk = (L + J_STEP - 1) / J_STEP;
+  dim3 grid((unsigned)ncolblk, (unsigned)plan.n_slices);
+  j_accumulate_kernel<<<grid, J_THREADS, 0, s>>>(d_packed, L, q_count, d_gamma, plan.n_slices, d_jpart);
+}
+
+}  // namespace mqcb200

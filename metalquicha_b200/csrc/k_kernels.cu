@@ -1,0 +1,383 @@
+// k_kernels.cu -- the exchange half of build_fock_df on the FP64 tensor pipe.
+//
+//   half-transform   X_Q = B_Q . C_occ                 (reference rhf.f90:1636)
+//   accumulation     K  += X_Q . X_Q^T                 (reference rhf.f90:1637)
+//
+// tcgen05/TMEM have no FP64 kind, so the sm_100a tensor path for this contraction
+// is DMMA.8x8x4 (mma.sync.m8n8k4.f64); cuBLAS's own DGEMM on B200 is the same
+// instruction (profiles/r01_ubench.md).  What is Blackwell-specific here is the
+// feeding: operands live in HBM already in DMMA fragment order, so every pipeline
+// stage is a handful of 1-D bulk-TMA copies (cp.async.bulk -> SASS UBLKCP) landing
+// on an mbarrier, and every fragment a warp needs is 256 contiguous, bank-conflict-
+// free bytes of shared memory.  One producer warp drives the TMA ring; eight
+// consumer warps (4 along M x 2 along N) issue DMMA.
+//
+// Half-transform: the M dimension is the flattened (Q, tile-row) index, so a CTA's
+// eight 16-row slots may straddle two auxiliary functions and there is no padding
+// waste along M.  Slot s at k-chunk kc needs the 16x16 tile B_Q[tr_s, kc]; it is the
+// stored tile (max, min) and is read transposed out of shared memory when
+// tr_s < kc (the packed tensor holds each off-diagonal tile once).
+//
+// Accumulation: SYRK over 128x128 lower-triangular tiles of K with the (Q, i)
+// contraction index split across CTAs; partial tiles are written (or added to, on
+// later Q-chunks) in a fixed order -- no floating-point atomics.
+#include "common.cuh"
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace mqcb200 {
+
+constexpr int K_CONSUMER_WARPS = 8;
+// Eight consumer warps (two warpgroups) + one producer warpgroup of which only warp 8
+// works.  Three warps share each SM sub-partition's 16K registers, so the launch
+// allocation is capped at 168/thread; the producer warpgroup hands its share back
+// (setmaxnreg.dec) and the consumers grow to 232 (setmaxnreg.inc): 2*232 + 40 <= 512.
+constexpr int K_THREADS = (K_CONSUMER_WARPS + 4) * 32;
+constexpr int K_PRODUCER_REGS = 40;
+constexpr int K_CONSUMER_REGS = 232;
+
+__device__ __forceinline__ void reg_dealloc_producer() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K_PRODUCER_REGS));
+}
+__device__ __forceinline__ void reg_alloc_consumer() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K_CONSUMER_REGS));
+}
+constexpr int K_SLOTS = 8;                               // 16-row slots per CTA (BM = 128)
+
+// ------------------------------------------------------------------------------------
+// Half-transform
+// ------------------------------------------------------------------------------------
+template <int NB>
+struct HalfCfg {
+  static constexpr int kStages = 4;
+  static constexpr int kAElems = K_SLOTS * TILE_ELEMS;   // 2048 doubles = 16 KiB
+  static constexpr int kBElems = NB * 256;               // 2*NB i-blocks * 4 k-subs * 32
+  static constexpr int kStageElems = kAElems + kBElems;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageElems * sizeof(double) + 2 * kStages * sizeof(uint64_t);
+};
+
+template <int NB>
+__global__ void __launch_bounds__(K_THREADS, 1)
+k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, int q_count,
+                        const double *__restrict__ ctf, int nib, double *__restrict__ x, int nkc, int nmb) {
+  using Cfg = HalfCfg<NB>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *stage_base = reinterpret_cast<double *>(smem_raw);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)Cfg::kStages * Cfg::kStageElems * sizeof(double));
+  uint64_t *empty_bar = full_bar + Cfg::kStages;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total_rows = (long long)q_count * nt;        // flattened (Q, tile-row)
+  const long long f0 = (long long)blockIdx.x * K_SLOTS;
+  const int ib0 = blockIdx.y * (2 * NB);                        // first 8-wide i-block of this N tile
+
+  // Zero the A regions once: slots past the end of the tensor are never filled by TMA.
+  for (int e = threadIdx.x; e < Cfg::kStages * Cfg::kStageElems; e += K_THREADS) stage_base[e] = 0.0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], K_CONSUMER_WARPS);
+    }
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  if (warp >= K_CONSUMER_WARPS) {
+    reg_dealloc_producer();
+    if (warp != K_CONSUMER_WARPS) return;
+    // ===== TMA producer warp: lanes 0..7 own one slot each, lane 8 owns the C operand =====
+    long long f = f0 + lane;
+    const bool valid = lane < K_SLOTS && f < total_rows;
+    int q = 0, tr = 0;
+    if (valid) { q = (int)(f / nt); tr = (int)(f % nt); }
+    const double *row = packed + (size_t)q * L;
+    int n_valid = 0;
+    for (int s = 0; s < K_SLOTS; ++s) n_valid += (f0 + s < total_rows) ? 1 : 0;
+    const uint32_t stage_bytes = (uint32_t)(n_valid * TILE_ELEMS + Cfg::kBElems) * sizeof(double);
+    for (int kc = 0; kc < nt; ++kc) {
+      const int st = kc % Cfg::kStages;
+      const uint32_t ph = (kc / Cfg::kStages) & 1;
+      mbar_wait(&empty_bar[st], ph ^ 1);
+      double *a_s = stage_base + (size_t)st * Cfg::kStageElems;
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
+      __syncwarp();
+      if (valid) {
+        const int a = tr > kc ? tr : kc, b = tr > kc ? kc : tr;
+        tma_load_1d(a_s + lane * TILE_ELEMS, row + (size_t)tile_index(a, b, nt) * TILE_ELEMS,
+                    TILE_ELEMS * sizeof(double), &full_bar[st]);
+      } else if (lane == K_SLOTS) {
+        tma_load_1d(a_s + Cfg::kAElems, ctf + ((size_t)kc * nib + ib0) * 128, Cfg::kBElems * sizeof(double),
+                    &full_bar[st]);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  reg_alloc_consumer();
+  const int wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  // the two 16-row slots of this warp
+  int tr_s[2], q_s[2];
+  bool ok_s[2];
+#pragma unroll
+  for (int sl = 0; sl < 2; ++sl) {
+    const long long f = f0 + 2 * wm + sl;
+    ok_s[sl] = f < total_rows;
+    q_s[sl] = ok_s[sl] ? (int)(f / nt) : 0;
+    tr_s[sl] = ok_s[sl] ? (int)(f % nt) : 0;
+  }
+  const int lane_direct = lane;                                // (g*4 + t)
+  const int lane_transp = ((g >> 2) << 5) + (t << 2) + (g & 3);
+
+  double acc[4][NB][2];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
+
+  for (int kc = 0; kc < nt; ++kc) {
+    const int st = kc % Cfg::kStages;
+    const uint32_t ph = (kc / Cfg::kStages) & 1;
+    mbar_wait(&full_bar[st], ph);
+    const double *a_s = stage_base + (size_t)st * Cfg::kStageElems + (2 * wm) * TILE_ELEMS;
+    const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + Cfg::kAElems + (wn * NB) * 128;
+    const bool tp0 = tr_s[0] < kc, tp1 = tr_s[1] < kc;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      double a[4], b[NB];
+      // direct:     ((rh*4 + ks)*32 + lane)
+      // transposed: (((ks>>1)*4 + 2*rh)*32 + (ks&1)*16 + lane_transp)
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const bool tp = sl ? tp1 : tp0;
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          const int off_d = (rh * 4 + ks) * 32 + lane_direct;
+          const int off_t = (((ks >> 1) * 4 + 2 * rh) * 32) + (ks & 1) * 16 + lane_transp;
+          a[sl * 2 + rh] = a_s[sl * TILE_ELEMS + (tp ? off_t : off_d)];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) dmma884(acc[m][j][0], acc[m][j][1], a[m], b[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);
+  }
+
+  // epilogue: X[q][kc_out][mb][ks_out][g*4 + t_out], two adjacent i per thread (16-byte stores)
+#pragma unroll
+  for (int sl = 0; sl < 2; ++sl) {
+    if (!ok_s[sl]) continue;
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      const int mb = 2 * tr_s[sl] + rh;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int i0 = (ib0 + wn * NB + j) * 8;                 // first i of this n8 block
+        const int kc_out = i0 >> 4;
+        const int ks_out = ((i0 & 15) >> 2) + (t >> 1);
+        const size_t off = (((size_t)q_s[sl] * nkc + kc_out) * nmb + mb) * 128 + ks_out * 32 + g * 4 + 2 * (t & 1);
+        *reinterpret_cast<double2 *>(x + off) = make_double2(acc[sl * 2 + rh][j][0], acc[sl * 2 + rh][j][1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Accumulation (SYRK)
+// ------------------------------------------------------------------------------------
+struct SyrkCfg {
+  static constexpr int kStages = 4;
+  static constexpr int kPanelElems = 16 * 128;            // 16 m-blocks * (4 k-subs * 32) = 16 KiB
+  static constexpr int kStageElems = 2 * kPanelElems;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageElems * sizeof(double) + 2 * kStages * sizeof(uint64_t);
+};
+
+__global__ void __launch_bounds__(K_THREADS, 1)
+k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count, int n_ktiles, int n_splits,
+                    double *__restrict__ kpart, int accumulate) {
+  using Cfg = SyrkCfg;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *stage_base = reinterpret_cast<double *>(smem_raw);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)Cfg::kStages * Cfg::kStageElems * sizeof(double));
+  uint64_t *empty_bar = full_bar + Cfg::kStages;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x % n_ktiles, split = blockIdx.x / n_ktiles;
+  int mp = 0;
+  while ((mp + 1) * (mp + 2) / 2 <= tile) ++mp;
+  const int np = tile - mp * (mp + 1) / 2;
+  const bool diag = mp == np;
+  const int qa = (int)((long long)split * q_count / n_splits);
+  const int qb = (int)((long long)(split + 1) * q_count / n_splits);
+  const int n_steps = (qb - qa) * nkc;
+  const int valid_a = nmb - 16 * mp < 16 ? nmb - 16 * mp : 16;   // 8-row blocks present in each panel
+  const int valid_b = nmb - 16 * np < 16 ? nmb - 16 * np : 16;
+
+  for (int e = threadIdx.x; e < Cfg::kStages * Cfg::kStageElems; e += K_THREADS) stage_base[e] = 0.0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], K_CONSUMER_WARPS);
+    }
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  if (warp >= K_CONSUMER_WARPS) {
+    reg_dealloc_producer();
+    if (warp == K_CONSUMER_WARPS && lane == 0) {
+      const uint32_t bytes_a = (uint32_t)valid_a * 128 * sizeof(double);
+      const uint32_t bytes_b = diag ? 0u : (uint32_t)valid_b * 128 * sizeof(double);
+      for (int step = 0; step < n_steps; ++step) {
+        const int st = step % Cfg::kStages;
+        const uint32_t ph = (step / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        double *a_s = stage_base + (size_t)st * Cfg::kStageElems;
+        const size_t blk = ((size_t)(qa + step / nkc) * nkc + (step % nkc)) * nmb;
+        mbar_arrive_expect_tx(&full_bar[st], bytes_a + bytes_b);
+        tma_load_1d(a_s, x + (blk + 16 * mp) * 128, bytes_a, &full_bar[st]);
+        if (!diag) tma_load_1d(a_s + Cfg::kPanelElems, x + (blk + 16 * np) * 128, bytes_b, &full_bar[st]);
+      }
+    }
+    return;
+  }
+
+  reg_alloc_consumer();
+  const int wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][8][2];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
+
+  for (int step = 0; step < n_steps; ++step) {
+    const int st = step % Cfg::kStages;
+    const uint32_t ph = (step / Cfg::kStages) & 1;
+    mbar_wait(&full_bar[st], ph);
+    const double *a_s = stage_base + (size_t)st * Cfg::kStageElems + (4 * wm) * 128;
+    const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + (diag ? 0 : Cfg::kPanelElems) + (8 * wn) * 128;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      double a[4], b[8];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) a[m] = a_s[(m * 4 + ks) * 32 + lane];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma884(acc[m][j][0], acc[m][j][1], a[m], b[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);
+  }
+
+  double *out = kpart + (((size_t)split * n_ktiles + tile) << 14);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int r = 32 * wm + 8 * m + g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = 64 * wn + 8 * j + 2 * t;
+      double2 *p = reinterpret_cast<double2 *>(out + r * 128 + c);
+      double2 v = make_double2(acc[m][j][0], acc[m][j][1]);
+      if (accumulate) { const double2 o = *p; v.x += o.x; v.y += o.y; }
+      *p = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// planning + launch
+// ------------------------------------------------------------------------------------
+KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm_count) {
+  KPlan p;
+  const int nt = num_tiles(n);
+  const int op16 = ((n_occ > 0 ? n_occ : 1) + 15) / 16 * 16;
+  p.n_ntiles = (op16 + 127) / 128;
+  int bn = (op16 + p.n_ntiles - 1) / p.n_ntiles;
+  bn = (bn + 15) / 16 * 16;
+  p.nb = bn / 16;
+  p.nib = p.n_ntiles * 2 * p.nb;
+  p.nkc = p.nib / 2;
+  p.nmb = 2 * nt;
+  p.n_panels = (n + 127) / 128;
+  p.n_ktiles = p.n_panels * (p.n_panels + 1) / 2;
+  p.x_elems_per_q = (size_t)p.nkc * p.nmb * 128;
+  size_t qc = workspace_limit_bytes / (p.x_elems_per_q * sizeof(double));
+  if (qc < 1) qc = 1;
+  if (qc > (size_t)(q_count > 0 ? q_count : 1)) qc = (size_t)(q_count > 0 ? q_count : 1);
+  p.q_chunk = (int)qc;
+  // split of the contraction range: fill the machine with whole waves of one CTA per SM
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 64; ++s) {
+    if (s > p.q_chunk) break;
+    const long long units = (long long)s * p.n_ktiles;
+    const long long waves = (units + sm_count - 1) / sm_count;
+    const double eff = (double)units / (double)(waves * sm_count);
+    const long long steps = (long long)(p.q_chunk / s) * p.nkc;
+    if (s > 1 && steps < 64) break;
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  p.n_splits = best;
+  p.kpart_elems = ((size_t)p.n_splits * p.n_ktiles) << 14;
+  return p;
+}
+
+template <int NB>
+static void launch_half_nb(const double *d_packed, long long L, int n, int q_count, const double *d_ctf,
+                           const KPlan &plan, double *d_x, cudaStream_t s) {
+  const int nt = num_tiles(n);
+  const long long rows = (long long)q_count * nt;
+  dim3 grid((unsigned)((rows + K_SLOTS - 1) / K_SLOTS), (unsigned)plan.n_ntiles);
+  k_half_transform_kernel<NB><<<grid, K_THREADS, HalfCfg<NB>::kSmemBytes, s>>>(d_packed, L, nt, q_count, d_ctf,
+                                                                             plan.nib, d_x, plan.nkc, plan.nmb);
+}
+
+void launch_k_half_transform(const double *d_packed, long long L, int n, int q_count, const double *d_ctf,
+                             const KPlan &plan, double *d_x, cudaStream_t s) {
+  switch (plan.nb) {
+    case 1: launch_half_nb<1>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
+    case 2: launch_half_nb<2>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
+    case 3: launch_half_nb<3>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
+    case 4: launch_half_nb<4>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
+    case 5: launch_half_nb<5>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
+    case 6: launch_half_nb<6>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
+    case 7: launch_half_nb<7>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
+    default: launch_half_nb<8>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
+  }
+}
+
+void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, double *d_kpart, int accumulate,
+                         cudaStream_t s) {
+  // A short last chunk still touches every (split, tile) partial -- splits with an empty
+  // auxiliary range write (or add) zeros -- so the fixed-order sum in finalize is defined.
+  const int splits = plan.n_splits;
+  k_accumulate_kernel<<<(unsigned)(splits * plan.n_ktiles), K_THREADS, SyrkCfg::kSmemBytes, s>>>(
+      d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, d_kpart, accumulate);
+}
+
+template <int NB>
+static void configure_half() {
+  cudaFuncSetAttribute(k_half_transform_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)HalfCfg<NB>::kSmemBytes);
+}
+
+void configure_kernels() {
+  configure_half<1>(); configure_half<2>(); configure_half<3>(); configure_half<4>();
+  configure_half<5>(); configure_half<6>(); configure_half<7>(); configure_half<8>();
+  cudaFuncSetAttribute(k_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::kSmemBytes);
+}
+
+}  // namespace mqcb200

@@ -1,0 +1,67 @@
+// kernels.cuh -- host-callable launchers of every CUDA kernel of the engine.
+// Implementations: prep_kernels.cu (layout conversion, assembly),
+// j_kernels.cu (Coulomb, HBM-bound), k_kernels.cu (exchange, FP64 DMMA).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mqcb200 {
+
+// ---- layout / preparation -------------------------------------------------
+// Full-square slabs (q_count of them, each n*n column-major) -> packed rows.
+void launch_pack_tensor(const double *d_full, int n, int q_count, double *d_packed, cudaStream_t s);
+// Counter-based synthetic tensor written directly in packed form.
+void launch_synth_tensor(double *d_packed, int n, int q_global_begin, int q_count, uint64_t seed,
+                         double scale, cudaStream_t s);
+// w[L]: the density in packed order with the off-diagonal weight folded in.
+void launch_pack_density(const double *d_density, int n, double *d_w, cudaStream_t s);
+// C(n x n_occ, ld) -> fragment-ordered, zero-padded [nt][nib][4][32] operand.
+void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib, double *d_ctf,
+                       cudaStream_t s);
+// Sum the J / K partial buffers in fixed order and unpack to full n x n matrices.
+// Either output may be null.  k_factor multiplies K (2 for RHF, 1 per spin).
+void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits,
+                        int n, double k_factor, double *d_j, double *d_k, cudaStream_t s);
+// F = H + jf*J - kf*K  (any of J/K may be null == zero).
+void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf,
+                          int n, double *d_fock, cudaStream_t s);
+// e = 1/2 sum D (H + F), deterministic single-block reduction into d_out[0].
+void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n,
+                   double *d_out, cudaStream_t s);
+
+// ---- J: two passes over the packed tensor -----------------------------------
+struct JPlan {
+  int n_seg;      // pass 1: segments of a packed row
+  int n_slices;   // pass 2: slices of the auxiliary range
+  size_t gamma_partial_elems;  // n_seg * q_count
+  size_t j_partial_elems;      // n_slices * L
+};
+JPlan plan_j(int n, int q_count);
+void launch_j_gamma(const double *d_packed, long long L, int q_count, const double *d_w,
+                    const JPlan &plan, double *d_gamma_partial, double *d_gamma, cudaStream_t s);
+void launch_j_accumulate(const double *d_packed, long long L, int q_count, const double *d_gamma,
+                         const JPlan &plan, double *d_jpart, cudaStream_t s);
+
+// ---- K: half-transform + symmetric accumulation on the FP64 tensor pipe -----
+struct KPlan {
+  int nb;          // n8-blocks per warp in the half-transform (BN = 16*nb)
+  int n_ntiles;    // N tiles of the half-transform
+  int nib;         // padded occupied count / 8   (= n_ntiles * 2 * nb)
+  int nkc;         // padded occupied count / 16
+  int nmb;         // 8-row blocks of X per (q, kc): 2*nt
+  int n_panels;    // 128-row panels of K
+  int n_ktiles;    // lower-triangular 128x128 tiles of K
+  int n_splits;    // split of the auxiliary range in the accumulation
+  int q_chunk;     // auxiliary functions per half-transform launch
+  size_t x_elems_per_q;     // doubles of X per auxiliary function
+  size_t kpart_elems;       // n_splits * n_ktiles * 128*128
+};
+KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm_count);
+void launch_k_half_transform(const double *d_packed, long long L, int n, int q_count,
+                             const double *d_ctf, const KPlan &plan, double *d_x, cudaStream_t s);
+void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, double *d_kpart,
+                         int accumulate, cudaStream_t s);
+// One-time opt-in to large dynamic shared memory for the K kernels.
+void configure_kernels();
+
+}  // namespace mqcb200

@@ -1,0 +1,204 @@
+// prep_kernels.cu -- layout conversion and Fock assembly kernels (all O(n^2) or a
+// single pass over the tensor at set-up time; none is on the per-build critical path
+// except the O(n^2) ones).
+#include "common.cuh"
+#include "kernels.cuh"
+#include "synth.cuh"
+
+namespace mqcb200 {
+
+// tile id (column-major lower triangle) -> (tr, tc)
+__device__ __forceinline__ void tile_coords(int tile, int nt, int &tr, int &tc) {
+  // column tc starts at off(tc) = tc*nt - tc*(tc-1)/2; find the largest tc with off(tc) <= tile
+  int c = 0, off = 0;
+  // closed form via the quadratic, then a correction step for rounding
+  const double b = 2.0 * nt + 1.0;
+  c = (int)((b - sqrt(b * b - 8.0 * (double)tile)) * 0.5);
+  if (c < 0) c = 0;
+  if (c > nt - 1) c = nt - 1;
+  off = c * nt - (c * (c - 1)) / 2;
+  while (off > tile) { --c; off = c * nt - (c * (c - 1)) / 2; }
+  while (c + 1 < nt && (c + 1) * nt - ((c + 1) * c) / 2 <= tile) { ++c; off = c * nt - (c * (c - 1)) / 2; }
+  tc = c;
+  tr = tc + (tile - off);
+}
+
+// One CTA (256 threads) per (tile, q): thread -> element (r = tid%16, c = tid/16).
+__global__ void __launch_bounds__(256) pack_tensor_kernel(const double *__restrict__ full, int n, int nt,
+                                                          long long L, double *__restrict__ packed) {
+  int tr, tc;
+  tile_coords(blockIdx.x, nt, tr, tc);
+  const int q = blockIdx.y;
+  const int r = threadIdx.x & 15, c = threadIdx.x >> 4;
+  int mu = tr * TILE + r, nu = tc * TILE + c;
+  double v = 0.0;
+  if (mu < n && nu < n) {
+    if (mu < nu) { int t = mu; mu = nu; nu = t; }  // diagonal tile: mirror the lower triangle
+    v = full[(size_t)q * n * n + (size_t)mu + (size_t)n * nu];
+  }
+  packed[(size_t)q * L + (size_t)blockIdx.x * TILE_ELEMS + in_tile_offset(r, c)] = v;
+}
+
+__global__ void __launch_bounds__(256) synth_tensor_kernel(double *__restrict__ packed, int n, int nt,
+                                                           long long L, int q_global_begin, uint64_t seed,
+                                                           double inv_width, double scale) {
+  int tr, tc;
+  tile_coords(blockIdx.x, nt, tr, tc);
+  const int q = blockIdx.y;
+  // threads walk the tile in storage order so the 2 KiB store is fully coalesced
+  const int o = threadIdx.x;
+  const int f = o >> 5, rr = (o & 31) >> 2, cc = o & 3;
+  const int r = ((f >> 2) << 3) + rr, c = ((f & 3) << 2) + cc;
+  int mu = tr * TILE + r, nu = tc * TILE + c;
+  double v = 0.0;
+  if (mu < n && nu < n) {
+    if (mu < nu) { int t = mu; mu = nu; nu = t; }
+    v = synth_value(seed, (uint32_t)(q_global_begin + q), (uint32_t)mu, (uint32_t)nu, inv_width, scale);
+  }
+  packed[(size_t)q * L + (size_t)blockIdx.x * TILE_ELEMS + o] = v;
+}
+
+__global__ void __launch_bounds__(256) pack_density_kernel(const double *__restrict__ d, int n, int nt,
+                                                           double *__restrict__ w) {
+  int tr, tc;
+  tile_coords(blockIdx.x, nt, tr, tc);
+  const int r = threadIdx.x & 15, c = threadIdx.x >> 4;
+  const int mu = tr * TILE + r, nu = tc * TILE + c;
+  double v = 0.0;
+  if (mu < n && nu < n) {
+    v = d[(size_t)mu + (size_t)n * nu];
+    if (tr != tc) v += d[(size_t)nu + (size_t)n * mu];  // both triangles of an off-diagonal tile
+  }
+  w[(size_t)blockIdx.x * TILE_ELEMS + in_tile_offset(r, c)] = v;
+}
+
+// ctf[((kc*nib + ib)*4 + ks)*32 + g*4 + t] = C[nu = 16kc + 4ks + t][i = 8ib + g]
+__global__ void __launch_bounds__(256) pack_coeff_kernel(const double *__restrict__ coeff, int ldc, int n,
+                                                         int n_occ, int nib, int nt,
+                                                         double *__restrict__ ctf) {
+  const size_t total = (size_t)nt * nib * 128;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int t = e & 3, g = (e >> 2) & 7, ks = (e >> 5) & 3;
+    const size_t blk = e >> 7;
+    const int ib = (int)(blk % nib), kc = (int)(blk / nib);
+    const int nu = kc * 16 + ks * 4 + t, i = ib * 8 + g;
+    ctf[e] = (nu < n && i < n_occ) ? coeff[(size_t)nu + (size_t)ldc * i] : 0.0;
+  }
+}
+
+// One thread per (mu, nu) of the full matrices; the lower-triangle element is the
+// source of both (mu,nu) and (nu,mu), so the outputs are exactly symmetric.
+__global__ void __launch_bounds__(256) finalize_jk_kernel(const double *__restrict__ jpart, int n_jslices,
+                                                          long long L, const double *__restrict__ kpart,
+                                                          int n_ksplits, int n_ktiles, int n, int nt,
+                                                          double k_factor, double *__restrict__ j_out,
+                                                          double *__restrict__ k_out) {
+  const int mu = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int nu = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (mu >= n || nu >= n) return;
+  const int a = mu > nu ? mu : nu, b = mu > nu ? nu : mu;  // a >= b
+  if (j_out) {
+    const size_t off = (size_t)tile_index(a >> 4, b >> 4, nt) * TILE_ELEMS + in_tile_offset(a & 15, b & 15);
+    double s = 0.0;
+    for (int sl = 0; sl < n_jslices; ++sl) s += jpart[(size_t)sl * L + off];
+    j_out[(size_t)mu + (size_t)n * nu] = s;
+  }
+  if (k_out) {
+    const int mp = a >> 7, np = b >> 7;
+    const size_t off = ((size_t)(mp * (mp + 1) / 2 + np) << 14) + ((size_t)(a & 127) << 7) + (b & 127);
+    double s = 0.0;
+    for (int sp = 0; sp < n_ksplits; ++sp) s += kpart[((size_t)sp * n_ktiles << 14) + off];
+    k_out[(size_t)mu + (size_t)n * nu] = k_factor * s;
+  }
+}
+
+__global__ void __launch_bounds__(256) assemble_fock_kernel(const double *__restrict__ h,
+                                                            const double *__restrict__ j,
+                                                            const double *__restrict__ k, double jf, double kf,
+                                                            size_t nn, double *__restrict__ f) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.x * blockDim.x) {
+    double v = h ? h[e] : 0.0;
+    if (j) v += jf * j[e];
+    if (k) v -= kf * k[e];
+    f[e] = v;
+  }
+}
+
+__global__ void __launch_bounds__(1024) energy_kernel(const double *__restrict__ d, const double *__restrict__ h,
+                                                      const double *__restrict__ f, size_t nn,
+                                                      double *__restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (size_t e = threadIdx.x; e < nn; e += blockDim.x) s += d[e] * (h[e] + f[e]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = red[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] = 0.5 * s;
+  }
+}
+
+// ------------------------------- launchers ----------------------------------
+void launch_pack_tensor(const double *d_full, int n, int q_count, double *d_packed, cudaStream_t s) {
+  const int nt = num_tiles(n);
+  const long long L = packed_row_len(n);
+  for (int q0 = 0; q0 < q_count; q0 += 65535) {
+    const int qc = q_count - q0 < 65535 ? q_count - q0 : 65535;
+    dim3 grid((unsigned)num_lower_tiles(nt), (unsigned)qc);
+    pack_tensor_kernel<<<grid, 256, 0, s>>>(d_full + (size_t)q0 * n * n, n, nt, L, d_packed + (size_t)q0 * L);
+  }
+}
+
+void launch_synth_tensor(double *d_packed, int n, int q_global_begin, int q_count, uint64_t seed,
+                         double scale, cudaStream_t s) {
+  const int nt = num_tiles(n);
+  const long long L = packed_row_len(n);
+  const double inv_width = 8.0 / (double)n;
+  for (int q0 = 0; q0 < q_count; q0 += 65535) {
+    const int qc = q_count - q0 < 65535 ? q_count - q0 : 65535;
+    dim3 grid((unsigned)num_lower_tiles(nt), (unsigned)qc);
+    synth_tensor_kernel<<<grid, 256, 0, s>>>(d_packed + (size_t)q0 * L, n, nt, L, q_global_begin + q0, seed,
+                                             inv_width, scale);
+  }
+}
+
+void launch_pack_density(const double *d_density, int n, double *d_w, cudaStream_t s) {
+  const int nt = num_tiles(n);
+  pack_density_kernel<<<(unsigned)num_lower_tiles(nt), 256, 0, s>>>(d_density, n, nt, d_w);
+}
+
+void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib, double *d_ctf,
+                       cudaStream_t s) {
+  const int nt = num_tiles(n);
+  const size_t total = (size_t)nt * nib * 128;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_coeff_kernel<<<blocks, 256, 0, s>>>(d_coeff, ldc, n, n_occ, nib, nt, d_ctf);
+}
+
+void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits, int n,
+                        double k_factor, double *d_j, double *d_k, cudaStream_t s) {
+  const int nt = num_tiles(n);
+  const int np = (n + 127) / 128;
+  dim3 grid((unsigned)nt, (unsigned)nt);
+  finalize_jk_kernel<<<grid, 256, 0, s>>>(d_jpart, n_jslices, packed_row_len(n), d_kpart, n_ksplits,
+                                          np * (np + 1) / 2, n, nt, k_factor, d_j, d_k);
+}
+
+void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf, int n,
+                          double *d_fock, cudaStream_t s) {
+  const size_t nn = (size_t)n * n;
+  unsigned blocks = (unsigned)((nn + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  assemble_fock_kernel<<<blocks, 256, 0, s>>>(d_h, d_j, d_k, jf, kf, nn, d_fock);
+}
+
+void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n, double *d_out,
+                   cudaStream_t s) {
+  energy_kernel<<<1, 1024, 0, s>>>(d_density, d_h, d_fock, (size_t)n * n, d_out);
+}
+
+}  // namespace mqcb200

@@ -1,0 +1,355 @@
+"""Host-side mirror of the reference's Fock-build interface on top of the C ABI.
+
+Method names, argument meaning and error behaviour follow the reference routines
+they stand in for (paths relative to the reference tree):
+
+* ``build_fock_df``       -- backends/libcint/mqc_libcint_rhf.f90:1576-1646
+* ``assemble_fock``       -- DF branch, mqc_libcint_rhf.f90:1089-1106, energy :1207
+* ``atomic_guess_fock``   -- mqc_libcint_rhf.f90:1382-1411 (pseudo-orbitals :1413-1462)
+* ``set_tensor``          -- the ``bmat`` produced by build_df_tensor,
+                             backends/libcint/mqc_libcint_integrals.F90:913-990
+* ``WorkQueue``           -- src/fragmentation/common/mqc_work_queue.f90:10-57
+
+The tensor argument ``b`` of the reference routines is replaced by a resident
+device copy (set once per geometry, exactly as ``run_libcint_rhf`` builds ``bmat``
+once at :486-498).  Every call goes through ``libmqcb200.so``; nothing here
+computes J or K on the host, and a failure in the library raises ``B200Error``
+with the library's message (the reference sets ``error_t`` and returns).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_int, c_int64, c_size_t, c_void_p
+
+import numpy as np
+
+from . import _lib
+
+SLOT_FULL_RANGE = 0
+SLOT_ATTENUATED = 1
+
+OCCUPATION_FLOOR = 1.0e-12   # mqc_libcint_rhf.f90:1438
+
+
+class B200Error(RuntimeError):
+    """A call into libmqcb200.so returned MQCB200_FAIL / MQCB200_BAD_HANDLE."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+def _check(rc: int) -> None:
+    if rc != _lib.MQCB200_OK:
+        raise B200Error(rc, _lib.last_error())
+
+
+def _f64_colmajor(a, name: str) -> np.ndarray:
+    arr = np.asarray(a)
+    if arr.dtype != np.float64:
+        raise TypeError(f"{name} must be float64 (the reference's real(dp)), got {arr.dtype}")
+    if arr.ndim != 2:
+        raise ValueError(f"{name} must be a matrix")
+    if not arr.flags.f_contiguous:
+        if arr.strides[0] == arr.itemsize and arr.strides[1] >= arr.itemsize * arr.shape[0]:
+            return arr                    # a column-major view with a leading dimension
+        arr = np.asfortranarray(arr)
+    return arr
+
+
+def _ptr(arr) -> c_void_p:
+    return c_void_p(arr.ctypes.data) if arr is not None else c_void_p(None)
+
+
+class B200FockEngine:
+    """One engine handle == one GPU (``mod(device_rank, device_count)``)."""
+
+    def __init__(self, device_rank: int = 0):
+        self._lib = _lib.load()
+        self._h = c_void_p(None)
+        _check(self._lib.mqcb200_create(int(device_rank), byref(self._h)))
+        self.n = {}          # slot -> n
+        self.naux = {}       # slot -> (naux_total, q_begin, q_count)
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            rc = self._lib.mqcb200_destroy(self._h)
+            self._h = c_void_p(None)
+            _check(rc)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> c_void_p:
+        return self._h
+
+    def stream(self) -> int:
+        s = c_void_p(None)
+        _check(self._lib.mqcb200_get_stream(self._h, byref(s)))
+        return s.value or 0
+
+    def set_workspace_limit(self, n_bytes: int) -> None:
+        _check(self._lib.mqcb200_set_workspace_limit(self._h, c_size_t(int(n_bytes))))
+
+    # -- the fitted tensor ------------------------------------------------------------
+    def set_tensor(self, b, n: int | None = None, slot: int = SLOT_FULL_RANGE) -> None:
+        """``b`` is the reference's ``bmat(nao*nao, naux)`` (column-major)."""
+        b = _f64_colmajor(b, "b")
+        if not b.flags.f_contiguous:
+            b = np.asfortranarray(b)
+        nn, naux = b.shape
+        if n is None:
+            n = int(round(np.sqrt(nn)))
+        if n * n != nn:
+            raise ValueError("b must have nao*nao rows")
+        _check(self._lib.mqcb200_set_tensor(self._h, slot, n, naux, _ptr(b)))
+        self.n[slot] = n
+        self.naux[slot] = (naux, 0, naux)
+
+    def set_tensor_shard(self, b_shard, n: int, naux_total: int, q_begin: int,
+                         slot: int = SLOT_FULL_RANGE) -> None:
+        """Only auxiliary functions ``[q_begin, q_begin + b_shard.shape[1])`` live here."""
+        b_shard = np.asfortranarray(_f64_colmajor(b_shard, "b_shard"))
+        if b_shard.shape[0] != n * n:
+            raise ValueError("b_shard must have nao*nao rows")
+        q_count = b_shard.shape[1]
+        _check(self._lib.mqcb200_set_tensor_shard(self._h, slot, n, naux_total, q_begin, q_count,
+                                                  _ptr(b_shard)))
+        self.n[slot] = n
+        self.naux[slot] = (naux_total, q_begin, q_count)
+
+    def set_tensor_from_3c(self, three, half, n: int, slot: int = SLOT_FULL_RANGE) -> None:
+        three = np.asfortranarray(_f64_colmajor(three, "three"))
+        half = np.asfortranarray(_f64_colmajor(half, "half"))
+        naux = three.shape[1]
+        _check(self._lib.mqcb200_set_tensor_from_3c(self._h, slot, n, naux, _ptr(three), _ptr(half)))
+        self.n[slot] = n
+        self.naux[slot] = (naux, 0, naux)
+
+    def synth_tensor(self, n: int, naux_total: int, seed: int, scale: float,
+                     q_begin: int = 0, q_count: int | None = None,
+                     slot: int = SLOT_FULL_RANGE) -> None:
+        if q_count is None:
+            q_count = naux_total - q_begin
+        _check(self._lib.mqcb200_synth_tensor(self._h, slot, n, naux_total, q_begin, q_count,
+                                              ctypes.c_uint64(seed), c_double(scale)))
+        self.n[slot] = n
+        self.naux[slot] = (naux_total, q_begin, q_count)
+
+    def clear_tensor(self, slot: int = SLOT_FULL_RANGE) -> None:
+        _check(self._lib.mqcb200_clear_tensor(self._h, slot))
+        self.n.pop(slot, None)
+        self.naux.pop(slot, None)
+
+    def tensor_bytes(self, slot: int = SLOT_FULL_RANGE) -> int:
+        out = c_size_t(0)
+        _check(self._lib.mqcb200_tensor_bytes(self._h, slot, byref(out)))
+        return out.value
+
+    # -- the Fock build -----------------------------------------------------------------
+    def build_fock_df(self, h, density, coeff, n_occ: int, k_scale=None, j_scale=None,
+                      slot: int = SLOT_FULL_RANGE, out=None) -> np.ndarray:
+        """``build_fock_df(h, b, density, coeff, n_occ, fock, k_scale, j_scale)`` with ``b`` resident."""
+        h = _f64_colmajor(h, "h")
+        density = _f64_colmajor(density, "density")
+        n = h.shape[0]
+        if h.shape != (n, n) or density.shape != (n, n):
+            raise ValueError("h and density must both be n x n")
+        coeff, ldc = self._coeff(coeff, n, n_occ)
+        fock = out if out is not None else np.empty((n, n), dtype=np.float64, order="F")
+        _check(self._lib.mqcb200_build_fock(
+            self._h, slot, _ptr(h), _ptr(density), _ptr(coeff), ldc, int(n_occ),
+            c_double(1.0 if k_scale is None else k_scale),
+            c_double(1.0 if j_scale is None else j_scale), _ptr(fock)))
+        return fock
+
+    def build_jk(self, density, coeff, n_occ: int, want_j: bool = True, want_k: bool = True,
+                 slot: int = SLOT_FULL_RANGE):
+        """J and K of ``build_fock_df`` before scaling (K carries the RHF factor 2)."""
+        n = self.n[slot]
+        density = _f64_colmajor(density, "density") if density is not None else None
+        coeff, ldc = self._coeff(coeff, n, n_occ) if want_k else (None, n)
+        j = np.empty((n, n), dtype=np.float64, order="F") if want_j else None
+        k = np.empty((n, n), dtype=np.float64, order="F") if want_k else None
+        _check(self._lib.mqcb200_build_jk(self._h, slot, _ptr(density), _ptr(coeff), ldc, int(n_occ),
+                                          _ptr(j), _ptr(k)))
+        return j, k
+
+    def build_jk_uhf(self, density_total, coeff_a, n_alpha: int, coeff_b, n_beta: int,
+                     slot: int = SLOT_FULL_RANGE):
+        """J[Da+Db], K_alpha, K_beta (no factor 2); K_beta is ``None`` when n_beta == 0."""
+        n = self.n[slot]
+        density_total = _f64_colmajor(density_total, "density_total")
+        ca, lda = self._coeff(coeff_a, n, n_alpha)
+        cb, ldb = self._coeff(coeff_b, n, n_beta) if n_beta > 0 else (None, n)
+        j = np.empty((n, n), dtype=np.float64, order="F")
+        ka = np.empty((n, n), dtype=np.float64, order="F")
+        kb = np.empty((n, n), dtype=np.float64, order="F") if n_beta > 0 else None
+        _check(self._lib.mqcb200_build_jk_uhf(self._h, slot, _ptr(density_total), _ptr(ca), lda,
+                                              int(n_alpha), _ptr(cb), ldb, int(n_beta),
+                                              _ptr(j), _ptr(ka), _ptr(kb)))
+        return j, ka, kb
+
+    def build_fock_df_uhf(self, h, d_alpha, d_beta, coeff_a, n_alpha: int, coeff_b, n_beta: int,
+                          k_scale=None, slot: int = SLOT_FULL_RANGE):
+        """F_sigma = H + J[Da+Db] - k_scale*K[C_sigma]."""
+        h = _f64_colmajor(h, "h")
+        n = h.shape[0]
+        dt = np.asfortranarray(np.asarray(d_alpha) + np.asarray(d_beta))
+        ca, lda = self._coeff(coeff_a, n, n_alpha)
+        cb, ldb = self._coeff(coeff_b, n, n_beta) if n_beta > 0 else (None, n)
+        fa = np.empty((n, n), dtype=np.float64, order="F")
+        fb = np.empty((n, n), dtype=np.float64, order="F")
+        _check(self._lib.mqcb200_build_fock_uhf(self._h, slot, _ptr(h), _ptr(dt), _ptr(ca), lda, int(n_alpha),
+                                                _ptr(cb), ldb, int(n_beta),
+                                                c_double(1.0 if k_scale is None else k_scale),
+                                                _ptr(fa), _ptr(fb)))
+        return fa, fb
+
+    def last_energy(self) -> float:
+        """``electronic_energy(h, fock, density)`` of the last ``build_fock_df`` (rhf.f90:1691-1697)."""
+        e = c_double(0.0)
+        _check(self._lib.mqcb200_last_energy(self._h, byref(e)))
+        return e.value
+
+    def assemble_fock(self, h, density, coeff, n_occ: int, k_scale=None, rs_k_lr=None):
+        """DF branch of ``assemble_fock``: returns ``(fock, e_elec)`` before any V_xc.
+
+        With a tensor on the attenuated slot and ``rs_k_lr`` given, the second pass of a
+        range-separated functional runs with ``h = 0``, ``k_scale = rs_k_lr``, ``j_scale = 0``
+        and is added to the Fock matrix (rhf.f90:1094-1105).
+        """
+        h = _f64_colmajor(h, "h")
+        density = _f64_colmajor(density, "density")
+        fock = self.build_fock_df(h, density, coeff, n_occ, k_scale=k_scale)
+        if rs_k_lr is not None:
+            if SLOT_ATTENUATED not in self.n:
+                raise B200Error(_lib.MQCB200_FAIL, "range-separated pass requested but no attenuated tensor is set")
+            k_lr = self.build_fock_df(np.zeros_like(h), density, coeff, n_occ, k_scale=rs_k_lr,
+                                      j_scale=0.0, slot=SLOT_ATTENUATED)
+            fock = fock + k_lr
+            e_elec = 0.5 * float(np.sum(density * (h + fock)))
+        else:
+            e_elec = self.last_energy()
+        return fock, e_elec
+
+    def atomic_guess_fock(self, h, density) -> np.ndarray:
+        """One build from a guess density through its pseudo-orbitals (rhf.f90:1402-1405)."""
+        pseudo, n_modes = density_pseudo_orbitals(density)
+        return self.build_fock_df(h, density, pseudo, n_modes)
+
+    # -- device-resident variant (torch CUDA tensors, column-major storage) --------------
+    def build_fock_device(self, d_h, d_density, d_coeff, n_occ: int, d_fock, k_scale=1.0,
+                          j_scale=1.0, slot: int = SLOT_FULL_RANGE, sync: bool = True) -> None:
+        """All arguments are CUDA tensors holding column-major matrices (data_ptr is used)."""
+        for t in (d_h, d_density, d_coeff, d_fock):
+            if not t.is_cuda or str(t.dtype) != "torch.float64" or not t.is_contiguous():
+                raise TypeError("device operands must be contiguous float64 CUDA tensors")
+        _check(self._lib.mqcb200_build_fock_device(
+            self._h, slot, c_void_p(d_h.data_ptr()), c_void_p(d_density.data_ptr()),
+            c_void_p(d_coeff.data_ptr()), int(n_occ), c_double(k_scale), c_double(j_scale),
+            c_void_p(d_fock.data_ptr()), 1 if sync else 0))
+
+    # -- multi-GPU --------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        _check(_lib.load().mqcb200_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes) -> None:
+        if len(unique_id) != 128:
+            raise ValueError("the communicator id is 128 bytes")
+        _check(self._lib.mqcb200_comm_init(self._h, n_ranks, rank, unique_id))
+
+    def comm_destroy(self) -> None:
+        _check(self._lib.mqcb200_comm_destroy(self._h))
+
+    # -- instrumentation --------------------------------------------------------------------
+    def set_profiling(self, on: bool) -> None:
+        _check(self._lib.mqcb200_set_profiling(self._h, 1 if on else 0))
+
+    def last_timings(self) -> dict:
+        ms = (c_double * _lib.NUM_TIMERS)()
+        _check(self._lib.mqcb200_last_timings(self._h, ms))
+        return dict(zip(_lib.TIMER_NAMES, list(ms)))
+
+    def last_launches(self) -> int:
+        n = c_int(0)
+        _check(self._lib.mqcb200_last_launches(self._h, byref(n)))
+        return n.value
+
+    # -- helpers ------------------------------------------------------------------------------
+    @staticmethod
+    def _coeff(coeff, n: int, n_occ: int):
+        if n_occ == 0:
+            return None, n
+        coeff = _f64_colmajor(coeff, "coeff")
+        if coeff.shape[0] != n or coeff.shape[1] < n_occ:
+            raise ValueError("coeff must be (n, >= n_occ)")
+        ldc = coeff.strides[1] // coeff.itemsize if coeff.shape[1] > 1 else max(n, coeff.shape[0])
+        return coeff, int(ldc)
+
+
+def density_pseudo_orbitals(density):
+    """Columns c_i with D = 2 sum_i c_i c_i^T  (mqc_libcint_rhf.f90:1413-1462).
+
+    Host-side, as in the reference: one dsyev on the guess density, modes with
+    occupation above 1e-12 kept, ``c_i = v_i*sqrt(w_i/2)``.  Raises the reference's
+    message when nothing is occupied.
+    """
+    density = np.asarray(density, dtype=np.float64)
+    values, vectors = np.linalg.eigh(density, UPLO="U")
+    keep = values > OCCUPATION_FLOOR
+    n_modes = int(np.count_nonzero(keep))
+    if n_modes == 0:
+        raise B200Error(_lib.MQCB200_FAIL, "guess: the guess density carries no occupation")
+    coeff = np.asfortranarray(vectors[:, keep] * np.sqrt(0.5 * values[keep])[None, :])
+    return coeff, n_modes
+
+
+class WorkQueue:
+    """FIFO of int64 fragment ids with the semantics of the reference's ``queue_t``
+    (``queue_init_from_list`` / ``queue_pop`` / ``queue_is_empty`` / ``queue_destroy``)."""
+
+    def __init__(self, ids):
+        self._lib = _lib.load()
+        arr = np.ascontiguousarray(np.asarray(ids, dtype=np.int64))
+        self._q = c_void_p(None)
+        _check(self._lib.mqcb200_queue_create(arr.ctypes.data_as(ctypes.POINTER(c_int64)),
+                                              c_int64(arr.size), byref(self._q)))
+
+    def pop(self):
+        """Returns ``(item_idx, has_item)``; ``(-1, False)`` once drained."""
+        idx = c_int64(0)
+        has = c_int(0)
+        _check(self._lib.mqcb200_queue_pop(self._q, byref(idx), byref(has)))
+        return idx.value, bool(has.value)
+
+    def is_empty(self) -> bool:
+        out = c_int(0)
+        _check(self._lib.mqcb200_queue_is_empty(self._q, byref(out)))
+        return bool(out.value)
+
+    def destroy(self) -> None:
+        if self._q is not None and self._q.value:
+            rc = self._lib.mqcb200_queue_destroy(self._q)
+            self._q = c_void_p(None)
+            _check(rc)
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

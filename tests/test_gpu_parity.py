@@ -1,0 +1,256 @@
+"""Parity of the CUDA engine (through the C ABI) with the CPU oracle.
+
+Tolerances are the ones BASELINE.json's north_star states: J/K/F agree to 1e-10
+max-abs, energies to 1e-9 Eh.  Every test runs on seeded inputs small enough for
+the oracle to finish in seconds; full-size properties live in test_gpu_fullsize.py.
+"""
+import numpy as np
+import pytest
+
+from metalquicha_b200 import B200Error, synth
+from metalquicha_b200.engine import SLOT_ATTENUATED
+from oracle import df_fock_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+TOL_E = 1e-9
+
+
+def _maxabs(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))))
+
+
+# (n, n_occ, naux): the reference's own water cases, the MBE fragment shapes, ragged n
+# (not a multiple of the 16-wide tile or of the 128-wide panel), and occupied counts that
+# exercise every half-transform tile width (n_occ -> NB 1..8 and two N tiles).
+SHAPES = [
+    (24, 5, 116), (24, 5, 139), (48, 10, 227), (72, 15, 340),
+    (19, 5, 19), (1, 1, 3), (17, 3, 7), (33, 16, 40), (100, 17, 50), (130, 33, 64),
+    (145, 48, 70), (200, 50, 96), (129, 65, 33), (160, 81, 40), (136, 97, 24),
+    (150, 113, 20), (257, 128, 12), (140, 130, 10), (144, 144, 9),
+]
+
+
+@pytest.mark.parametrize("n,n_occ,naux", SHAPES)
+def test_build_fock_df_matches_oracle(engine, n, n_occ, naux):
+    b, h, density, coeff = synth.synth_problem(100 + n, n, n_occ, naux)
+    engine.set_tensor(b)
+    fock = engine.build_fock_df(h, density, coeff, n_occ)
+    ref = oracle.build_fock_df(h, b, density, coeff, n_occ)
+    assert _maxabs(fock, ref) <= TOL
+    assert abs(engine.last_energy() - oracle.electronic_energy(h, ref, density)) <= TOL_E
+    assert engine.last_launches() > 0
+
+
+@pytest.mark.parametrize("n,n_occ,naux", [(24, 5, 116), (72, 15, 340), (130, 33, 64), (200, 50, 96)])
+def test_jk_match_oracle(engine, n, n_occ, naux):
+    b, h, density, coeff = synth.synth_problem(7, n, n_occ, naux)
+    engine.set_tensor(b)
+    j, k = engine.build_jk(density, coeff, n_occ)
+    j_ref, k_ref, _ = oracle.jk_df(b, density, coeff, n_occ)
+    assert _maxabs(j, j_ref) <= TOL
+    assert _maxabs(k, k_ref) <= TOL
+    # exact symmetry of the engine's outputs (it mirrors the lower triangle)
+    assert np.array_equal(j, j.T) and np.array_equal(k, k.T)
+    j_only, none_k = engine.build_jk(density, coeff, n_occ, want_k=False)
+    assert none_k is None and np.array_equal(j_only, j)
+    none_j, k_only = engine.build_jk(None, coeff, n_occ, want_j=False)
+    assert none_j is None and np.array_equal(k_only, k)
+
+
+def test_scales_and_attenuated_second_pass(engine):
+    """k_scale / j_scale and the range-separated second call (rhf.f90:1094-1105)."""
+    n, n_occ, naux = 72, 15, 200
+    b, h, density, coeff = synth.synth_problem(11, n, n_occ, naux)
+    b_lr = synth.synth_tensor(12, n, naux)
+    engine.set_tensor(b)
+    engine.set_tensor(b_lr, slot=SLOT_ATTENUATED)
+    f = engine.build_fock_df(h, density, coeff, n_occ, k_scale=0.2)
+    assert _maxabs(f, oracle.build_fock_df(h, b, density, coeff, n_occ, k_scale=0.2)) <= TOL
+    k_lr = engine.build_fock_df(np.zeros_like(h), density, coeff, n_occ, k_scale=0.37, j_scale=0.0,
+                                slot=SLOT_ATTENUATED)
+    assert _maxabs(k_lr, oracle.build_fock_df(np.zeros_like(h), b_lr, density, coeff, n_occ,
+                                              k_scale=0.37, j_scale=0.0)) <= TOL
+    fock, e = engine.assemble_fock(h, density, coeff, n_occ, k_scale=0.2, rs_k_lr=0.37)
+    fock_ref, e_ref = oracle.assemble_fock_df(h, b, density, coeff, n_occ, k_scale=0.2,
+                                              bmat_lr=b_lr, rs_k_lr=0.37)
+    assert _maxabs(fock, fock_ref) <= TOL and abs(e - e_ref) <= TOL_E
+    fock, e = engine.assemble_fock(h, density, coeff, n_occ)
+    fock_ref, e_ref = oracle.assemble_fock_df(h, b, density, coeff, n_occ)
+    assert _maxabs(fock, fock_ref) <= TOL and abs(e - e_ref) <= TOL_E
+    engine.clear_tensor(SLOT_ATTENUATED)
+
+
+def test_coeff_leading_dimension_and_extra_columns(engine):
+    """Only coeff(:, 1:n_occ) is read (rhf.f90:1618); coeff has n_mo >= n_occ columns."""
+    n, n_occ, naux = 50, 9, 40
+    b, h, density, _ = synth.synth_problem(3, n, n_occ, naux)
+    full = synth.synth_orbitals(3, n, n)            # all n "molecular orbitals"
+    engine.set_tensor(b)
+    ref = oracle.build_fock_df(h, b, density, full, n_occ)
+    assert _maxabs(engine.build_fock_df(h, density, full, n_occ), ref) <= TOL
+    padded = np.zeros((n + 6, n), order="F")
+    padded[:n, :] = full
+    view = padded[:n, :]                            # column-major view, ldc = n + 6
+    assert _maxabs(engine.build_fock_df(h, density, view, n_occ), ref) <= TOL
+    assert _maxabs(engine.build_fock_df(h, density, np.ascontiguousarray(full), n_occ), ref) <= TOL
+
+
+def test_pseudo_orbital_guess_build(engine):
+    """atomic_guess_fock: a non-idempotent guess density through its pseudo-orbitals."""
+    n, naux = 60, 80
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((n, 14))
+    occ = rng.uniform(0.1, 2.0, size=14)
+    density = np.asfortranarray((a * occ[None, :]) @ a.T)       # PSD, rank 14, not idempotent
+    h = synth.synth_core_hamiltonian(5, n)
+    b = synth.synth_tensor(5, n, naux)
+    engine.set_tensor(b)
+    fock = engine.atomic_guess_fock(h, density)
+    pseudo, n_modes = oracle.density_pseudo_orbitals(density)
+    assert n_modes == 14
+    assert _maxabs(fock, oracle.build_fock_df(h, b, density, pseudo, n_modes)) <= 1e-9
+    # K through pseudo-orbitals equals the general-density form sum_P B_P D B_P
+    _, k = engine.build_jk(density, pseudo, n_modes)
+    assert _maxabs(k, oracle.fitted_exchange_general(b, density)) <= 1e-9
+    # full-rank guess: n_modes == n (K cost n/n_occ times larger on that one call)
+    d_full = np.asfortranarray(density + 0.01 * np.eye(n))
+    pseudo, n_modes = oracle.density_pseudo_orbitals(d_full)
+    assert n_modes == n
+    assert _maxabs(engine.atomic_guess_fock(h, d_full), oracle.build_fock_df(h, b, d_full, pseudo, n)) <= 1e-9
+
+
+def test_asymmetric_density_is_symmetrised(engine):
+    """The reference sums B_P * D over the full square; a packed engine sees (D + D^T)/2
+    implicitly -- identical because every B_P is symmetric."""
+    n, n_occ, naux = 40, 6, 30
+    b, h, density, coeff = synth.synth_problem(21, n, n_occ, naux)
+    rng = np.random.default_rng(21)
+    d_asym = np.asfortranarray(density + 0.1 * rng.standard_normal((n, n)))
+    engine.set_tensor(b)
+    j, _ = engine.build_jk(d_asym, coeff, n_occ, want_k=False)
+    j_ref, _, _ = oracle.jk_df(b, d_asym, coeff, n_occ)
+    assert _maxabs(j, j_ref) <= TOL
+
+
+def test_two_spin_build(engine):
+    """DF-UHF: J from the total density, K per spin without the factor 2."""
+    n, na, nb_, naux = 66, 9, 8, 120
+    b = synth.synth_tensor(31, n, naux)
+    h = synth.synth_core_hamiltonian(31, n)
+    ca = synth.synth_orbitals(31, n, na)
+    cb = synth.synth_orbitals(32, n, nb_)
+    da, db = oracle.build_density_spin(ca, na), oracle.build_density_spin(cb, nb_)
+    engine.set_tensor(b)
+    j, ka, kb = engine.build_jk_uhf(da + db, ca, na, cb, nb_)
+    j_ref, ka_ref, kb_ref = oracle.jk_df_uhf(b, da + db, ca, na, cb, nb_)
+    assert _maxabs(j, j_ref) <= TOL and _maxabs(ka, ka_ref) <= TOL and _maxabs(kb, kb_ref) <= TOL
+    fa, fb = engine.build_fock_df_uhf(h, da, db, ca, na, cb, nb_, k_scale=0.5)
+    fa_ref, fb_ref = oracle.build_fock_df_uhf(h, b, da, db, ca, na, cb, nb_, k_scale=0.5)
+    assert _maxabs(fa, fa_ref) <= TOL and _maxabs(fb, fb_ref) <= TOL
+    e = oracle.uhf_electronic_energy(h, fa, fb, da, db)
+    assert abs(e - oracle.uhf_electronic_energy(h, fa_ref, fb_ref, da, db)) <= TOL_E
+    # restricted vs two-spin with C_alpha = C_beta: K_rhf = 2 K_sigma, same J
+    _, k_rhf = engine.build_jk(2.0 * da, ca, na)
+    assert _maxabs(k_rhf, 2.0 * ka) <= TOL
+    # empty beta channel is skipped, not zeroed
+    j1, ka1, kb1 = engine.build_jk_uhf(da, ca, na, None, 0)
+    assert kb1 is None and _maxabs(ka1, ka_ref) <= TOL
+    fa1, fb1 = engine.build_fock_df_uhf(h, da, np.zeros_like(da), ca, na, None, 0)
+    fa1_ref, fb1_ref = oracle.build_fock_df_uhf(h, b, da, np.zeros_like(da), ca, na, cb, 0)
+    assert _maxabs(fa1, fa1_ref) <= TOL and _maxabs(fb1, fb1_ref) <= TOL
+
+
+def test_physical_like_tensor_with_dropped_modes(engine):
+    """B = three . metric^(-1/2) with two metric modes below the 1e-10 threshold."""
+    n, n_occ, naux = 24, 5, 30
+    three, metric = synth.synth_physical_like_tensor(1, n, naux, n_null=2)
+    b = np.asfortranarray(oracle.whiten(three, metric))
+    _, h, density, coeff = synth.synth_problem(1, n, n_occ, naux, with_tensor=False)
+    engine.set_tensor(b)
+    fock = engine.build_fock_df(h, density, coeff, n_occ)
+    scale = max(1.0, float(np.max(np.abs(fock))))
+    assert _maxabs(fock, oracle.build_fock_df(h, b, density, coeff, n_occ)) <= TOL * scale
+
+
+def test_device_generator_matches_host_generator(engine):
+    """mqcb200_synth_tensor == synth.synth_tensor bit for bit (checked through a build)."""
+    n, n_occ, naux = 70, 11, 50
+    _, h, density, coeff = synth.synth_problem(9, n, n_occ, naux, with_tensor=False)
+    scale = synth.default_scale(n, naux)
+    b = synth.synth_tensor(1234, n, naux, scale)
+    engine.set_tensor(b)
+    f_host = engine.build_fock_df(h, density, coeff, n_occ)
+    engine.synth_tensor(n, naux, 1234, scale)
+    f_dev = engine.build_fock_df(h, density, coeff, n_occ)
+    assert np.array_equal(f_host, f_dev)
+
+
+def test_repeat_builds_are_bit_identical(engine):
+    """MBE differences fragment energies, so the reference relies on bit-reproducible
+    repeats (backends/cuest/backend/mqc_cuest_context.f90:209-213)."""
+    n, n_occ, naux = 150, 40, 130
+    b, h, density, coeff = synth.synth_problem(77, n, n_occ, naux)
+    engine.set_tensor(b)
+    first = engine.build_fock_df(h, density, coeff, n_occ)
+    for _ in range(3):
+        assert np.array_equal(first, engine.build_fock_df(h, density, coeff, n_occ))
+
+
+def test_small_workspace_chunks_the_auxiliary_range(engine):
+    """A tight scratch limit forces several half-transform/accumulate rounds."""
+    n, n_occ, naux = 90, 20, 300
+    b, h, density, coeff = synth.synth_problem(8, n, n_occ, naux)
+    engine.set_tensor(b)
+    ref = oracle.build_fock_df(h, b, density, coeff, n_occ)
+    engine.set_workspace_limit(1 << 20)       # 1 MiB: a few auxiliary functions per round
+    try:
+        assert _maxabs(engine.build_fock_df(h, density, coeff, n_occ), ref) <= TOL
+    finally:
+        engine.set_workspace_limit(4 << 30)
+    assert _maxabs(engine.build_fock_df(h, density, coeff, n_occ), ref) <= TOL
+
+
+def test_n_occ_zero_and_k_scale_zero(engine):
+    n, naux = 30, 20
+    b, h, density, coeff = synth.synth_problem(4, n, 4, naux)
+    engine.set_tensor(b)
+    j_ref, _, _ = oracle.jk_df(b, density, coeff, 4)
+    assert _maxabs(engine.build_fock_df(h, density, coeff, 0), h + j_ref) <= TOL
+    assert _maxabs(engine.build_fock_df(h, density, coeff, 4, k_scale=0.0), h + j_ref) <= TOL
+    j, k = engine.build_jk(density, coeff, 0)
+    assert _maxabs(j, j_ref) <= TOL and not k.any()
+
+
+def test_sharded_tensor_partial_sums(engine):
+    """A shard holds auxiliary functions [q_begin, q_begin+q_count); partial J/K add up."""
+    n, n_occ, naux = 64, 12, 90
+    b, h, density, coeff = synth.synth_problem(15, n, n_occ, naux)
+    j_ref, k_ref, _ = oracle.jk_df(b, density, coeff, n_occ)
+    j_sum, k_sum = np.zeros((n, n)), np.zeros((n, n))
+    for rank in range(3):
+        q0, qc = synth.shard_range(naux, 3, rank)
+        engine.set_tensor_shard(b[:, q0:q0 + qc], n, naux, q0)
+        j, k = engine.build_jk(density, coeff, n_occ)
+        j_sum += j
+        k_sum += k
+    assert _maxabs(j_sum, j_ref) <= TOL and _maxabs(k_sum, k_ref) <= TOL
+
+
+def test_errors_surface_as_status_and_message(engine):
+    """Refuse, never abort (reference: result%error%set + return)."""
+    from metalquicha_b200 import B200FockEngine
+    with B200FockEngine(0) as fresh:
+        with pytest.raises(B200Error, match="no fitted tensor"):
+            fresh.build_fock_df(np.zeros((4, 4)), np.zeros((4, 4)), np.zeros((4, 2)), 2)
+        with pytest.raises(B200Error, match="slot"):
+            fresh.synth_tensor(8, 4, 1, 1.0, slot=5)
+    n, n_occ, naux = 20, 3, 10
+    b, h, density, coeff = synth.synth_problem(2, n, n_occ, naux)
+    engine.set_tensor(b)
+    with pytest.raises(B200Error, match="negative"):
+        engine.build_fock_df(h, density, coeff, -1)
+    # the engine is still usable after a refused call
+    assert _maxabs(engine.build_fock_df(h, density, coeff, n_occ),
+                   oracle.build_fock_df(h, b, density, coeff, n_occ)) <= TOL

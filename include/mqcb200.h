@@ -147,8 +147,11 @@ int mqcb200_queue_is_empty(void *queue, int *is_empty);
 int mqcb200_queue_destroy(void *queue);
 
 /* ---- instrumentation -------------------------------------------------------
- * Per-phase device times (ms, CUDA events on the engine's stream) of the last
- * build when profiling is on; kernels launched by the last build. */
+ * With profiling on, every phase of every build is bracketed by CUDA events on the
+ * engine's stream.  mqcb200_last_timings synchronises the stream, returns the per-
+ * phase sums (ms) over all builds since the previous call, and clears them -- so a
+ * loop of asynchronous builds can be timed without a host sync per build.
+ * mqcb200_last_launches: kernels launched by the last build. */
 int mqcb200_set_profiling(void *handle, int on);
 int mqcb200_last_timings(void *handle, double ms[MQCB200_NUM_TIMERS]);
 int mqcb200_last_launches(void *handle, int *n_kernels);

@@ -163,17 +163,15 @@ struct Engine {
         return;
       }
   }
-  void reset_timers() {
-    n_spans = 0;
-    for (int i = 0; i < MQCB200_NUM_TIMERS; ++i) last_ms[i] = 0.0;
-    launches = 0;
-  }
+  // Spans accumulate over builds until mqcb200_last_timings collects and clears them, so
+  // a caller can time a whole loop of asynchronous builds without a host sync per build.
   void collect_timers() {
-    if (!profiling) return;
+    for (int i = 0; i < MQCB200_NUM_TIMERS; ++i) last_ms[i] = 0.0;
     for (size_t i = 0; i < n_spans; ++i) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, spans[i].a, spans[i].b) == cudaSuccess) last_ms[spans[i].idx] += ms;
     }
+    n_spans = 0;
   }
 };
 
@@ -281,7 +279,7 @@ static void build(Engine *e, const BuildArgs &a) {
   if (a.want_k && a.n_a > 0 && (!a.coeff_a || a.lda < sl.n)) throw Failure("mqcb200: bad coefficient matrix / leading dimension");
   if (a.want_k && a.two_spin && a.n_b > 0 && (!a.coeff_b || a.ldb < sl.n)) throw Failure("mqcb200: bad beta coefficient matrix / leading dimension");
   e->bind();
-  e->reset_timers();
+  e->launches = 0;
   const int n = sl.n;
   const size_t nn = (size_t)n * n;
   const bool sharded = e->comm != nullptr;
@@ -414,7 +412,6 @@ static void build(Engine *e, const BuildArgs &a) {
   if (a.sync) {
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     if (!a.device_operands && !a.assemble && a.k_a && a.want_k && !do_ka) std::memset(a.k_a, 0, nn * sizeof(double));
-    e->collect_timers();
   }
 }
 
@@ -765,14 +762,19 @@ int mqcb200_queue_destroy(void *queue) {
 int mqcb200_set_profiling(void *handle, int on) {
   GET_ENGINE(handle)
   e->profiling = on != 0;
+  if (!e->profiling) e->n_spans = 0;
   return MQCB200_OK;
 }
 
 int mqcb200_last_timings(void *handle, double ms[MQCB200_NUM_TIMERS]) {
   GET_ENGINE(handle)
   if (!ms) { g_last_error = "mqcb200: null output pointer"; return MQCB200_FAIL; }
+  API_BEGIN
+  e->bind();
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  e->collect_timers();
   for (int i = 0; i < MQCB200_NUM_TIMERS; ++i) ms[i] = e->last_ms[i];
-  return MQCB200_OK;
+  API_END
 }
 
 int mqcb200_last_launches(void *handle, int *n_kernels) {

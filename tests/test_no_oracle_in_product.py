@@ -1,0 +1,27 @@
+"""The product never imports, links or executes anything under oracle/."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_package_and_csrc_do_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "metalquicha_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".f90", "Makefile")):
+                continue
+            text = open(os.path.join(dirpath, f), errors="replace").read()
+            if re.search(r"^\s*(from|import)\s+oracle\b|df_fock_oracle|df_fock_ref|oracle/", text, re.M):
+                offenders.append(os.path.join(dirpath, f))
+    assert offenders == []
+
+
+def test_numpy_is_not_used_for_contractions_in_the_engine_mirror():
+    """engine.py may diagonalise the guess density (as the reference's caller does with
+    dsyev) but must not contract B with anything on the host."""
+    text = open(os.path.join(ROOT, "metalquicha_b200", "engine.py")).read()
+    assert "einsum" not in text and "tensordot" not in text and "matmul" not in text

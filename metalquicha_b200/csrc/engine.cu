@@ -340,8 +340,8 @@ static void build(Engine *e, const BuildArgs &a) {
   }
   e->phase_begin(T_FINAL);
   if (sl.q_count > 0) {
-    launch_finalize_jk(do_j ? e->d_jpart.d() : nullptr, jp.n_slices, do_ka ? e->d_kpart.d() : nullptr, kp.n_splits, n,
-                       kfac, do_j ? d_j : nullptr, do_ka ? d_ka : nullptr, e->stream);
+    launch_finalize_jk(do_j ? e->d_jpart.d() : nullptr, jp.n_slices, do_ka ? e->d_kpart.d() : nullptr, kp.n_splits,
+                       kp.ktile ? kp.ktile : 64, n, kfac, do_j ? d_j : nullptr, do_ka ? d_ka : nullptr, e->stream);
     e->launches += 1;
   } else {
     if (do_j) CUDA_CHECK(cudaMemsetAsync(d_j, 0, nn * sizeof(double), e->stream));
@@ -354,7 +354,7 @@ static void build(Engine *e, const BuildArgs &a) {
       e->d_kpart.ensure(probe.kpart_elems * sizeof(double));  // stream-ordered: finalize above has consumed it
       KPlan kpb{};
       run_k(e, sl, d_cb, ldb, a.n_b, e->d_kpart.d(), kpb);
-      launch_finalize_jk(nullptr, 0, e->d_kpart.d(), kpb.n_splits, n, kfac, nullptr, d_kb, e->stream);
+      launch_finalize_jk(nullptr, 0, e->d_kpart.d(), kpb.n_splits, kpb.ktile, n, kfac, nullptr, d_kb, e->stream);
       e->launches += 1;
     } else {
       CUDA_CHECK(cudaMemsetAsync(d_kb, 0, nn * sizeof(double), e->stream));

@@ -25,6 +25,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace mqcb200 {
 
@@ -39,6 +40,16 @@ constexpr int K_CONSUMER_REGS = 232;
 
 __device__ __forceinline__ void reg_dealloc_producer() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K_PRODUCER_REGS));
+}
+// Consumer-side release of a pipeline stage.  The stage was read through the generic
+// proxy (LDS) and will be overwritten through the async proxy (bulk TMA): without a
+// cross-proxy fence ptxas is free to hoist the mbarrier arrive above the DMMAs that
+// wait for the LDS results, and the TMA refill then races the reads (seen on B200 as
+// run-to-run differences with short pipelines, see profiles/r01_notes.md).
+__device__ __forceinline__ void release_stage(uint64_t *empty_bar, int lane) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty_bar);
 }
 __device__ __forceinline__ void reg_alloc_consumer() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K_CONSUMER_REGS));
@@ -57,10 +68,15 @@ struct HalfCfg {
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageElems * sizeof(double) + 2 * kStages * sizeof(uint64_t);
 };
 
+// Persistent: one CTA per SM walks the (row-group, N-tile) list round-robin.  The TMA
+// ring runs continuously across tile boundaries -- while the consumer warps store one
+// tile's X the producer is already filling stages for the next -- and the consumer
+// warps never synchronise with each other (each owns its accumulators and its rows).
 template <int NB>
 __global__ void __launch_bounds__(K_THREADS, 1)
 k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, int q_count,
-                        const double *__restrict__ ctf, int nib, double *__restrict__ x, int nkc, int nmb) {
+                        const double *__restrict__ ctf, int nib, int n_ntiles, double *__restrict__ x, int nkc,
+                        int nmb) {
   using Cfg = HalfCfg<NB>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stage_base = reinterpret_cast<double *>(smem_raw);
@@ -69,11 +85,9 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total_rows = (long long)q_count * nt;        // flattened (Q, tile-row)
-  const long long f0 = (long long)blockIdx.x * K_SLOTS;
-  const int ib0 = blockIdx.y * (2 * NB);                        // first 8-wide i-block of this N tile
+  const long long n_groups = (total_rows + K_SLOTS - 1) / K_SLOTS;
+  const long long n_work = n_groups * n_ntiles;
 
-  // Zero the A regions once: slots past the end of the tensor are never filled by TMA.
-  for (int e = threadIdx.x; e < Cfg::kStages * Cfg::kStageElems; e += K_THREADS) stage_base[e] = 0.0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -81,35 +95,37 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
     }
     fence_mbar_init();
   }
-  fence_proxy_async();
   __syncthreads();
 
   if (warp >= K_CONSUMER_WARPS) {
     reg_dealloc_producer();
     if (warp != K_CONSUMER_WARPS) return;
     // ===== TMA producer warp: lanes 0..7 own one slot each, lane 8 owns the C operand =====
-    long long f = f0 + lane;
-    const bool valid = lane < K_SLOTS && f < total_rows;
-    int q = 0, tr = 0;
-    if (valid) { q = (int)(f / nt); tr = (int)(f % nt); }
-    const double *row = packed + (size_t)q * L;
-    int n_valid = 0;
-    for (int s = 0; s < K_SLOTS; ++s) n_valid += (f0 + s < total_rows) ? 1 : 0;
-    const uint32_t stage_bytes = (uint32_t)(n_valid * TILE_ELEMS + Cfg::kBElems) * sizeof(double);
-    for (int kc = 0; kc < nt; ++kc) {
-      const int st = kc % Cfg::kStages;
-      const uint32_t ph = (kc / Cfg::kStages) & 1;
-      mbar_wait(&empty_bar[st], ph ^ 1);
-      double *a_s = stage_base + (size_t)st * Cfg::kStageElems;
-      if (lane == 0) mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
-      __syncwarp();
-      if (valid) {
-        const int a = tr > kc ? tr : kc, b = tr > kc ? kc : tr;
-        tma_load_1d(a_s + lane * TILE_ELEMS, row + (size_t)tile_index(a, b, nt) * TILE_ELEMS,
-                    TILE_ELEMS * sizeof(double), &full_bar[st]);
-      } else if (lane == K_SLOTS) {
-        tma_load_1d(a_s + Cfg::kAElems, ctf + ((size_t)kc * nib + ib0) * 128, Cfg::kBElems * sizeof(double),
-                    &full_bar[st]);
+    constexpr uint32_t stage_bytes = (uint32_t)(Cfg::kAElems + Cfg::kBElems) * sizeof(double);
+    uint32_t it = 0;                                            // ring position, continuous over tiles
+    for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
+      const long long f0 = (work / n_ntiles) * K_SLOTS;
+      const int ib0 = (int)(work % n_ntiles) * (2 * NB);
+      // slots past the end of the tensor re-load the last row; their results are not stored
+      long long f = f0 + lane;
+      if (f > total_rows - 1) f = total_rows - 1;
+      const int q = (int)(f / nt), tr = (int)(f % nt);
+      const double *row = packed + (size_t)q * L;
+      for (int kc = 0; kc < nt; ++kc, ++it) {
+        const int st = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        double *a_s = stage_base + (size_t)st * Cfg::kStageElems;
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
+        __syncwarp();
+        if (lane < K_SLOTS) {
+          const int a = tr > kc ? tr : kc, b = tr > kc ? kc : tr;
+          tma_load_1d(a_s + lane * TILE_ELEMS, row + (size_t)tile_index(a, b, nt) * TILE_ELEMS,
+                      TILE_ELEMS * sizeof(double), &full_bar[st]);
+        } else if (lane == K_SLOTS) {
+          tma_load_1d(a_s + Cfg::kAElems, ctf + ((size_t)kc * nib + ib0) * 128, Cfg::kBElems * sizeof(double),
+                      &full_bar[st]);
+        }
       }
     }
     return;
@@ -119,72 +135,78 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
   reg_alloc_consumer();
   const int wm = warp & 3, wn = warp >> 2;
   const int g = lane >> 2, t = lane & 3;
-  // the two 16-row slots of this warp
-  int tr_s[2], q_s[2];
-  bool ok_s[2];
-#pragma unroll
-  for (int sl = 0; sl < 2; ++sl) {
-    const long long f = f0 + 2 * wm + sl;
-    ok_s[sl] = f < total_rows;
-    q_s[sl] = ok_s[sl] ? (int)(f / nt) : 0;
-    tr_s[sl] = ok_s[sl] ? (int)(f % nt) : 0;
-  }
   const int lane_direct = lane;                                // (g*4 + t)
   const int lane_transp = ((g >> 2) << 5) + (t << 2) + (g & 3);
+  uint32_t it = 0;
 
-  double acc[4][NB][2];
+  for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
+    const long long f0 = (work / n_ntiles) * K_SLOTS;
+    const int ib0 = (int)(work % n_ntiles) * (2 * NB);
+    // the two 16-row slots of this warp
+    int tr_s[2], q_s[2];
+    bool ok_s[2];
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
-#pragma unroll
-    for (int j = 0; j < NB; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
-
-  for (int kc = 0; kc < nt; ++kc) {
-    const int st = kc % Cfg::kStages;
-    const uint32_t ph = (kc / Cfg::kStages) & 1;
-    mbar_wait(&full_bar[st], ph);
-    const double *a_s = stage_base + (size_t)st * Cfg::kStageElems + (2 * wm) * TILE_ELEMS;
-    const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + Cfg::kAElems + (wn * NB) * 128;
-    const bool tp0 = tr_s[0] < kc, tp1 = tr_s[1] < kc;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      double a[4], b[NB];
-      // direct:     ((rh*4 + ks)*32 + lane)
-      // transposed: (((ks>>1)*4 + 2*rh)*32 + (ks&1)*16 + lane_transp)
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        const bool tp = sl ? tp1 : tp0;
-#pragma unroll
-        for (int rh = 0; rh < 2; ++rh) {
-          const int off_d = (rh * 4 + ks) * 32 + lane_direct;
-          const int off_t = (((ks >> 1) * 4 + 2 * rh) * 32) + (ks & 1) * 16 + lane_transp;
-          a[sl * 2 + rh] = a_s[sl * TILE_ELEMS + (tp ? off_t : off_d)];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NB; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int j = 0; j < NB; ++j) dmma884(acc[m][j][0], acc[m][j][1], a[m], b[j]);
+    for (int sl = 0; sl < 2; ++sl) {
+      long long f = f0 + 2 * wm + sl;
+      ok_s[sl] = f < total_rows;
+      if (!ok_s[sl]) f = total_rows - 1;
+      q_s[sl] = (int)(f / nt);
+      tr_s[sl] = (int)(f % nt);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[st]);
-  }
 
-  // epilogue: X[q][kc_out][mb][ks_out][g*4 + t_out], two adjacent i per thread (16-byte stores)
+    double acc[4][NB][2];
 #pragma unroll
-  for (int sl = 0; sl < 2; ++sl) {
-    if (!ok_s[sl]) continue;
+    for (int m = 0; m < 4; ++m)
 #pragma unroll
-    for (int rh = 0; rh < 2; ++rh) {
-      const int mb = 2 * tr_s[sl] + rh;
+      for (int j = 0; j < NB; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
+
+    for (int kc = 0; kc < nt; ++kc, ++it) {
+      const int st = it % Cfg::kStages;
+      const uint32_t ph = (it / Cfg::kStages) & 1;
+      mbar_wait(&full_bar[st], ph);
+      const double *a_s = stage_base + (size_t)st * Cfg::kStageElems + (2 * wm) * TILE_ELEMS;
+      const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + Cfg::kAElems + (wn * NB) * 128;
+      const bool tp0 = tr_s[0] < kc, tp1 = tr_s[1] < kc;
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int i0 = (ib0 + wn * NB + j) * 8;                 // first i of this n8 block
-        const int kc_out = i0 >> 4;
-        const int ks_out = ((i0 & 15) >> 2) + (t >> 1);
-        const size_t off = (((size_t)q_s[sl] * nkc + kc_out) * nmb + mb) * 128 + ks_out * 32 + g * 4 + 2 * (t & 1);
-        *reinterpret_cast<double2 *>(x + off) = make_double2(acc[sl * 2 + rh][j][0], acc[sl * 2 + rh][j][1]);
+      for (int ks = 0; ks < 4; ++ks) {
+        double a[4], b[NB];
+        // direct:     ((rh*4 + ks)*32 + lane)
+        // transposed: (((ks>>1)*4 + 2*rh)*32 + (ks&1)*16 + lane_transp)
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const bool tp = sl ? tp1 : tp0;
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            const int off_d = (rh * 4 + ks) * 32 + lane_direct;
+            const int off_t = (((ks >> 1) * 4 + 2 * rh) * 32) + (ks & 1) * 16 + lane_transp;
+            a[sl * 2 + rh] = a_s[sl * TILE_ELEMS + (tp ? off_t : off_d)];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) dmma884(acc[m][j][0], acc[m][j][1], a[m], b[j]);
+      }
+      release_stage(&empty_bar[st], lane);
+    }
+
+    // epilogue: X[q][kc_out][mb][ks_out][g*4 + t_out], two adjacent i per thread (16-byte stores)
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      if (!ok_s[sl]) continue;
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        const int mb = 2 * tr_s[sl] + rh;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int i0 = (ib0 + wn * NB + j) * 8;                 // first i of this n8 block
+          const int kc_out = i0 >> 4;
+          const int ks_out = ((i0 & 15) >> 2) + (t >> 1);
+          const size_t off = (((size_t)q_s[sl] * nkc + kc_out) * nmb + mb) * 128 + ks_out * 32 + g * 4 + 2 * (t & 1);
+          *reinterpret_cast<double2 *>(x + off) = make_double2(acc[sl * 2 + rh][j][0], acc[sl * 2 + rh][j][1]);
+        }
       }
     }
   }
@@ -193,17 +215,35 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
 // ------------------------------------------------------------------------------------
 // Accumulation (SYRK)
 // ------------------------------------------------------------------------------------
+// TILE = 128: 8 consumer warps (4x2, 32x64 warp tiles), one CTA per SM, setmaxnreg.
+// TILE =  64: 4 consumer warps (2x2, 32x32 warp tiles) + 1 producer warp, three CTAs per
+//             SM.  Less diagonal/padding waste (c2: 1.14x the triangle instead of 1.45x) at
+//             twice the L2->smem traffic per flop.
+template <int TILE>
 struct SyrkCfg {
+  static constexpr int kWarpsM = TILE == 128 ? 4 : 2;
+  static constexpr int kWarpsN = 2;
+  static constexpr int kConsumerWarps = kWarpsM * kWarpsN;
+  static constexpr int kTN = TILE / (8 * kWarpsN);          // n8-blocks per warp
+  static constexpr int kThreads = TILE == 128 ? K_THREADS : (kConsumerWarps + 1) * 32;
+  static constexpr int kMinBlocks = TILE == 128 ? 1 : 3;
+#ifdef MQCB200_DBG_STAGES
+  static constexpr int kStages = MQCB200_DBG_STAGES;
+#else
   static constexpr int kStages = 4;
-  static constexpr int kPanelElems = 16 * 128;            // 16 m-blocks * (4 k-subs * 32) = 16 KiB
+#endif
+  static constexpr int kPanelBlocks = TILE / 8;              // 8-row blocks per panel
+  static constexpr int kPanelElems = kPanelBlocks * 128;     // * (4 k-subs * 32)
   static constexpr int kStageElems = 2 * kPanelElems;
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageElems * sizeof(double) + 2 * kStages * sizeof(uint64_t);
 };
 
-__global__ void __launch_bounds__(K_THREADS, 1)
+template <int TILE>
+__global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads, SyrkCfg<TILE>::kMinBlocks)
 k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count, int n_ktiles, int n_splits,
                     double *__restrict__ kpart, int accumulate) {
-  using Cfg = SyrkCfg;
+  using Cfg = SyrkCfg<TILE>;
+  constexpr int PB = Cfg::kPanelBlocks;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stage_base = reinterpret_cast<double *>(smem_raw);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)Cfg::kStages * Cfg::kStageElems * sizeof(double));
@@ -218,23 +258,26 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
   const int qa = (int)((long long)split * q_count / n_splits);
   const int qb = (int)((long long)(split + 1) * q_count / n_splits);
   const int n_steps = (qb - qa) * nkc;
-  const int valid_a = nmb - 16 * mp < 16 ? nmb - 16 * mp : 16;   // 8-row blocks present in each panel
-  const int valid_b = nmb - 16 * np < 16 ? nmb - 16 * np : 16;
+  const int valid_a = nmb - PB * mp < PB ? nmb - PB * mp : PB;   // 8-row blocks present in each panel
+  const int valid_b = nmb - PB * np < PB ? nmb - PB * np : PB;
 
-  for (int e = threadIdx.x; e < Cfg::kStages * Cfg::kStageElems; e += K_THREADS) stage_base[e] = 0.0;
+  // panels past the end of the matrix are never filled by TMA: keep them zero
+#ifndef MQCB200_DBG_NOZERO
+  for (int e = threadIdx.x; e < Cfg::kStages * Cfg::kStageElems; e += Cfg::kThreads) stage_base[e] = 0.0;
+#endif
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], K_CONSUMER_WARPS);
+      mbar_init(&empty_bar[s], Cfg::kConsumerWarps);
     }
     fence_mbar_init();
   }
   fence_proxy_async();
   __syncthreads();
 
-  if (warp >= K_CONSUMER_WARPS) {
-    reg_dealloc_producer();
-    if (warp == K_CONSUMER_WARPS && lane == 0) {
+  if (warp >= Cfg::kConsumerWarps) {
+    if (TILE == 128) reg_dealloc_producer();
+    if (warp == Cfg::kConsumerWarps && lane == 0) {
       const uint32_t bytes_a = (uint32_t)valid_a * 128 * sizeof(double);
       const uint32_t bytes_b = diag ? 0u : (uint32_t)valid_b * 128 * sizeof(double);
       for (int step = 0; step < n_steps; ++step) {
@@ -244,52 +287,52 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
         double *a_s = stage_base + (size_t)st * Cfg::kStageElems;
         const size_t blk = ((size_t)(qa + step / nkc) * nkc + (step % nkc)) * nmb;
         mbar_arrive_expect_tx(&full_bar[st], bytes_a + bytes_b);
-        tma_load_1d(a_s, x + (blk + 16 * mp) * 128, bytes_a, &full_bar[st]);
-        if (!diag) tma_load_1d(a_s + Cfg::kPanelElems, x + (blk + 16 * np) * 128, bytes_b, &full_bar[st]);
+        tma_load_1d(a_s, x + (blk + PB * mp) * 128, bytes_a, &full_bar[st]);
+        if (!diag) tma_load_1d(a_s + Cfg::kPanelElems, x + (blk + PB * np) * 128, bytes_b, &full_bar[st]);
       }
     }
     return;
   }
 
-  reg_alloc_consumer();
-  const int wm = warp & 3, wn = warp >> 2;
+  if (TILE == 128) reg_alloc_consumer();
+  const int wm = warp % Cfg::kWarpsM, wn = warp / Cfg::kWarpsM;
   const int g = lane >> 2, t = lane & 3;
-  double acc[4][8][2];
+  constexpr int TN = Cfg::kTN;
+  double acc[4][TN][2];
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
+    for (int j = 0; j < TN; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
 
   for (int step = 0; step < n_steps; ++step) {
     const int st = step % Cfg::kStages;
     const uint32_t ph = (step / Cfg::kStages) & 1;
     mbar_wait(&full_bar[st], ph);
     const double *a_s = stage_base + (size_t)st * Cfg::kStageElems + (4 * wm) * 128;
-    const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + (diag ? 0 : Cfg::kPanelElems) + (8 * wn) * 128;
+    const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + (diag ? 0 : Cfg::kPanelElems) + (TN * wn) * 128;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      double a[4], b[8];
+      double a[4], b[TN];
 #pragma unroll
       for (int m = 0; m < 4; ++m) a[m] = a_s[(m * 4 + ks) * 32 + lane];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
+      for (int j = 0; j < TN; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
 #pragma unroll
       for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dmma884(acc[m][j][0], acc[m][j][1], a[m], b[j]);
+        for (int j = 0; j < TN; ++j) dmma884(acc[m][j][0], acc[m][j][1], a[m], b[j]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[st]);
+    release_stage(&empty_bar[st], lane);
   }
 
-  double *out = kpart + (((size_t)split * n_ktiles + tile) << 14);
+  double *out = kpart + ((size_t)split * n_ktiles + tile) * (TILE * TILE);
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     const int r = 32 * wm + 8 * m + g;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = 64 * wn + 8 * j + 2 * t;
-      double2 *p = reinterpret_cast<double2 *>(out + r * 128 + c);
+    for (int j = 0; j < TN; ++j) {
+      const int c = 8 * TN * wn + 8 * j + 2 * t;
+      double2 *p = reinterpret_cast<double2 *>(out + r * TILE + c);
       double2 v = make_double2(acc[m][j][0], acc[m][j][1]);
       if (accumulate) { const double2 o = *p; v.x += o.x; v.y += o.y; }
       *p = v;
@@ -300,6 +343,16 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
 // ------------------------------------------------------------------------------------
 // planning + launch
 // ------------------------------------------------------------------------------------
+static int ktile_override() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("MQCB200_KTILE");
+    v = e ? atoi(e) : 0;
+    if (v != 64 && v != 128) v = 0;
+  }
+  return v;
+}
+
 KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm_count) {
   KPlan p;
   const int nt = num_tiles(n);
@@ -311,27 +364,38 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
   p.nib = p.n_ntiles * 2 * p.nb;
   p.nkc = p.nib / 2;
   p.nmb = 2 * nt;
-  p.n_panels = (n + 127) / 128;
+  // K tile edge: 64 trims the diagonal/padding waste of the SYRK; 128 halves the operand
+  // traffic per flop and wins once n is large enough that the waste is small.
+  p.ktile = ktile_override() ? ktile_override() : 64;
+  p.n_panels = (n + p.ktile - 1) / p.ktile;
   p.n_ktiles = p.n_panels * (p.n_panels + 1) / 2;
+  const int slots = sm_count * (p.ktile == 128 ? 1 : 3);
+  p.sm_count = sm_count;
   p.x_elems_per_q = (size_t)p.nkc * p.nmb * 128;
   size_t qc = workspace_limit_bytes / (p.x_elems_per_q * sizeof(double));
   if (qc < 1) qc = 1;
   if (qc > (size_t)(q_count > 0 ? q_count : 1)) qc = (size_t)(q_count > 0 ? q_count : 1);
   p.q_chunk = (int)qc;
-  // split of the contraction range: fill the machine with whole waves of one CTA per SM
+  // Split of the contraction range over CTAs.  Cost model: waves * (steps per unit + a fixed
+  // per-CTA overhead worth ~12 pipeline steps); small problems get many short units, big
+  // ones whole waves.  The partial buffer is capped at 256 MiB.
   int best = 1;
-  double best_eff = 0.0;
-  for (int s = 1; s <= 64; ++s) {
-    if (s > p.q_chunk) break;
+  double best_cost = 1e300;
+  const size_t tile_bytes = (size_t)p.ktile * p.ktile * sizeof(double);
+  for (int s = 1; s <= 512 && s <= p.q_chunk; ++s) {
+    if ((size_t)s * p.n_ktiles * tile_bytes > ((size_t)256 << 20) && s > 1) break;
     const long long units = (long long)s * p.n_ktiles;
-    const long long waves = (units + sm_count - 1) / sm_count;
-    const double eff = (double)units / (double)(waves * sm_count);
-    const long long steps = (long long)(p.q_chunk / s) * p.nkc;
-    if (s > 1 && steps < 64) break;
-    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    const long long waves = (units + slots - 1) / slots;
+    const long long steps = (long long)((p.q_chunk + s - 1) / s) * p.nkc;
+    const double cost = (double)waves * ((double)steps + 12.0);
+    if (cost < best_cost * 0.995) { best_cost = cost; best = s; }
+  }
+  if (const char *e = getenv("MQCB200_KSPLITS")) {   // development override
+    const int v = atoi(e);
+    if (v >= 1) best = v < p.q_chunk ? v : p.q_chunk;
   }
   p.n_splits = best;
-  p.kpart_elems = ((size_t)p.n_splits * p.n_ktiles) << 14;
+  p.kpart_elems = (size_t)p.n_splits * p.n_ktiles * p.ktile * p.ktile;
   return p;
 }
 
@@ -340,9 +404,10 @@ static void launch_half_nb(const double *d_packed, long long L, int n, int q_cou
                            const KPlan &plan, double *d_x, cudaStream_t s) {
   const int nt = num_tiles(n);
   const long long rows = (long long)q_count * nt;
-  dim3 grid((unsigned)((rows + K_SLOTS - 1) / K_SLOTS), (unsigned)plan.n_ntiles);
-  k_half_transform_kernel<NB><<<grid, K_THREADS, HalfCfg<NB>::kSmemBytes, s>>>(d_packed, L, nt, q_count, d_ctf,
-                                                                             plan.nib, d_x, plan.nkc, plan.nmb);
+  const long long n_work = (rows + K_SLOTS - 1) / K_SLOTS * plan.n_ntiles;
+  const unsigned grid = (unsigned)(n_work < plan.sm_count ? n_work : plan.sm_count);
+  k_half_transform_kernel<NB><<<grid, K_THREADS, HalfCfg<NB>::kSmemBytes, s>>>(
+      d_packed, L, nt, q_count, d_ctf, plan.nib, plan.n_ntiles, d_x, plan.nkc, plan.nmb);
 }
 
 void launch_k_half_transform(const double *d_packed, long long L, int n, int q_count, const double *d_ctf,
@@ -364,8 +429,12 @@ void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, doub
   // A short last chunk still touches every (split, tile) partial -- splits with an empty
   // auxiliary range write (or add) zeros -- so the fixed-order sum in finalize is defined.
   const int splits = plan.n_splits;
-  k_accumulate_kernel<<<(unsigned)(splits * plan.n_ktiles), K_THREADS, SyrkCfg::kSmemBytes, s>>>(
-      d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, d_kpart, accumulate);
+  if (plan.ktile == 128)
+    k_accumulate_kernel<128><<<(unsigned)(splits * plan.n_ktiles), SyrkCfg<128>::kThreads, SyrkCfg<128>::kSmemBytes, s>>>(
+        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, d_kpart, accumulate);
+  else
+    k_accumulate_kernel<64><<<(unsigned)(splits * plan.n_ktiles), SyrkCfg<64>::kThreads, SyrkCfg<64>::kSmemBytes, s>>>(
+        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, d_kpart, accumulate);
 }
 
 template <int NB>
@@ -377,7 +446,8 @@ static void configure_half() {
 void configure_kernels() {
   configure_half<1>(); configure_half<2>(); configure_half<3>(); configure_half<4>();
   configure_half<5>(); configure_half<6>(); configure_half<7>(); configure_half<8>();
-  cudaFuncSetAttribute(k_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg::kSmemBytes);
+  cudaFuncSetAttribute(k_accumulate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg<128>::kSmemBytes);
+  cudaFuncSetAttribute(k_accumulate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg<64>::kSmemBytes);
 }
 
 }  // namespace mqcb200

@@ -21,7 +21,7 @@ void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib
 // Sum the J / K partial buffers in fixed order and unpack to full n x n matrices.
 // Either output may be null.  k_factor multiplies K (2 for RHF, 1 per spin).
 void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits,
-                        int n, double k_factor, double *d_j, double *d_k, cudaStream_t s);
+                        int ktile, int n, double k_factor, double *d_j, double *d_k, cudaStream_t s);
 // F = H + jf*J - kf*K  (any of J/K may be null == zero).
 void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf,
                           int n, double *d_fock, cudaStream_t s);
@@ -49,12 +49,14 @@ struct KPlan {
   int nib;         // padded occupied count / 8   (= n_ntiles * 2 * nb)
   int nkc;         // padded occupied count / 16
   int nmb;         // 8-row blocks of X per (q, kc): 2*nt
-  int n_panels;    // 128-row panels of K
-  int n_ktiles;    // lower-triangular 128x128 tiles of K
+  int ktile;       // edge of the square K tiles of the accumulation (64 or 128)
+  int n_panels;    // ktile-row panels of K
+  int n_ktiles;    // lower-triangular ktile x ktile tiles of K
   int n_splits;    // split of the auxiliary range in the accumulation
   int q_chunk;     // auxiliary functions per half-transform launch
+  int sm_count;    // persistent grid size of the half-transform
   size_t x_elems_per_q;     // doubles of X per auxiliary function
-  size_t kpart_elems;       // n_splits * n_ktiles * 128*128
+  size_t kpart_elems;       // n_splits * n_ktiles * ktile*ktile
 };
 KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm_count);
 void launch_k_half_transform(const double *d_packed, long long L, int n, int q_count,

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) pack_coeff_kernel(const double *__restric
 // source of both (mu,nu) and (nu,mu), so the outputs are exactly symmetric.
 __global__ void __launch_bounds__(256) finalize_jk_kernel(const double *__restrict__ jpart, int n_jslices,
                                                           long long L, const double *__restrict__ kpart,
-                                                          int n_ksplits, int n_ktiles, int n, int nt,
+                                                          int n_ksplits, int n_ktiles, int ktile_log2, int n, int nt,
                                                           double k_factor, double *__restrict__ j_out,
                                                           double *__restrict__ k_out) {
   const int mu = blockIdx.x * 16 + (threadIdx.x & 15);
@@ -105,10 +105,10 @@ __global__ void __launch_bounds__(256) finalize_jk_kernel(const double *__restri
     j_out[(size_t)mu + (size_t)n * nu] = s;
   }
   if (k_out) {
-    const int mp = a >> 7, np = b >> 7;
-    const size_t off = ((size_t)(mp * (mp + 1) / 2 + np) << 14) + ((size_t)(a & 127) << 7) + (b & 127);
+    const int mp = a >> ktile_log2, np = b >> ktile_log2, msk = (1 << ktile_log2) - 1;
+    const size_t off = ((size_t)(mp * (mp + 1) / 2 + np) << (2 * ktile_log2)) + ((size_t)(a & msk) << ktile_log2) + (b & msk);
     double s = 0.0;
-    for (int sp = 0; sp < n_ksplits; ++sp) s += kpart[((size_t)sp * n_ktiles << 14) + off];
+    for (int sp = 0; sp < n_ksplits; ++sp) s += kpart[((size_t)sp * n_ktiles << (2 * ktile_log2)) + off];
     k_out[(size_t)mu + (size_t)n * nu] = k_factor * s;
   }
 }
@@ -179,13 +179,14 @@ void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib
   pack_coeff_kernel<<<blocks, 256, 0, s>>>(d_coeff, ldc, n, n_occ, nib, nt, d_ctf);
 }
 
-void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits, int n,
-                        double k_factor, double *d_j, double *d_k, cudaStream_t s) {
+void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits, int ktile,
+                        int n, double k_factor, double *d_j, double *d_k, cudaStream_t s) {
   const int nt = num_tiles(n);
-  const int np = (n + 127) / 128;
+  const int ktile_log2 = ktile == 128 ? 7 : 6;
+  const int np = (n + ktile - 1) / ktile;
   dim3 grid((unsigned)nt, (unsigned)nt);
   finalize_jk_kernel<<<grid, 256, 0, s>>>(d_jpart, n_jslices, packed_row_len(n), d_kpart, n_ksplits,
-                                          np * (np + 1) / 2, n, nt, k_factor, d_j, d_k);
+                                          np * (np + 1) / 2, ktile_log2, n, nt, k_factor, d_j, d_k);
 }
 
 void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf, int n,

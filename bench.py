@@ -116,42 +116,31 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's build_fock_df on a bounded sub-sample
 # ------------------------------------------------------------------------------------------
-def cpu_port_time(n, n_occ, naux, q_sample, reps, two_spin_nb=None):
-    """Seconds per FULL build, extrapolated from `q_sample` auxiliary functions."""
-    from metalquicha_b200 import synth
-    from oracle import df_fock_oracle as oracle
-    qs = min(q_sample, naux)
-    scale = synth.default_scale(n, naux)
-    b = synth.synth_tensor(SEED, n, naux, scale, q_begin=0, q_count=qs)
-    _, h, density, coeff = synth.synth_problem(SEED, n, n_occ, naux, with_tensor=False)
-    times = []
-    fock = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        fock = oracle.build_fock_df(h, b, density, coeff, n_occ)
-        times.append(time.perf_counter() - t0)
-    t = min(times)
-    return t * (naux / qs), t, qs, (b, h, density, coeff, fock)
-
-
 def run_reference(args, cfg):
+    """Reference arm: the CPU port of build_fock_df (the Fortran reference cannot be built
+    here) on all host cores; each step is a bounded auxiliary sub-sample of the workload."""
     rank = _env_int("RANK", 0)
     if rank != 0:
         return
-    n, n_occ, naux = cfg["n"], cfg["n_occ"], cfg["naux"]
-    cores = os.cpu_count() or 1
-    # warm-up + timed "steps", each a bounded sample of the workload
-    q_sample = args.cpu_sample
-    total_reps = args.warmup + args.steps
     from metalquicha_b200 import synth
     from oracle import df_fock_oracle as oracle
-    qs = min(q_sample, naux)
+    n, n_occ, naux = cfg["n"], cfg["n_occ"], cfg["naux"]
+    n_beta = cfg.get("n_beta", 0)
+    cores = os.cpu_count() or 1
+    qs = min(args.cpu_sample, naux)
+    k_scale = 0.2 if args.workload == "c4" else 1.0
     b = synth.synth_tensor(SEED, n, naux, synth.default_scale(n, naux), 0, qs)
     _, h, density, coeff = synth.synth_problem(SEED, n, n_occ, naux, with_tensor=False)
+    if n_beta:
+        coeff_b = synth.synth_orbitals(SEED + 1, n, n_beta)
+        da, db = oracle.build_density_spin(coeff, n_occ), oracle.build_density_spin(coeff_b, n_beta)
     times = []
-    for r in range(total_reps):
+    for r in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        oracle.build_fock_df(h, b, density, coeff, n_occ)
+        if n_beta:
+            oracle.build_fock_df_uhf(h, b, da, db, coeff, n_occ, coeff_b, n_beta, k_scale=k_scale)
+        else:
+            oracle.build_fock_df(h, b, density, coeff, n_occ, k_scale=k_scale)
         if r >= args.warmup:
             times.append(time.perf_counter() - t0)
     t_full = (sum(times) / len(times)) * (naux / qs)
@@ -162,31 +151,171 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": "DF-J/K Fock builds/sec", "value": value, "unit": "builds/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_full,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": _config(args, cfg),
+        "data": "synthetic", "config": _config(args, cfg, args.gpus),
         "cpu_baseline": {"value": value, "unit": "builds/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "builds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def _config(args, cfg):
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
+    `ncu --set full` captures (profiles/ncu_traffic.json), keyed by workload and kernel."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+def _config(args, cfg, world, workers=None):
+    if args.workload == "c3":
+        w = workers if workers is not None else args.workers_per_gpu
+        return {"workload": "c3: (H2O)64 MBE-3 def2-SVP fragment farm, 256-fragment batch "
+                            "(1 monomer : 12 dimers : 243 trimers), 12 builds per fragment",
+                "n_ao": cfg["n"], "n_occ": cfg["n_occ"], "naux": cfg["naux"],
+                "parallelism": f"fragment FIFO over {world} GPU(s) x {w} worker(s) per GPU, no collective",
+                "l2": "fragments are L2-resident by nature (7 MB packed); timed as dispatched, no flush",
+                "timing": "host wall clock bracketed by barrier + cudaDeviceSynchronize, max over ranks"}
+    packed_gb = 8.0 * ((cfg["n"] + 15) // 16) * ((cfg["n"] + 15) // 16 + 1) / 2 * 256 * cfg["naux"] / 1e9
     return {"workload": f"{args.workload}: {cfg['what']}", "n_ao": cfg["n"], "n_occ": cfg.get("n_occ"),
-            "naux": cfg["naux"], "parallelism": f"aux-sharded x{args.gpus}" if args.gpus > 1 else "single GPU",
-            "l2": "packed tensor (>= 3.4 GB at c2) is larger than the 126 MB L2; no flush needed",
+            "n_beta": cfg.get("n_beta"), "naux": cfg["naux"],
+            "parallelism": f"aux-sharded x{world}, one all-reduce of [J;K] per build" if world > 1 else "single GPU",
+            "l2": f"packed tensor {packed_gb:.2f} GB >> 126 MB L2: inputs larger than L2, no flush",
             "timing": "CUDA events on the engine stream, max over ranks"}
+
+
+# ------------------------------------------------------------------------------------------
+# fragment farm (BASELINE configs[2]): independent fragments, one per GPU worker at a time
+# ------------------------------------------------------------------------------------------
+FARM_BUILDS_PER_FRAGMENT = 12          # guess + ~10 SCF iterations + final rebuild (rhf.f90:546,566,646)
+FARM_BATCH = {"c3_monomer": 1, "c3_dimer": 12, "c3": 243}   # 64 : 2016 : 41664 scaled to 256 fragments
+
+
+def run_farm(args, world, rank, local_rank):
+    """One step = one batch of 256 MBE-3 fragments (monomers/dimers/trimers in the run's
+    proportions), largest first, pulled by every GPU worker from a shared FIFO (queue_t
+    semantics); each fragment = set its tensor + FARM_BUILDS_PER_FRAGMENT Fock builds through
+    the host-buffer C-ABI call (that is the only way a fragment's SCF drives the engine, so
+    `value` and `e2e` coincide for this workload)."""
+    import torch
+    import torch.distributed as dist
+    from metalquicha_b200 import B200FockEngine, farm, synth
+
+    frags = []
+    for name, count in FARM_BATCH.items():
+        frags += [name] * count
+    sizes = [synth.CONFIGS[f]["n"] for f in frags]
+    order = farm.sort_fragments_largest_first(sizes)
+    problems = {}
+    for name in FARM_BATCH:
+        c = synth.CONFIGS[name]
+        _, h, d, co = synth.synth_problem(SEED, c["n"], c["n_occ"], c["naux"], with_tensor=False)
+        problems[name] = (c, h, d, co)
+
+    n_workers = max(1, args.workers_per_gpu)
+    engines = [B200FockEngine(local_rank) for _ in range(n_workers)]
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
+    builds_done = [0] * n_workers
+    launches = [0] * n_workers
+
+    def do_fragment(eng, widx, idx):
+        c, h, d, co = problems[frags[idx]]
+        eng.synth_tensor(c["n"], c["naux"], SEED + idx, synth.default_scale(c["n"], c["naux"]))
+        e = 0.0
+        for _ in range(FARM_BUILDS_PER_FRAGMENT):
+            eng.build_fock_df(h, d, co, c["n_occ"])
+            e = eng.last_energy()
+            launches[widx] += eng.last_launches() + 1
+        builds_done[widx] += FARM_BUILDS_PER_FRAGMENT
+        return e
+
+    import threading
+
+    def run_step(step_id):
+        if world > 1:
+            q = farm.DistributedWorkQueue(order, store, name=f"farm{step_id}")
+        else:
+            from metalquicha_b200 import WorkQueue
+            q = WorkQueue(order)
+        threads = [threading.Thread(target=farm.worker_loop, args=(q, lambda i, w=w: do_fragment(engines[w], w, i)))
+                   for w in range(n_workers)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        run_step(f"w{w}")
+    builds_done[:] = [0] * n_workers
+    launches[:] = [0] * n_workers
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    for s_ in range(args.steps):
+        run_step(f"s{s_}")
+    torch.cuda.synchronize()
+    t_local = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([t_local, float(sum(builds_done)), float(sum(launches))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_all, builds_all, launches_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    else:
+        t_all, builds_all, launches_all = float(tt[0]), float(tt[1]), float(tt[2])
+    for e in engines:
+        e.close()
+    if rank != 0:
+        return
+    trimer = synth.CONFIGS["c3"]
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import df_fock_oracle as oracle
+        c, h, d, co = problems["c3"]
+        b = synth.synth_tensor(SEED, c["n"], c["naux"])
+        ts = []
+        for _ in range(3):
+            t1 = time.perf_counter(); oracle.build_fock_df(h, b, d, co, c["n_occ"]); ts.append(time.perf_counter() - t1)
+        cpu_baseline = {"value": 1.0 / min(ts), "unit": "builds/s", "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": "one (H2O)3 trimer build (95 % of the batch is trimers), NumPy port on OpenBLAS, best of 3"}
+    value = builds_all / t_all
+    h2d = 8 * (2 * trimer["n"] ** 2 + trimer["n"] * trimer["n_occ"])
+    line = {
+        "metric": "DF-J/K Fock builds/sec", "value": value, "unit": "builds/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": _config(args, trimer, world, n_workers),
+        "e2e": {"value": value, "unit": "builds/s", "ms_per_step": 1e3 * t_all / args.steps,
+                "h2d_bytes_per_step": h2d * 256 * FARM_BUILDS_PER_FRAGMENT,
+                "d2h_bytes_per_step": 8 * trimer["n"] ** 2 * 256 * FARM_BUILDS_PER_FRAGMENT,
+                "note": "every build goes through mqcb200_build_fock with host buffers"},
+        "gpu_launches": int(launches_all),
+        "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                     "note": "79 MFLOP and 14 MB per trimer build: launch/latency-bound, see DESIGN.md"},
+        "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=200, help="auxiliary functions in the CPU-port sample")
+    ap.add_argument("--cpu-sample", type=int, default=None, help="auxiliary functions in the CPU-port sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--k-scale", type=float, default=None)
+    ap.add_argument("--workers-per-gpu", type=int, default=4, help="fragment farm: host workers (engine handles) per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -194,8 +323,17 @@ def main():
     if args.workload not in synth.CONFIGS:
         raise SystemExit(f"unknown workload {args.workload}; choose from {sorted(synth.CONFIGS)}")
     cfg = dict(synth.CONFIGS[args.workload])
-    if "n_occ" not in cfg:
+    two_spin = "n_alpha" in cfg
+    if two_spin:
         cfg["n_occ"] = cfg["n_alpha"]
+    n, n_occ, naux = cfg["n"], cfg["n_occ"], cfg["naux"]
+    n_beta = cfg.get("n_beta", 0)
+    # defaults sized so that a default run finishes within minutes and the timed region is ~1 s
+    flops_per_build = 3.0 * n * n * (n_occ + n_beta) * naux
+    if args.steps is None:
+        args.steps = 5 if args.workload == "c3" else int(min(200, max(5, 1.0 / (flops_per_build / 28e12 + 2e-4))))
+    if args.cpu_sample is None:
+        args.cpu_sample = int(min(naux, max(8, 2.0e10 / (4.0 * n * n * max(n_occ + n_beta, 1)))))
     if args.impl == "reference":
         run_reference(args, cfg)
         return
@@ -207,17 +345,25 @@ def main():
     world = _env_int("WORLD_SIZE", 1)
     rank = _env_int("RANK", 0)
     local_rank = _env_int("LOCAL_RANK", 0)
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n, n_occ, naux = cfg["n"], cfg["n_occ"], cfg["naux"]
+    if args.workload == "c3":
+        run_farm(args, world, rank, local_rank)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    from oracle import df_fock_oracle as oracle   # checker only: cpu_baseline + in-bench parity
     k_scale = args.k_scale if args.k_scale is not None else (0.2 if args.workload == "c4" else 1.0)
     scale = synth.default_scale(n, naux)
     _, h, density, coeff = synth.synth_problem(SEED, n, n_occ, naux, with_tensor=False)
+    coeff_b = synth.synth_orbitals(SEED + 1, n, n_beta) if two_spin else None
+    if two_spin:
+        density = np.asfortranarray(oracle.build_density_spin(coeff, n_occ) + oracle.build_density_spin(coeff_b, n_beta))
 
     eng = B200FockEngine(local_rank)
     q_begin, q_count = synth.shard_range(naux, world, rank)
@@ -231,19 +377,44 @@ def main():
     eng.synth_tensor(n, naux, SEED, scale, q_begin=q_begin, q_count=q_count)
     t_synth = time.perf_counter() - t_synth0
 
-    # device-resident operands (column-major == the transpose of a row-major torch tensor;
-    # H and D are symmetric, C is passed as its (n_occ, n) row-major image)
-    d_h = torch.from_numpy(np.ascontiguousarray(h.T)).cuda()
-    d_d = torch.from_numpy(np.ascontiguousarray(density.T)).cuda()
-    d_c = torch.from_numpy(np.ascontiguousarray(coeff.T)).cuda()
+    def dev(a):      # column-major matrix -> CUDA tensor whose memory is that column-major image
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(a).T)).cuda()
+
+    def pinned(a):   # same, in pinned host memory; returns (tensor, column-major numpy view)
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a).T)).pin_memory()
+        return t, t.numpy().T
+
+    d_h, d_d, d_c = dev(h), dev(density), dev(coeff)
     d_f = torch.empty_like(d_h)
-    # pinned host operands for the end-to-end arm
-    p_h = torch.from_numpy(np.asfortranarray(h).T.copy()).pin_memory()       # memory == column-major h
-    p_d = torch.from_numpy(np.asfortranarray(density).T.copy()).pin_memory()
-    p_c = torch.from_numpy(np.asfortranarray(coeff).T.copy()).pin_memory()
-    p_f = torch.empty(n, n, dtype=torch.float64).pin_memory()
-    h_np, d_np, f_np = p_h.numpy().T, p_d.numpy().T, p_f.numpy().T           # column-major views
-    c_np = p_c.numpy().T
+    _ph, h_np = pinned(h)
+    _pd, d_np = pinned(density)
+    _pc, c_np = pinned(coeff)
+    _pf, f_np = pinned(np.zeros((n, n)))
+    if two_spin:
+        d_cb = dev(coeff_b)
+        d_fb = torch.empty_like(d_h)
+        _pcb, cb_np = pinned(coeff_b)
+        _pfb, fb_np = pinned(np.zeros((n, n)))
+
+    if two_spin:
+        def dev_step(sync):
+            eng.build_fock_uhf_device(d_h, d_d, d_c, n_occ, d_cb, n_beta, d_f, d_fb, k_scale=k_scale, sync=sync)
+
+        def e2e_step():
+            from metalquicha_b200.engine import _check, _ptr
+            from ctypes import c_double
+            _check(eng._lib.mqcb200_build_fock_uhf(eng.handle, 0, _ptr(h_np), _ptr(d_np), _ptr(c_np), n, n_occ,
+                                                   _ptr(cb_np), n, n_beta, c_double(k_scale), _ptr(f_np), _ptr(fb_np)))
+        h2d = 8 * (2 * n * n + n * (n_occ + n_beta))
+        d2h = 16 * n * n
+    else:
+        def dev_step(sync):
+            eng.build_fock_device(d_h, d_d, d_c, n_occ, d_f, k_scale=k_scale, sync=sync)
+
+        def e2e_step():
+            eng.build_fock_df(h_np, d_np, c_np, n_occ, k_scale=k_scale, out=f_np)
+        h2d = 8 * (2 * n * n + n * n_occ)
+        d2h = 8 * n * n
 
     stream = torch.cuda.ExternalStream(eng.stream())
 
@@ -261,7 +432,7 @@ def main():
 
     # ---- device-resident arm -------------------------------------------------------------
     for _ in range(args.warmup):
-        eng.build_fock_device(d_h, d_d, d_c, n_occ, d_f, k_scale=k_scale, sync=True)
+        dev_step(True)
     launches_per_build = eng.last_launches()
     eng.set_profiling(True)
     eng.last_timings()
@@ -272,12 +443,11 @@ def main():
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
-        eng.build_fock_device(d_h, d_d, d_c, n_occ, d_f, k_scale=k_scale, sync=False)
+        dev_step(False)
     e1.record(stream)
     e1.synchronize()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
     phase = eng.last_timings()                       # sums over the timed steps, this rank
     eng.set_profiling(False)
     ms_per_step = ms_total / args.steps
@@ -286,34 +456,35 @@ def main():
 
     # ---- end-to-end arm: host buffers through the reference-facing call ----------------------
     for _ in range(max(1, args.warmup)):
-        eng.build_fock_df(h_np, d_np, c_np, n_occ, k_scale=k_scale, out=f_np)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
-        eng.build_fock_df(h_np, d_np, c_np, n_occ, k_scale=k_scale, out=f_np)
+        e2e_step()
     e1.record(stream)
     e1.synchronize()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
-    h2d = 8 * (2 * n * n + n * n_occ)
-    d2h = 8 * n * n
     e2e_equal = bool(np.array_equal(np.asarray(f_np), fock_dev))
 
     # ---- rooflines ----------------------------------------------------------------------------
     hbm_peak, hbm_src = _peaks()
     npair = n * (n + 1) // 2
     steps = args.steps
+    occ_total = n_occ + n_beta
     t_k1 = phase["k_half_transform"] / steps * 1e-3
     t_k2 = phase["k_accumulate"] / steps * 1e-3
     t_j1 = phase["j_gamma"] / steps * 1e-3
     t_j2 = phase["j_accumulate"] / steps * 1e-3
-    fl_k1 = 2.0 * n * n * n_occ * q_count            # half-transform, per launch (this rank's shard)
-    fl_k2 = 1.0 * n * n * n_occ * q_count            # SYRK-form accumulation
+    fl_k1 = 2.0 * n * n * occ_total * q_count        # half-transform (all spins), this rank's shard
+    fl_k2 = 1.0 * n * n * occ_total * q_count        # SYRK-form accumulation
     by_j = 8.0 * npair * q_count                     # one pass over the packed shard
 
     # live FP64 peak: cuBLAS DGEMM (its B200 kernel is DMMA.8x8x4 too), best of 5
+    torch.cuda.synchronize()
     a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
     bmat = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
     best = 1e9
@@ -336,6 +507,11 @@ def main():
         kern("j_gamma_kernel", "hbm", by_j, t_j1, hbm_peak, "GB/s", 1e-9),
         kern("j_accumulate_kernel", "hbm", by_j, t_j2, hbm_peak, "GB/s", 1e-9),
     ]
+    for k in kernels:
+        k["ms_per_launch"] = k["ms_per_launch"] / max(1, (2 if (two_spin and k["bound"] == "tensor") else 1))
+    traffic = _ncu_traffic()
+    for k in kernels:
+        k["traffic"] = traffic.get(args.workload, {}).get(k["kernel"])
     roofline = dict(kernels[0])
     roofline["peak_source"] = "measured live: cuBLAS DGEMM 8192^3 best of 5 (FP64 is not in MEASURED_PEAKS.json)"
     k_total = t_k1 + t_k2
@@ -345,9 +521,11 @@ def main():
         "K_frac_of_fp64_peak": (fl_k1 + fl_k2) / k_total * 1e-12 / fp64_peak if k_total > 0 else 0.0,
         "J_gbs": 2 * by_j / j_total * 1e-9 if j_total > 0 else 0.0,
         "J_frac_of_hbm_peak": 2 * by_j / j_total * 1e-9 / hbm_peak if j_total > 0 else 0.0,
-        "fp64_peak_tflops": fp64_peak, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+        "fp64_peak_tflops": fp64_peak, "fp64_issue_bound_tflops": 37.05,
+        "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
         "phase_ms_per_build": {k: v / steps for k, v in phase.items()},
-        "reference_flops_as_executed_tflops": 4.0 * n * n * n_occ * q_count / k_total * 1e-12 if k_total > 0 else 0.0,
+        "reference_flops_as_executed_tflops": 4.0 * n * n * occ_total * q_count / k_total * 1e-12 if k_total > 0 else 0.0,
+        "packed_tensor_gb_per_rank": eng.tensor_bytes() / 1e9,
     }
 
     # ---- CPU baseline + in-bench parity on the sampled auxiliary range (rank 0, N=1) -----------
@@ -355,13 +533,28 @@ def main():
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        t_full, t_s, qs, (b_s, h_s, d_s, c_s, f_ref) = cpu_port_time(n, n_occ, naux, args.cpu_sample, 2)
+        qs = min(args.cpu_sample, naux)
+        b_s = synth.synth_tensor(SEED, n, naux, scale, q_begin=0, q_count=qs)
+        ts = []
+        for _ in range(2):
+            t1 = time.perf_counter()
+            if two_spin:
+                da = oracle.build_density_spin(coeff, n_occ); db = oracle.build_density_spin(coeff_b, n_beta)
+                f_ref, _fb = oracle.build_fock_df_uhf(h, b_s, da, db, coeff, n_occ, coeff_b, n_beta, k_scale=k_scale)
+            else:
+                f_ref = oracle.build_fock_df(h, b_s, density, coeff, n_occ, k_scale=k_scale)
+            ts.append(time.perf_counter() - t1)
+        t_s = min(ts)
+        t_full = t_s * naux / qs
         cpu_baseline = {"value": 1.0 / t_full, "unit": "builds/s", "cores": cores, "kind": "port",
                         "sample": f"{qs} of {naux} auxiliary functions ({t_s:.2f} s), scaled by {naux}/{qs}; "
                                   "NumPy loop-for-loop port of build_fock_df on OpenBLAS"}
         with B200FockEngine(local_rank) as chk:
             chk.synth_tensor(n, naux, SEED, scale, q_begin=0, q_count=qs)
-            f_gpu = chk.build_fock_df(h_s, d_s, c_s, n_occ)
+            if two_spin:
+                f_gpu, _ = chk.build_fock_df_uhf(h, da, db, coeff, n_occ, coeff_b, n_beta, k_scale=k_scale)
+            else:
+                f_gpu = chk.build_fock_df(h, density, coeff, n_occ, k_scale=k_scale)
         parity = {"max_abs_err_vs_oracle": float(np.max(np.abs(f_gpu - f_ref))), "sample_naux": qs,
                   "tolerance": 1e-10}
 
@@ -372,7 +565,7 @@ def main():
             "metric": "DF-J/K Fock builds/sec", "value": value, "unit": "builds/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": _config(args, cfg),
+            "data": "synthetic", "config": _config(args, cfg, world),
             "e2e": {"value": 1e3 / e2e_ms, "unit": "builds/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "bit_identical_to_device_arm": e2e_equal},

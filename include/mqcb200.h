@@ -126,6 +126,13 @@ int mqcb200_build_fock_device(void *handle, int slot, const double *d_h,
                               const double *d_density, const double *d_coeff, int n_occ,
                               double k_scale, double j_scale, double *d_fock, int sync);
 
+/* Two-spin device-resident variant (same conventions as mqcb200_build_fock_uhf). */
+int mqcb200_build_fock_uhf_device(void *handle, int slot, const double *d_h,
+                                  const double *d_density_total,
+                                  const double *d_coeff_a, int n_alpha,
+                                  const double *d_coeff_b, int n_beta, double k_scale,
+                                  double *d_fock_a, double *d_fock_b, int sync);
+
 /* ---- multi-GPU (whole-molecule builds sharded by auxiliary index) ---------
  * New behaviour relative to the reference, which never splits one Fock build
  * (SURVEY 2.2).  One process per GPU; each holds a shard set with

@@ -46,6 +46,8 @@ SIGNATURES = {
     "mqcb200_last_energy": (c_int, [c_void_p, POINTER(c_double)]),
     "mqcb200_build_fock_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                           c_double, c_double, c_void_p, c_int]),
+    "mqcb200_build_fock_uhf_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                              c_void_p, c_int, c_double, c_void_p, c_void_p, c_int]),
     "mqcb200_comm_unique_id": (c_int, [c_char_p]),
     "mqcb200_comm_init": (c_int, [c_void_p, c_int, c_int, c_char_p]),
     "mqcb200_comm_destroy": (c_int, [c_void_p]),

@@ -658,6 +658,25 @@ int mqcb200_build_fock_device(void *handle, int slot, const double *d_h, const d
   API_END
 }
 
+int mqcb200_build_fock_uhf_device(void *handle, int slot, const double *d_h, const double *d_density_total,
+                                  const double *d_coeff_a, int n_alpha, const double *d_coeff_b, int n_beta,
+                                  double k_scale, double *d_fock_a, double *d_fock_b, int sync) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!d_h || !d_density_total || !d_fock_a || !d_fock_b)
+    throw Failure("mqcb200: null device pointer argument to build_fock_uhf_device");
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  BuildArgs a;
+  a.slot = slot; a.device_operands = true; a.two_spin = true; a.h = d_h; a.density = d_density_total;
+  a.coeff_a = d_coeff_a; a.lda = e->slots[slot].n; a.n_a = n_alpha;
+  a.coeff_b = d_coeff_b; a.ldb = e->slots[slot].n; a.n_b = n_beta;
+  a.k_scale = k_scale; a.j_scale = 1.0; a.fock_a = d_fock_a; a.fock_b = d_fock_b;
+  a.assemble = true; a.sync = sync != 0;
+  a.want_k = k_scale != 0.0;
+  build(e, a);
+  API_END
+}
+
 int mqcb200_last_energy(void *handle, double *e_elec) {
   GET_ENGINE(handle)
   API_BEGIN

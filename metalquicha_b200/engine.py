@@ -261,6 +261,19 @@ class B200FockEngine:
             c_void_p(d_coeff.data_ptr()), int(n_occ), c_double(k_scale), c_double(j_scale),
             c_void_p(d_fock.data_ptr()), 1 if sync else 0))
 
+    def build_fock_uhf_device(self, d_h, d_density_total, d_coeff_a, n_alpha: int, d_coeff_b, n_beta: int,
+                              d_fock_a, d_fock_b, k_scale=1.0, slot: int = SLOT_FULL_RANGE,
+                              sync: bool = True) -> None:
+        tensors = [d_h, d_density_total, d_coeff_a, d_fock_a, d_fock_b] + ([d_coeff_b] if n_beta > 0 else [])
+        for t in tensors:
+            if not t.is_cuda or str(t.dtype) != "torch.float64" or not t.is_contiguous():
+                raise TypeError("device operands must be contiguous float64 CUDA tensors")
+        _check(self._lib.mqcb200_build_fock_uhf_device(
+            self._h, slot, c_void_p(d_h.data_ptr()), c_void_p(d_density_total.data_ptr()),
+            c_void_p(d_coeff_a.data_ptr()), int(n_alpha),
+            c_void_p(d_coeff_b.data_ptr() if n_beta > 0 else None), int(n_beta), c_double(k_scale),
+            c_void_p(d_fock_a.data_ptr()), c_void_p(d_fock_b.data_ptr()), 1 if sync else 0))
+
     # -- multi-GPU --------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -139,9 +139,39 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
   const int lane_transp = ((g >> 2) << 5) + (t << 2) + (g & 3);
   uint32_t it = 0;
 
+  // Fragments are double-buffered in registers and loaded one k-sub ahead of the DMMAs
+  // that consume them -- across the stage boundary too: the wait on the next stage's
+  // barrier and its first LDS are issued before the last DMMA block of the current stage,
+  // so neither the mbarrier round trip nor the LDS latency is exposed.
+  double fa[2][4], fb[2][NB];
+  auto load_frags = [&](double (&a)[4], double (&b)[NB], int st, int ks, bool tp0, bool tp1) {
+    const double *a_s = stage_base + (size_t)st * Cfg::kStageElems + (2 * wm) * TILE_ELEMS;
+    const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + Cfg::kAElems + (wn * NB) * 128;
+    // direct:     ((rh*4 + ks)*32 + lane)
+    // transposed: (((ks>>1)*4 + 2*rh)*32 + (ks&1)*16 + lane_transp)
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const bool tp = sl ? tp1 : tp0;
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        const int off_d = (rh * 4 + ks) * 32 + lane_direct;
+        const int off_t = (((ks >> 1) * 4 + 2 * rh) * 32) + (ks & 1) * 16 + lane_transp;
+        a[sl * 2 + rh] = a_s[sl * TILE_ELEMS + (tp ? off_t : off_d)];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
+  };
+
+  if (blockIdx.x < n_work) {                                   // prologue: first stage, k-sub 0 (kc = 0 is never transposed)
+    mbar_wait(&full_bar[0], 0);
+    load_frags(fa[0], fb[0], 0, 0, false, false);
+  }
+
   for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
     const long long f0 = (work / n_ntiles) * K_SLOTS;
     const int ib0 = (int)(work % n_ntiles) * (2 * NB);
+    const bool more_work = work + gridDim.x < n_work;
     // the two 16-row slots of this warp
     int tr_s[2], q_s[2];
     bool ok_s[2];
@@ -162,32 +192,22 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
 
     for (int kc = 0; kc < nt; ++kc, ++it) {
       const int st = it % Cfg::kStages;
-      const uint32_t ph = (it / Cfg::kStages) & 1;
-      mbar_wait(&full_bar[st], ph);
-      const double *a_s = stage_base + (size_t)st * Cfg::kStageElems + (2 * wm) * TILE_ELEMS;
-      const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + Cfg::kAElems + (wn * NB) * 128;
       const bool tp0 = tr_s[0] < kc, tp1 = tr_s[1] < kc;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        double a[4], b[NB];
-        // direct:     ((rh*4 + ks)*32 + lane)
-        // transposed: (((ks>>1)*4 + 2*rh)*32 + (ks&1)*16 + lane_transp)
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const bool tp = sl ? tp1 : tp0;
-#pragma unroll
-          for (int rh = 0; rh < 2; ++rh) {
-            const int off_d = (rh * 4 + ks) * 32 + lane_direct;
-            const int off_t = (((ks >> 1) * 4 + 2 * rh) * 32) + (ks & 1) * 16 + lane_transp;
-            a[sl * 2 + rh] = a_s[sl * TILE_ELEMS + (tp ? off_t : off_d)];
-          }
+        if (ks < 3) {
+          load_frags(fa[(ks + 1) & 1], fb[(ks + 1) & 1], st, ks + 1, tp0, tp1);
+        } else if (kc + 1 < nt || more_work) {
+          const uint32_t it1 = it + 1;
+          const int st1 = it1 % Cfg::kStages;
+          mbar_wait(&full_bar[st1], (it1 / Cfg::kStages) & 1);
+          const bool in_tile = kc + 1 < nt;                    // the next tile starts at kc = 0: direct
+          load_frags(fa[0], fb[0], st1, 0, in_tile && tr_s[0] < kc + 1, in_tile && tr_s[1] < kc + 1);
         }
-#pragma unroll
-        for (int j = 0; j < NB; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
 #pragma unroll
         for (int m = 0; m < 4; ++m)
 #pragma unroll
-          for (int j = 0; j < NB; ++j) dmma884(acc[m][j][0], acc[m][j][1], a[m], b[j]);
+          for (int j = 0; j < NB; ++j) dmma884(acc[m][j][0], acc[m][j][1], fa[ks & 1][m], fb[ks & 1][j]);
       }
       release_stage(&empty_bar[st], lane);
     }
@@ -304,23 +324,35 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
 #pragma unroll
     for (int j = 0; j < TN; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
 
-  for (int step = 0; step < n_steps; ++step) {
-    const int st = step % Cfg::kStages;
-    const uint32_t ph = (step / Cfg::kStages) & 1;
-    mbar_wait(&full_bar[st], ph);
+  // register double-buffered fragments, loaded one k-sub ahead (see the half-transform)
+  double fa[2][4], fb[2][TN];
+  auto load_frags = [&](double (&a)[4], double (&b)[TN], int st, int ks) {
     const double *a_s = stage_base + (size_t)st * Cfg::kStageElems + (4 * wm) * 128;
     const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + (diag ? 0 : Cfg::kPanelElems) + (TN * wn) * 128;
 #pragma unroll
+    for (int m = 0; m < 4; ++m) a[m] = a_s[(m * 4 + ks) * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
+  };
+  if (n_steps > 0) {
+    mbar_wait(&full_bar[0], 0);
+    load_frags(fa[0], fb[0], 0, 0);
+  }
+  for (int step = 0; step < n_steps; ++step) {
+    const int st = step % Cfg::kStages;
+#pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      double a[4], b[TN];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) a[m] = a_s[(m * 4 + ks) * 32 + lane];
-#pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
+      if (ks < 3) {
+        load_frags(fa[(ks + 1) & 1], fb[(ks + 1) & 1], st, ks + 1);
+      } else if (step + 1 < n_steps) {
+        const int st1 = (step + 1) % Cfg::kStages;
+        mbar_wait(&full_bar[st1], ((step + 1) / Cfg::kStages) & 1);
+        load_frags(fa[0], fb[0], st1, 0);
+      }
 #pragma unroll
       for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) dmma884(acc[m][j][0], acc[m][j][1], a[m], b[j]);
+        for (int j = 0; j < TN; ++j) dmma884(acc[m][j][0], acc[m][j][1], fa[ks & 1][m], fb[ks & 1][j]);
     }
     release_stage(&empty_bar[st], lane);
   }

@@ -39,6 +39,19 @@ sys.path.insert(0, ROOT)
 SEED = 20261018
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun
+# notices) write to file descriptor 1 behind Python's back, so everything else is sent
+# to stderr and only emit() writes to the real stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def _env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -155,7 +168,7 @@ def run_reference(args, cfg):
         "cpu_baseline": {"value": value, "unit": "builds/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "builds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def _ncu_traffic():
@@ -301,7 +314,7 @@ def run_farm(args, world, rank, local_rank):
                      "note": "79 MFLOP and 14 MB per trimer build: launch/latency-bound, see DESIGN.md"},
         "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -574,7 +587,7 @@ def main():
             "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
             "tensor_setup_s": t_synth,
         }
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -162,6 +162,9 @@ int mqcb200_queue_destroy(void *queue);
 int mqcb200_set_profiling(void *handle, int on);
 int mqcb200_last_timings(void *handle, double ms[MQCB200_NUM_TIMERS]);
 int mqcb200_last_launches(void *handle, int *n_kernels);
+/* Device time (ms) of the whitening GEMM of the last mqcb200_set_tensor_from_3c and its
+ * flop count 2*naux^2*L ("timed separately", not part of builds/sec). */
+int mqcb200_last_whiten(void *handle, double *ms, double *flops);
 
 #ifdef __cplusplus
 }

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mqcb200_set_profiling": (c_int, [c_void_p, c_int]),
     "mqcb200_last_timings": (c_int, [c_void_p, _dp]),
     "mqcb200_last_launches": (c_int, [c_void_p, POINTER(c_int)]),
+    "mqcb200_last_whiten": (c_int, [c_void_p, _dp, _dp]),
 }
 
 _lib = None

@@ -125,6 +125,7 @@ struct Engine {
   DevBuf d_h, d_density, d_coeff, d_coeff_b, d_w, d_ctf, d_gamma_partial, d_gamma, d_jpart, d_x, d_kpart;
   DevBuf d_jk;       // [J | K | K_beta] contiguous so one all-reduce covers them
   DevBuf d_fock, d_fock_b, d_scalar, d_stage;
+  double whiten_ms = 0.0, whiten_flops = 0.0;
   int last_n = 0;    // shape of the operands of the last build_fock (for last_energy)
   bool have_last_fock = false;
 
@@ -546,8 +547,61 @@ int mqcb200_set_tensor_shard(void *handle, int slot, int n, int naux_total, int 
 int mqcb200_set_tensor_from_3c(void *handle, int slot, int n, int naux, const double *three, const double *half) {
   GET_ENGINE(handle)
   API_BEGIN
-  (void)slot; (void)n; (void)naux; (void)three; (void)half;
-  throw Failure("mqcb200: device whitening (set_tensor_from_3c) is not built yet; whiten on the host and call mqcb200_set_tensor");
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  if (!three || !half) throw Failure("mqcb200: null three-centre tensor or metric factor");
+  e->bind();
+  // 1. pack (mu nu|P) exactly like a fitted tensor, into a scratch of the same size
+  DevBuf tp;
+  TensorSlot &sl = e->slots[slot];
+  slot_prepare(e, sl, n, naux, 0, naux);
+  try {
+    tp.ensure((size_t)sl.L * (size_t)naux * sizeof(double));
+    const size_t slab = (size_t)n * n;
+    size_t chunk = std::max<size_t>(1, ((size_t)512 << 20) / (slab * sizeof(double)));
+    chunk = std::min<size_t>(chunk, (size_t)naux);
+    e->d_stage.ensure(chunk * slab * sizeof(double));
+    for (size_t q0 = 0; q0 < (size_t)naux; q0 += chunk) {
+      const size_t qc = std::min(chunk, (size_t)naux - q0);
+      CUDA_CHECK(cudaMemcpyAsync(e->d_stage.ptr, three + q0 * slab, qc * slab * sizeof(double),
+                                 cudaMemcpyHostToDevice, e->stream));
+      launch_pack_tensor(e->d_stage.d(), n, (int)qc, tp.d() + q0 * (size_t)sl.L, e->stream);
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    }
+    // 2. metric^(-1/2) to the device, 3. Bp = half . Tp
+    DevBuf d_half, d_af;
+    try {
+      d_half.ensure((size_t)naux * naux * sizeof(double));
+      d_af.ensure(whiten_half_elems(naux) * sizeof(double));
+      CUDA_CHECK(cudaMemcpyAsync(d_half.ptr, half, (size_t)naux * naux * sizeof(double), cudaMemcpyHostToDevice,
+                                 e->stream));
+      cudaEvent_t w0, w1;
+      CUDA_CHECK(cudaEventCreate(&w0));
+      CUDA_CHECK(cudaEventCreate(&w1));
+      CUDA_CHECK(cudaEventRecord(w0, e->stream));
+      launch_whiten(d_half.d(), naux, tp.d(), n, d_af.d(), sl.packed.d(), e->stream);
+      CUDA_CHECK(cudaEventRecord(w1, e->stream));
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      float wms = 0.f;
+      cudaEventElapsedTime(&wms, w0, w1);
+      cudaEventDestroy(w0);
+      cudaEventDestroy(w1);
+      e->whiten_ms = wms;
+      e->whiten_flops = 2.0 * (double)naux * (double)naux * (double)sl.L;
+    } catch (...) {
+      d_half.release();
+      d_af.release();
+      throw;
+    }
+    d_half.release();
+    d_af.release();
+  } catch (...) {
+    tp.release();
+    throw;
+  }
+  tp.release();
+  sl.set = true;
   API_END
 }
 
@@ -794,6 +848,14 @@ int mqcb200_last_timings(void *handle, double ms[MQCB200_NUM_TIMERS]) {
   e->collect_timers();
   for (int i = 0; i < MQCB200_NUM_TIMERS; ++i) ms[i] = e->last_ms[i];
   API_END
+}
+
+int mqcb200_last_whiten(void *handle, double *ms, double *flops) {
+  GET_ENGINE(handle)
+  if (!ms || !flops) { g_last_error = "mqcb200: null output pointer"; return MQCB200_FAIL; }
+  *ms = e->whiten_ms;
+  *flops = e->whiten_flops;
+  return MQCB200_OK;
 }
 
 int mqcb200_last_launches(void *handle, int *n_kernels) {

@@ -29,33 +29,6 @@
 
 namespace mqcb200 {
 
-constexpr int K_CONSUMER_WARPS = 8;
-// Eight consumer warps (two warpgroups) + one producer warpgroup of which only warp 8
-// works.  Three warps share each SM sub-partition's 16K registers, so the launch
-// allocation is capped at 168/thread; the producer warpgroup hands its share back
-// (setmaxnreg.dec) and the consumers grow to 232 (setmaxnreg.inc): 2*232 + 40 <= 512.
-constexpr int K_THREADS = (K_CONSUMER_WARPS + 4) * 32;
-constexpr int K_PRODUCER_REGS = 40;
-constexpr int K_CONSUMER_REGS = 232;
-
-__device__ __forceinline__ void reg_dealloc_producer() {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K_PRODUCER_REGS));
-}
-// Consumer-side release of a pipeline stage.  The stage was read through the generic
-// proxy (LDS) and will be overwritten through the async proxy (bulk TMA): without a
-// cross-proxy fence ptxas is free to hoist the mbarrier arrive above the DMMAs that
-// wait for the LDS results, and the TMA refill then races the reads (seen on B200 as
-// run-to-run differences with short pipelines, see profiles/r01_notes.md).
-__device__ __forceinline__ void release_stage(uint64_t *empty_bar, int lane) {
-  fence_proxy_async();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(empty_bar);
-}
-__device__ __forceinline__ void reg_alloc_consumer() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K_CONSUMER_REGS));
-}
-constexpr int K_SLOTS = 8;                               // 16-row slots per CTA (BM = 128)
-
 // ------------------------------------------------------------------------------------
 // Half-transform
 // ------------------------------------------------------------------------------------

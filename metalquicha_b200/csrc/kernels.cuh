@@ -29,6 +29,11 @@ void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_
 void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n,
                    double *d_out, cudaStream_t s);
 
+// ---- whitening: Bp = half . Tp on the packed tensor (build_df_tensor's GEMM) ----
+size_t whiten_half_elems(int naux);   // doubles of the fragment-ordered copy of `half`
+void launch_whiten(const double *d_half, int naux, const double *d_tp, int n, double *d_af, double *d_bp,
+                   cudaStream_t s);
+
 // ---- J: two passes over the packed tensor -----------------------------------
 struct JPlan {
   int n_seg;      // pass 1: segments of a packed row

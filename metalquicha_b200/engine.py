@@ -137,6 +137,12 @@ class B200FockEngine:
         self.n[slot] = n
         self.naux[slot] = (naux, 0, naux)
 
+    def build_df_tensor(self, three, metric, n: int, slot: int = SLOT_FULL_RANGE) -> None:
+        """Last two stages of ``build_df_tensor`` (integrals.F90:981-987): ``half =
+        metric^(-1/2)`` on the host as in the reference, ``b = three . half`` on the device,
+        written straight into the packed resident layout."""
+        self.set_tensor_from_3c(three, metric_inverse_sqrt(metric), n, slot=slot)
+
     def synth_tensor(self, n: int, naux_total: int, seed: int, scale: float,
                      q_begin: int = 0, q_count: int | None = None,
                      slot: int = SLOT_FULL_RANGE) -> None:
@@ -298,6 +304,12 @@ class B200FockEngine:
         _check(self._lib.mqcb200_last_timings(self._h, ms))
         return dict(zip(_lib.TIMER_NAMES, list(ms)))
 
+    def last_whiten(self):
+        """``(ms, flops)`` of the last device whitening GEMM."""
+        ms, fl = c_double(0.0), c_double(0.0)
+        _check(self._lib.mqcb200_last_whiten(self._h, byref(ms), byref(fl)))
+        return ms.value, fl.value
+
     def last_launches(self) -> int:
         n = c_int(0)
         _check(self._lib.mqcb200_last_launches(self._h, byref(n)))
@@ -313,6 +325,23 @@ class B200FockEngine:
             raise ValueError("coeff must be (n, >= n_occ)")
         ldc = coeff.strides[1] // coeff.itemsize if coeff.shape[1] > 1 else max(n, coeff.shape[0])
         return coeff, int(ldc)
+
+
+NULL_THRESHOLD = 1.0e-10     # mqc_libcint_integrals.F90:1002
+
+
+def metric_inverse_sqrt(metric):
+    """J^(-1/2) = U s^(-1/2) U^T over the modes above 1e-10
+    (mqc_libcint_integrals.F90:992-1038).  Host-side like the reference (LAPACK dsyev
+    through pic_syev); eigenvalues at or below the threshold are zeroed, not errored;
+    a metric with no surviving mode raises the reference's message."""
+    metric = np.asarray(metric, dtype=np.float64)
+    values, vectors = np.linalg.eigh(metric, UPLO="U")
+    keep = values > NULL_THRESHOLD
+    if not np.any(keep):
+        raise B200Error(_lib.MQCB200_FAIL, "density fitting: the auxiliary metric is singular")
+    scaled = np.where(keep[None, :], vectors / np.sqrt(np.where(keep, values, 1.0))[None, :], 0.0)
+    return np.asfortranarray(scaled @ vectors.T)
 
 
 def density_pseudo_orbitals(density):

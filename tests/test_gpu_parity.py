@@ -174,6 +174,35 @@ def test_physical_like_tensor_with_dropped_modes(engine):
     assert _maxabs(fock, oracle.build_fock_df(h, b, density, coeff, n_occ)) <= TOL * scale
 
 
+@pytest.mark.parametrize("n,naux,n_null", [(24, 30, 2), (40, 139, 0), (37, 150, 3), (130, 260, 1)])
+def test_device_whitening_matches_reference_gemm(engine, n, naux, n_null):
+    """mqcb200_set_tensor_from_3c: b = three . metric^(-1/2) formed on the device in the
+    packed layout (integrals.F90:981-987) vs pic_gemm(three, half, b) of the oracle."""
+    from metalquicha_b200.engine import metric_inverse_sqrt
+    three, metric = synth.synth_physical_like_tensor(3, n, naux, n_null=n_null)
+    half_ref = oracle.metric_inverse_sqrt(metric)
+    half = metric_inverse_sqrt(metric)
+    assert _maxabs(half, half_ref) <= 1e-9 * max(1.0, float(np.max(np.abs(half_ref))))
+    b = np.asfortranarray(three @ half)              # the reference's whitening GEMM on these inputs
+    n_occ = max(1, n // 5)
+    _, h, density, coeff = synth.synth_problem(3, n, n_occ, naux, with_tensor=False)
+    engine.set_tensor(b)
+    f_host = engine.build_fock_df(h, density, coeff, n_occ)
+    engine.set_tensor_from_3c(three, half, n)
+    f_dev = engine.build_fock_df(h, density, coeff, n_occ)
+    scale = max(1.0, float(np.max(np.abs(f_host))))
+    assert _maxabs(f_dev, f_host) <= TOL * scale
+    assert _maxabs(f_dev, oracle.build_fock_df(h, b, density, coeff, n_occ)) <= TOL * scale
+    engine.build_df_tensor(three, metric, n)          # host eigendecomposition + device GEMM
+    assert _maxabs(engine.build_fock_df(h, density, coeff, n_occ), f_host) <= TOL * scale
+
+
+def test_singular_metric_is_refused():
+    from metalquicha_b200.engine import metric_inverse_sqrt
+    with pytest.raises(B200Error, match="singular"):
+        metric_inverse_sqrt(np.zeros((5, 5)))
+
+
 def test_device_generator_matches_host_generator(engine):
     """mqcb200_synth_tensor == synth.synth_tensor bit for bit (checked through a build)."""
     n, n_occ, naux = 70, 11, 50

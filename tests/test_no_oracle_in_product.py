@@ -25,3 +25,6 @@ def test_numpy_is_not_used_for_contractions_in_the_engine_mirror():
     dsyev) but must not contract B with anything on the host."""
     text = open(os.path.join(ROOT, "metalquicha_b200", "engine.py")).read()
     assert "einsum" not in text and "tensordot" not in text and "matmul" not in text
+    # the only host matrix product allowed is U s^-1/2 U^T of the (naux x naux) metric,
+    # which the reference also forms on the host (integrals.F90:1036)
+    assert text.count(" @ ") == 1

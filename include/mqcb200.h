@@ -115,6 +115,19 @@ int mqcb200_build_fock_uhf(void *handle, int slot, const double *h,
                            const double *coeff_a, int lda, int n_alpha,
                            const double *coeff_b, int ldb, int n_beta,
                            double k_scale, double *fock_a, double *fock_b);
+/* G = J[density] + ka*K[Ca] + kb*K[Cb] with K[C] = sum_P (B_P C)(B_P C)^T (no factor 2).
+ * The building block of the reference's other two fitted operators on the same tensor
+ * (SURVEY 8f row 3), which the host mirror assembles from it:
+ *   response_operator_df (backends/libcint/mqc_libcint_cphf.F90:499-566):
+ *       (B X)(B C)^T + h.c. = 1/2 [K[X+C] - K[X-C]]   ->  ka = -kf/4, kb = +kf/4
+ *   fitted_potential_general (mqc_libcint_cphf.F90:568-616): D = V+ w+ V+^T - V- |w-| V-^T
+ *       K = K[V+ sqrt(w+)] - K[V- sqrt|w-|]           ->  ka = -kf/2, kb = +kf/2
+ * A channel with n == 0 is skipped. */
+int mqcb200_build_g_two_factor(void *handle, int slot, const double *density,
+                               const double *coeff_a, int lda, int n_a,
+                               const double *coeff_b, int ldb, int n_b,
+                               double ka, double kb, double *g);
+
 /* E = 1/2 sum D (H + F)  (electronic_energy, mqc_libcint_rhf.f90:1691-1697),
  * evaluated on the device from the operands of the last mqcb200_build_fock. */
 int mqcb200_last_energy(void *handle, double *e_elec);

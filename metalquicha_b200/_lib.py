@@ -43,6 +43,8 @@ SIGNATURES = {
                                      c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mqcb200_build_fock_uhf": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                        c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
+    "mqcb200_build_g_two_factor": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                           c_void_p, c_int, c_int, c_double, c_double, c_void_p]),
     "mqcb200_last_energy": (c_int, [c_void_p, POINTER(c_double)]),
     "mqcb200_build_fock_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                           c_double, c_double, c_void_p, c_int]),

@@ -236,6 +236,8 @@ struct BuildArgs {
   double *j = nullptr, *k_a = nullptr, *k_b = nullptr, *fock_a = nullptr, *fock_b = nullptr;
   double k_scale = 1.0, j_scale = 1.0;
   bool assemble = false;
+  bool combine = false;           // G = J + ka_coef*Ka + kb_coef*Kb into fock_a (host pointer)
+  double ka_coef = 0.0, kb_coef = 0.0;
   bool sync = true;
 };
 
@@ -400,6 +402,16 @@ static void build(Engine *e, const BuildArgs &a) {
       e->phase_end(T_DOWNLOAD);
       if (!a.two_spin && d_h && d_density) { e->last_n = n; e->have_last_fock = true; }
     }
+  } else if (a.combine) {
+    e->phase_begin(T_FINAL);
+    e->d_fock.ensure(nn * sizeof(double));
+    launch_combine_g(do_j ? d_j : nullptr, do_ka ? d_ka : nullptr, do_kb ? d_kb : nullptr, a.ka_coef, a.kb_coef, n,
+                     e->d_fock.d(), e->stream);
+    e->launches += 1;
+    e->phase_end(T_FINAL);
+    e->phase_begin(T_DOWNLOAD);
+    CUDA_CHECK(cudaMemcpyAsync(a.fock_a, e->d_fock.d(), nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    e->phase_end(T_DOWNLOAD);
   } else if (!a.device_operands) {
     e->phase_begin(T_DOWNLOAD);
     if (a.j && do_j) CUDA_CHECK(cudaMemcpyAsync(a.j, d_j, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
@@ -708,6 +720,20 @@ int mqcb200_build_fock_device(void *handle, int slot, const double *d_h, const d
   a.assemble = true; a.sync = sync != 0;
   a.want_j = j_scale != 0.0;
   a.want_k = k_scale != 0.0;
+  build(e, a);
+  API_END
+}
+
+int mqcb200_build_g_two_factor(void *handle, int slot, const double *density, const double *coeff_a, int lda,
+                               int n_a, const double *coeff_b, int ldb, int n_b, double ka, double kb, double *g) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!density || !g) throw Failure("mqcb200: null matrix argument to build_g_two_factor");
+  BuildArgs a;
+  a.slot = slot; a.density = density; a.two_spin = true;
+  a.coeff_a = coeff_a; a.lda = lda; a.n_a = n_a; a.coeff_b = coeff_b; a.ldb = ldb; a.n_b = n_b;
+  a.combine = true; a.ka_coef = ka; a.kb_coef = kb; a.fock_a = g;
+  a.want_k = (ka != 0.0 && n_a > 0) || (kb != 0.0 && n_b > 0);
   build(e, a);
   API_END
 }

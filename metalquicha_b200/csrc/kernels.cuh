@@ -25,6 +25,9 @@ void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kp
 // F = H + jf*J - kf*K  (any of J/K may be null == zero).
 void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf,
                           int n, double *d_fock, cudaStream_t s);
+// G = J + ka*Ka + kb*Kb (null operands are skipped).
+void launch_combine_g(const double *d_j, const double *d_ka, const double *d_kb, double ka, double kb, int n,
+                      double *d_g, cudaStream_t s);
 // e = 1/2 sum D (H + F), deterministic single-block reduction into d_out[0].
 void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n,
                    double *d_out, cudaStream_t s);

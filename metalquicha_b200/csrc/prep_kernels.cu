@@ -125,6 +125,17 @@ __global__ void __launch_bounds__(256) assemble_fock_kernel(const double *__rest
   }
 }
 
+__global__ void __launch_bounds__(256) combine_g_kernel(const double *__restrict__ j, const double *__restrict__ ka,
+                                                        const double *__restrict__ kb, double ca, double cb,
+                                                        size_t nn, double *__restrict__ g) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.x * blockDim.x) {
+    double v = j ? j[e] : 0.0;
+    if (ka) v += ca * ka[e];
+    if (kb) v += cb * kb[e];
+    g[e] = v;
+  }
+}
+
 __global__ void __launch_bounds__(1024) energy_kernel(const double *__restrict__ d, const double *__restrict__ h,
                                                       const double *__restrict__ f, size_t nn,
                                                       double *__restrict__ out) {
@@ -195,6 +206,14 @@ void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_
   unsigned blocks = (unsigned)((nn + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   assemble_fock_kernel<<<blocks, 256, 0, s>>>(d_h, d_j, d_k, jf, kf, nn, d_fock);
+}
+
+void launch_combine_g(const double *d_j, const double *d_ka, const double *d_kb, double ka, double kb, int n,
+                      double *d_g, cudaStream_t s) {
+  const size_t nn = (size_t)n * n;
+  unsigned blocks = (unsigned)((nn + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  combine_g_kernel<<<blocks, 256, 0, s>>>(d_j, d_ka, d_kb, ka, kb, nn, d_g);
 }
 
 void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n, double *d_out,

@@ -223,6 +223,45 @@ class B200FockEngine:
                                                 _ptr(fa), _ptr(fb)))
         return fa, fb
 
+    def _g_two_factor(self, density, ca, n_a, cb, n_b, ka, kb, slot):
+        n = self.n[slot]
+        density = _f64_colmajor(density, "density")
+        ca, lda = self._coeff(ca, n, n_a)
+        cb, ldb = self._coeff(cb, n, n_b)
+        g = np.empty((n, n), dtype=np.float64, order="F")
+        _check(self._lib.mqcb200_build_g_two_factor(self._h, slot, _ptr(density), _ptr(ca), lda, int(n_a),
+                                                    _ptr(cb), ldb, int(n_b), c_double(ka), c_double(kb), _ptr(g)))
+        return g
+
+    def response_operator_df(self, x, c_occ, dtilde, k_scale=None, slot: int = SLOT_FULL_RANGE) -> np.ndarray:
+        """``response_operator_df(b, x, c_occ, dtilde, g, k_scale)`` with ``b`` resident
+        (backends/libcint/mqc_libcint_cphf.F90:499-566): ``g = J[dtilde] - kf/2 * sum_P
+        [(B_P X)(B_P C)^T + h.c.]``.  The rank-2 exchange is the difference of two
+        symmetric builds, ``1/2 (K[X+C] - K[X-C])``, so it runs on the same kernels."""
+        x = np.asarray(x, dtype=np.float64)
+        c_occ = np.asarray(c_occ, dtype=np.float64)
+        if x.shape != c_occ.shape:
+            raise ValueError("x and c_occ must both be (n_ao, n_occ)")
+        kf = 1.0 if k_scale is None else k_scale
+        n_occ = c_occ.shape[1]
+        plus = np.asfortranarray(x + c_occ)
+        minus = np.asfortranarray(x - c_occ)
+        return self._g_two_factor(dtilde, plus, n_occ, minus, n_occ, -0.25 * kf, 0.25 * kf, slot)
+
+    def fitted_potential_general(self, dens, k_scale=None, slot: int = SLOT_FULL_RANGE) -> np.ndarray:
+        """``fitted_potential_general(b, dens, g, k_scale)`` (mqc_libcint_cphf.F90:568-616):
+        ``g = J[D] - kf/2 * sum_P B_P D B_P`` for a symmetric, possibly indefinite ``D``.
+        ``D`` is split by its eigendecomposition into a positive and a negative part
+        (host dsyev, as ``density_pseudo_orbitals`` does for a guess density), each of
+        which has orbitals; the exchange is then ``K[V+ sqrt(w+)] - K[V- sqrt|w-|]``."""
+        dens = np.asarray(dens, dtype=np.float64)
+        kf = 1.0 if k_scale is None else k_scale
+        values, vectors = np.linalg.eigh(0.5 * (dens + dens.T), UPLO="U")
+        pos, neg = values > OCCUPATION_FLOOR, values < -OCCUPATION_FLOOR
+        cp = np.asfortranarray(vectors[:, pos] * np.sqrt(values[pos])[None, :])
+        cn = np.asfortranarray(vectors[:, neg] * np.sqrt(-values[neg])[None, :])
+        return self._g_two_factor(dens, cp, cp.shape[1], cn, cn.shape[1], -0.5 * kf, 0.5 * kf, slot)
+
     def last_energy(self) -> float:
         """``electronic_energy(h, fock, density)`` of the last ``build_fock_df`` (rhf.f90:1691-1697)."""
         e = c_double(0.0)

@@ -169,6 +169,39 @@ def fitted_exchange_general(b, density):
     return k
 
 
+def response_operator_df(b, x, c_occ, dtilde, k_scale=None):
+    """g = J[dtilde] - kf/2 * sum_P [(B_P X)(B_P C)^T + (B_P C)(B_P X)^T]
+    backends/libcint/mqc_libcint_cphf.F90:499-566, loop for loop (:551-562)."""
+    kf = 1.0 if k_scale is None else k_scale
+    n = c_occ.shape[0]
+    coul = np.zeros((n, n))
+    exch = np.zeros((n, n))
+    for p in range(b.shape[1]):
+        b_p = _slab(b, p, n)
+        c_p = np.sum(b_p * dtilde)
+        coul = coul + c_p * b_p
+        bx = b_p @ x
+        bc = b_p @ c_occ
+        exch = bx @ bc.T + exch
+        exch = bc @ bx.T + exch
+    return coul - 0.5 * kf * exch
+
+
+def fitted_potential_general(b, dens, k_scale=None):
+    """g = J[D] - kf/2 * sum_P B_P D B_P     mqc_libcint_cphf.F90:568-616 (:604-613)."""
+    kf = 1.0 if k_scale is None else k_scale
+    n = dens.shape[0]
+    coul = np.zeros((n, n))
+    exch = np.zeros((n, n))
+    for p in range(b.shape[1]):
+        b_p = _slab(b, p, n)
+        c_p = np.sum(b_p * dens)
+        coul = coul + c_p * b_p
+        bd = b_p @ dens
+        exch = bd @ b_p + exch
+    return coul - 0.5 * kf * exch
+
+
 def metric_inverse_sqrt(metric: np.ndarray) -> np.ndarray:
     """J^(-1/2) = U s^(-1/2) U^T over modes with eigenvalue > 1e-10.
 

@@ -197,6 +197,33 @@ def test_device_whitening_matches_reference_gemm(engine, n, naux, n_null):
     assert _maxabs(engine.build_fock_df(h, density, coeff, n_occ), f_host) <= TOL * scale
 
 
+def test_response_operator_and_general_density_potential(engine):
+    """The reference's other two fitted operators on the same resident tensor
+    (mqc_libcint_cphf.F90:499-566 and :568-616), SURVEY 8f row 3."""
+    n, n_occ, naux = 58, 9, 70
+    b, _, _, coeff_all = synth.synth_problem(41, n, n, naux)           # all n orbitals
+    c_occ = np.asfortranarray(coeff_all[:, :n_occ])
+    c_vir = coeff_all[:, n_occ:]
+    rng = np.random.default_rng(41)
+    x = np.asfortranarray(c_vir @ rng.standard_normal((n - n_occ, n_occ)))   # X = C_vir U
+    dtilde = np.asfortranarray(x @ c_occ.T + c_occ @ x.T)                    # symmetric, indefinite
+    engine.set_tensor(b)
+    for ks in (None, 0.25):
+        g = engine.response_operator_df(x, c_occ, dtilde, k_scale=ks)
+        g_ref = oracle.response_operator_df(b, x, c_occ, dtilde, k_scale=ks)
+        assert _maxabs(g, g_ref) <= TOL * max(1.0, float(np.max(np.abs(g_ref))))
+    # the rank-2 form and the general form agree on the same response density
+    g_gen = engine.fitted_potential_general(dtilde)
+    assert _maxabs(g_gen, oracle.fitted_potential_general(b, dtilde)) <= 1e-9
+    assert _maxabs(g_gen, engine.response_operator_df(x, c_occ, dtilde)) <= 1e-9
+    # an unstructured symmetric density that integrates to zero (MP2-relaxed-like)
+    a = rng.standard_normal((n, n)); d = a + a.T; d -= np.trace(d) / n * np.eye(n)
+    d = np.asfortranarray(d)
+    g = engine.fitted_potential_general(d, k_scale=0.5)
+    g_ref = oracle.fitted_potential_general(b, d, k_scale=0.5)
+    assert _maxabs(g, g_ref) <= 1e-9 * max(1.0, float(np.max(np.abs(g_ref))))
+
+
 def test_singular_metric_is_refused():
     from metalquicha_b200.engine import metric_inverse_sqrt
     with pytest.raises(B200Error, match="singular"):

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
@@ -123,6 +124,8 @@ struct Engine {
 
   // per-build device operands and scratch (grow-only)
   DevBuf d_h, d_density, d_coeff, d_coeff_b, d_w, d_ctf, d_gamma_partial, d_gamma, d_jpart, d_x, d_kpart;
+  DevBuf d_gpart_a, d_gpart_b;   // Coulomb-vector partials written by the half-transform
+  DevBuf d_cep;                  // coefficients in accumulator order for that epilogue
   DevBuf d_jk;       // [J | K | K_beta] contiguous so one all-reduce covers them
   DevBuf d_fock, d_fock_b, d_scalar, d_stage;
   double whiten_ms = 0.0, whiten_flops = 0.0;
@@ -180,6 +183,15 @@ static Engine *as_engine(void *h) {
   Engine *e = static_cast<Engine *>(h);
   if (!e || e->magic != kMagic) return nullptr;
   return e;
+}
+
+static bool fuse_gamma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *env = getenv("MQCB200_NO_FUSE_GAMMA");   // development switch: always take the pass over B
+    v = (env && env[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 enum { T_UPLOAD = 0, T_J1, T_J2, T_K1, T_K2, T_FINAL, T_ALLREDUCE, T_DOWNLOAD };
@@ -252,18 +264,23 @@ static void upload_matrix(Engine *e, DevBuf &dst, const double *src, int rows, i
 }
 
 static void run_k(Engine *e, const TensorSlot &sl, const double *d_coeff, int ldc, int n_occ, double *d_kpart_out,
-                  KPlan &plan) {
+                  double *d_gamma_part, KPlan &plan) {
   const int n = sl.n;
   plan = plan_k(n, n_occ, sl.q_count, e->workspace_limit, e->sm_count);
   e->d_ctf.ensure((size_t)num_tiles(n) * plan.nib * 128 * sizeof(double));
   e->d_x.ensure(plan.x_elems_per_q * (size_t)plan.q_chunk * sizeof(double));
-  launch_pack_coeff(d_coeff, ldc, n, n_occ, plan.nib, e->d_ctf.d(), e->stream);
+  double *d_cep = nullptr;
+  if (d_gamma_part) {
+    e->d_cep.ensure((size_t)num_tiles(n) * plan.nib * 128 * sizeof(double));
+    d_cep = e->d_cep.d();
+  }
+  launch_pack_coeff(d_coeff, ldc, n, n_occ, plan.nib, e->d_ctf.d(), d_cep, e->stream);
   e->launches += 1;
   for (int q0 = 0, chunk = 0; q0 < sl.q_count; q0 += plan.q_chunk, ++chunk) {
     const int qc = std::min(plan.q_chunk, sl.q_count - q0);
     e->phase_begin(T_K1);
-    launch_k_half_transform(sl.packed.d() + (size_t)q0 * sl.L, sl.L, n, qc, e->d_ctf.d(), plan, e->d_x.d(),
-                            e->stream);
+    launch_k_half_transform(sl.packed.d() + (size_t)q0 * sl.L, sl.L, n, qc, e->d_ctf.d(), d_cep, plan, e->d_x.d(),
+                            d_gamma_part ? d_gamma_part + (size_t)q0 * plan.gamma_stride : nullptr, e->stream);
     e->phase_end(T_K1);
     e->phase_begin(T_K2);
     launch_k_accumulate(e->d_x.d(), qc, plan, d_kpart_out, chunk > 0, e->stream);
@@ -313,56 +330,97 @@ static void build(Engine *e, const BuildArgs &a) {
   e->d_jk.ensure(3 * nn * sizeof(double));
   double *d_j = e->d_jk.d(), *d_ka = d_j + nn, *d_kb = d_j + 2 * nn;
 
-  // ---- J
+  const bool have = sl.q_count > 0;
+  const double kfac = a.two_spin ? 1.0 : 2.0;
   JPlan jp = plan_j(n, sl.q_count);
-  if (do_j) {
-    if (sl.q_count > 0) {
-      e->d_w.ensure((size_t)sl.L * sizeof(double));
-      e->d_gamma_partial.ensure(jp.gamma_partial_elems * sizeof(double));
-      e->d_gamma.ensure((size_t)sl.q_count * sizeof(double));
-      e->d_jpart.ensure(jp.j_partial_elems * sizeof(double));
-      e->phase_begin(T_J1);
-      launch_pack_density(d_density, n, e->d_w.d(), e->stream);
-      launch_j_gamma(sl.packed.d(), sl.L, sl.q_count, e->d_w.d(), jp, e->d_gamma_partial.d(), e->d_gamma.d(), e->stream);
-      e->phase_end(T_J1);
-      e->phase_begin(T_J2);
-      launch_j_accumulate(sl.packed.d(), sl.L, sl.q_count, e->d_gamma.d(), jp, e->d_jpart.d(), e->stream);
-      e->phase_end(T_J2);
-      e->launches += 4;
-      CUDA_CHECK(cudaGetLastError());
-    }
+
+  // ---- Coulomb vector from the half-transform when the density is the orbitals' own
+  // (D = f C C^T: every SCF iteration).  Decided on the device by an exact consistency
+  // check, so an arbitrary density (guess, response, user-supplied) silently takes the
+  // general pass over B instead.  Only worth its three extra tiny launches on tensors
+  // whose pass over B is not itself tiny.
+  const bool fuse = do_j && do_ka && have && fuse_gamma_enabled() &&
+                    (size_t)sl.L * (size_t)sl.q_count * sizeof(double) >= ((size_t)256 << 20) &&
+                    (!a.two_spin || do_kb || a.n_b == 0);
+  int *d_flag = nullptr;
+  KPlan kp{}, kpb{};
+  if (fuse) {
+    unsigned long long *scratch = reinterpret_cast<unsigned long long *>(static_cast<char *>(e->d_scalar.ptr) + 16);
+    d_flag = reinterpret_cast<int *>(static_cast<char *>(e->d_scalar.ptr) + 32);
+    e->phase_begin(T_J1);
+    launch_density_consistency(d_density, n, d_ca, lda, a.n_a, do_kb ? d_cb : nullptr, ldb, do_kb ? a.n_b : 0, kfac,
+                               scratch, d_flag, e->stream);
+    e->phase_end(T_J1);
+    e->launches += 2;
   }
 
-  // ---- K (alpha / closed shell), then finalize; K (beta) reuses the scratch afterwards
-  const double kfac = a.two_spin ? 1.0 : 2.0;
-  KPlan kp{};
-  if (do_ka && sl.q_count > 0) {
+  // ---- K (alpha / closed shell); K (beta) reuses the scratch after alpha has been finalized
+  bool ka_finalized = false;
+  if (do_ka && have) {
     KPlan probe = plan_k(n, a.n_a, sl.q_count, e->workspace_limit, e->sm_count);
     e->d_kpart.ensure(probe.kpart_elems * sizeof(double));
-    run_k(e, sl, d_ca, lda, a.n_a, e->d_kpart.d(), kp);
+    if (fuse) e->d_gpart_a.ensure((size_t)probe.gamma_stride * sl.q_count * sizeof(double));
+    run_k(e, sl, d_ca, lda, a.n_a, e->d_kpart.d(), fuse ? e->d_gpart_a.d() : nullptr, kp);
   }
-  e->phase_begin(T_FINAL);
-  if (sl.q_count > 0) {
-    launch_finalize_jk(do_j ? e->d_jpart.d() : nullptr, jp.n_slices, do_ka ? e->d_kpart.d() : nullptr, kp.n_splits,
-                       kp.ktile ? kp.ktile : 64, n, kfac, do_j ? d_j : nullptr, do_ka ? d_ka : nullptr, e->stream);
-    e->launches += 1;
-  } else {
-    if (do_j) CUDA_CHECK(cudaMemsetAsync(d_j, 0, nn * sizeof(double), e->stream));
-    if (do_ka) CUDA_CHECK(cudaMemsetAsync(d_ka, 0, nn * sizeof(double), e->stream));
-  }
-  e->phase_end(T_FINAL);
   if (do_kb) {
-    if (sl.q_count > 0) {
+    if (have) {
+      if (do_ka) {
+        e->phase_begin(T_FINAL);
+        launch_finalize_jk(nullptr, 0, e->d_kpart.d(), kp.n_splits, kp.ktile, n, kfac, nullptr, d_ka, e->stream);
+        e->phase_end(T_FINAL);
+        e->launches += 1;
+        ka_finalized = true;
+      }
       KPlan probe = plan_k(n, a.n_b, sl.q_count, e->workspace_limit, e->sm_count);
-      e->d_kpart.ensure(probe.kpart_elems * sizeof(double));  // stream-ordered: finalize above has consumed it
-      KPlan kpb{};
-      run_k(e, sl, d_cb, ldb, a.n_b, e->d_kpart.d(), kpb);
+      e->d_kpart.ensure(probe.kpart_elems * sizeof(double));  // stream-ordered: the finalize above has consumed it
+      if (fuse) e->d_gpart_b.ensure((size_t)probe.gamma_stride * sl.q_count * sizeof(double));
+      run_k(e, sl, d_cb, ldb, a.n_b, e->d_kpart.d(), fuse ? e->d_gpart_b.d() : nullptr, kpb);
+      e->phase_begin(T_FINAL);
       launch_finalize_jk(nullptr, 0, e->d_kpart.d(), kpb.n_splits, kpb.ktile, n, kfac, nullptr, d_kb, e->stream);
+      e->phase_end(T_FINAL);
       e->launches += 1;
     } else {
       CUDA_CHECK(cudaMemsetAsync(d_kb, 0, nn * sizeof(double), e->stream));
     }
   }
+
+  // ---- J
+  if (do_j && have) {
+    e->d_w.ensure((size_t)sl.L * sizeof(double));
+    e->d_gamma_partial.ensure(jp.gamma_partial_elems * sizeof(double));
+    e->d_gamma.ensure((size_t)sl.q_count * sizeof(double));
+    e->d_jpart.ensure(jp.j_partial_elems * sizeof(double));
+    e->phase_begin(T_J1);
+    launch_pack_density(d_density, n, e->d_w.d(), d_flag, e->stream);
+    launch_j_gamma(sl.packed.d(), sl.L, sl.q_count, e->d_w.d(), jp, e->d_gamma_partial.d(), e->d_gamma.d(), d_flag,
+                   e->stream);
+    e->launches += 3;
+    if (fuse) {
+      launch_gamma_from_x(e->d_gpart_a.d(), kp.gamma_stride, do_kb ? e->d_gpart_b.d() : nullptr, kpb.gamma_stride, kfac,
+                          sl.q_count, d_flag, e->d_gamma.d(), e->stream);
+      e->launches += 1;
+    }
+    e->phase_end(T_J1);
+    e->phase_begin(T_J2);
+    launch_j_accumulate(sl.packed.d(), sl.L, sl.q_count, e->d_gamma.d(), jp, e->d_jpart.d(), e->stream);
+    e->phase_end(T_J2);
+    e->launches += 1;
+  }
+
+  // ---- fixed-order sums of the partial buffers -> full matrices
+  e->phase_begin(T_FINAL);
+  if (have) {
+    const bool fin_k = do_ka && !ka_finalized;
+    if (do_j || fin_k) {
+      launch_finalize_jk(do_j ? e->d_jpart.d() : nullptr, jp.n_slices, fin_k ? e->d_kpart.d() : nullptr, kp.n_splits,
+                         kp.ktile ? kp.ktile : 64, n, kfac, do_j ? d_j : nullptr, fin_k ? d_ka : nullptr, e->stream);
+      e->launches += 1;
+    }
+  } else {
+    if (do_j) CUDA_CHECK(cudaMemsetAsync(d_j, 0, nn * sizeof(double), e->stream));
+    if (do_ka) CUDA_CHECK(cudaMemsetAsync(d_ka, 0, nn * sizeof(double), e->stream));
+  }
+  e->phase_end(T_FINAL);
   CUDA_CHECK(cudaGetLastError());
 
   // ---- multi-GPU: one sum all-reduce over whatever was built
@@ -514,7 +572,8 @@ int mqcb200_destroy(void *handle) {
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto &sl : e->slots) sl.packed.release();
   DevBuf *bufs[] = {&e->d_h, &e->d_density, &e->d_coeff, &e->d_coeff_b, &e->d_w, &e->d_ctf, &e->d_gamma_partial,
-                    &e->d_gamma, &e->d_jpart, &e->d_x, &e->d_kpart, &e->d_jk, &e->d_fock, &e->d_fock_b,
+                    &e->d_gamma, &e->d_jpart, &e->d_x, &e->d_kpart, &e->d_gpart_a, &e->d_gpart_b, &e->d_cep, &e->d_jk, &e->d_fock,
+                    &e->d_fock_b,
                     &e->d_scalar, &e->d_stage};
   for (DevBuf *b : bufs) b->release();
   for (auto &sp : e->spans) {

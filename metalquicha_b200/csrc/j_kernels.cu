@@ -21,7 +21,9 @@ constexpr int J_STEP = J_THREADS * 2;   // doubles covered by one CTA-wide 128-b
 __global__ void __launch_bounds__(J_THREADS) j_gamma_kernel(const double *__restrict__ packed, long long L,
                                                             int q_count, const double *__restrict__ w,
                                                             long long seg_len, int qblk0,
-                                                            double *__restrict__ gamma_partial) {
+                                                            double *__restrict__ gamma_partial,
+                                                            const int *__restrict__ skip_flag) {
+  if (skip_flag != nullptr && *skip_flag != 0) return;   // gamma comes from the half-transform
   const int seg = blockIdx.x;
   const int q0 = (qblk0 + blockIdx.y) * J_ROWS;
   const long long start = (long long)seg * seg_len;
@@ -87,12 +89,29 @@ __global__ void __launch_bounds__(J_THREADS) j_gamma_kernel(const double *__rest
 
 __global__ void __launch_bounds__(256) j_gamma_reduce_kernel(const double *__restrict__ gamma_partial,
                                                              int n_seg, int q_count,
-                                                             double *__restrict__ gamma) {
+                                                             double *__restrict__ gamma,
+                                                             const int *__restrict__ skip_flag) {
+  if (skip_flag != nullptr && *skip_flag != 0) return;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= q_count) return;
   double s = 0.0;
   for (int seg = 0; seg < n_seg; ++seg) s += gamma_partial[(size_t)seg * q_count + q];
   gamma[q] = s;
+}
+
+__global__ void __launch_bounds__(256) gamma_from_x_kernel(const double *__restrict__ part_a, int stride_a,
+                                                           const double *__restrict__ part_b, int stride_b,
+                                                           double factor, int q_count,
+                                                           const int *__restrict__ flag,
+                                                           double *__restrict__ gamma) {
+  if (*flag == 0) return;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= q_count) return;
+  double s = 0.0;
+  for (int k = 0; k < stride_a; ++k) s += part_a[(size_t)q * stride_a + k];
+  if (part_b != nullptr)
+    for (int k = 0; k < stride_b; ++k) s += part_b[(size_t)q * stride_b + k];
+  gamma[q] = factor * s;
 }
 
 constexpr int J2_QCHUNK = 1024;
@@ -161,17 +180,24 @@ JPlan plan_j(int n, int q_count) {
   return p;
 }
 
+void launch_gamma_from_x(const double *d_part_a, int stride_a, const double *d_part_b, int stride_b, double factor,
+                         int q_count, const int *d_flag, double *d_gamma, cudaStream_t s) {
+  gamma_from_x_kernel<<<(q_count + 255) / 256, 256, 0, s>>>(d_part_a, stride_a, d_part_b, stride_b, factor, q_count,
+                                                            d_flag, d_gamma);
+}
+
 void launch_j_gamma(const double *d_packed, long long L, int q_count, const double *d_w, const JPlan &plan,
-                    double *d_gamma_partial, double *d_gamma, cudaStream_t s) {
+                    double *d_gamma_partial, double *d_gamma, const int *d_skip_flag, cudaStream_t s) {
   long long seg_len = (L + plan.n_seg - 1) / plan.n_seg;
   seg_len = (seg_len + J_STEP - 1) / J_STEP * J_STEP;
   const int nqblk = (q_count + J_ROWS - 1) / J_ROWS;
   for (int b0 = 0; b0 < nqblk; b0 += 65535) {
     const int nb = nqblk - b0 < 65535 ? nqblk - b0 : 65535;
     dim3 grid((unsigned)plan.n_seg, (unsigned)nb);
-    j_gamma_kernel<<<grid, J_THREADS, 0, s>>>(d_packed, L, q_count, d_w, seg_len, b0, d_gamma_partial);
+    j_gamma_kernel<<<grid, J_THREADS, 0, s>>>(d_packed, L, q_count, d_w, seg_len, b0, d_gamma_partial, d_skip_flag);
   }
-  j_gamma_reduce_kernel<<<(q_count + 255) / 256, 256, 0, s>>>(d_gamma_partial, plan.n_seg, q_count, d_gamma);
+  j_gamma_reduce_kernel<<<(q_count + 255) / 256, 256, 0, s>>>(d_gamma_partial, plan.n_seg, q_count, d_gamma,
+                                                              d_skip_flag);
 }
 
 void launch_j_accumulate(const double *d_packed, long long L, int q_count, const double *d_gamma,

@@ -49,7 +49,7 @@ template <int NB>
 __global__ void __launch_bounds__(K_THREADS, 1)
 k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, int q_count,
                         const double *__restrict__ ctf, int nib, int n_ntiles, double *__restrict__ x, int nkc,
-                        int nmb) {
+                        int nmb, const double *__restrict__ cep, double *__restrict__ gamma_part) {
   using Cfg = HalfCfg<NB>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stage_base = reinterpret_cast<double *>(smem_raw);
@@ -200,6 +200,34 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
           const size_t off = (((size_t)q_s[sl] * nkc + kc_out) * nmb + mb) * 128 + ks_out * 32 + g * 4 + 2 * (t & 1);
           *reinterpret_cast<double2 *>(x + off) = make_double2(acc[sl * 2 + rh][j][0], acc[sl * 2 + rh][j][1]);
         }
+      }
+    }
+
+    // Coulomb vector for free when the density is the one these orbitals build:
+    // gamma_Q = sum B_Q.D = f * sum_{mu,i} X_Q[mu,i] C[mu,i]  (D = f C C^T).  Each warp reduces
+    // its 16-row slot against the C fragments and writes one partial per (Q, tile-row,
+    // N tile, N half); they are summed in fixed order by gamma_from_x_kernel.
+    if (gamma_part != nullptr) {
+      const int ntile = (int)(work % n_ntiles);
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        double sum = 0.0;
+        if (ok_s[sl]) {
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              const int ib = ib0 + wn * NB + j;
+              const double2 c2 = *reinterpret_cast<const double2 *>(
+                  cep + ((((size_t)tr_s[sl] * nib + ib) * 2 + rh) * 32 + lane) * 2);
+              sum = fma(acc[sl * 2 + rh][j][0], c2.x, sum);
+              sum = fma(acc[sl * 2 + rh][j][1], c2.y, sum);
+            }
+          }
+        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0 && ok_s[sl])
+          gamma_part[(((size_t)q_s[sl] * nt + tr_s[sl]) * n_ntiles + ntile) * 2 + wn] = sum;
       }
     }
   }
@@ -376,6 +404,7 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
   p.n_ktiles = p.n_panels * (p.n_panels + 1) / 2;
   const int slots = sm_count * (p.ktile == 128 ? 1 : 3);
   p.sm_count = sm_count;
+  p.gamma_stride = num_tiles(n) * p.n_ntiles * 2;
   p.x_elems_per_q = (size_t)p.nkc * p.nmb * 128;
   size_t qc = workspace_limit_bytes / (p.x_elems_per_q * sizeof(double));
   if (qc < 1) qc = 1;
@@ -406,26 +435,29 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
 
 template <int NB>
 static void launch_half_nb(const double *d_packed, long long L, int n, int q_count, const double *d_ctf,
-                           const KPlan &plan, double *d_x, cudaStream_t s) {
+                           const double *d_cep, const KPlan &plan, double *d_x, double *d_gamma_part,
+                           cudaStream_t s) {
   const int nt = num_tiles(n);
   const long long rows = (long long)q_count * nt;
   const long long n_work = (rows + K_SLOTS - 1) / K_SLOTS * plan.n_ntiles;
   const unsigned grid = (unsigned)(n_work < plan.sm_count ? n_work : plan.sm_count);
   k_half_transform_kernel<NB><<<grid, K_THREADS, HalfCfg<NB>::kSmemBytes, s>>>(
-      d_packed, L, nt, q_count, d_ctf, plan.nib, plan.n_ntiles, d_x, plan.nkc, plan.nmb);
+      d_packed, L, nt, q_count, d_ctf, plan.nib, plan.n_ntiles, d_x, plan.nkc, plan.nmb, d_cep,
+      d_cep ? d_gamma_part : nullptr);
 }
 
 void launch_k_half_transform(const double *d_packed, long long L, int n, int q_count, const double *d_ctf,
-                             const KPlan &plan, double *d_x, cudaStream_t s) {
+                             const double *d_cep, const KPlan &plan, double *d_x, double *d_gamma_part,
+                             cudaStream_t s) {
   switch (plan.nb) {
-    case 1: launch_half_nb<1>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
-    case 2: launch_half_nb<2>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
-    case 3: launch_half_nb<3>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
-    case 4: launch_half_nb<4>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
-    case 5: launch_half_nb<5>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
-    case 6: launch_half_nb<6>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
-    case 7: launch_half_nb<7>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
-    default: launch_half_nb<8>(d_packed, L, n, q_count, d_ctf, plan, d_x, s); break;
+    case 1: launch_half_nb<1>(d_packed, L, n, q_count, d_ctf, d_cep, plan, d_x, d_gamma_part, s); break;
+    case 2: launch_half_nb<2>(d_packed, L, n, q_count, d_ctf, d_cep, plan, d_x, d_gamma_part, s); break;
+    case 3: launch_half_nb<3>(d_packed, L, n, q_count, d_ctf, d_cep, plan, d_x, d_gamma_part, s); break;
+    case 4: launch_half_nb<4>(d_packed, L, n, q_count, d_ctf, d_cep, plan, d_x, d_gamma_part, s); break;
+    case 5: launch_half_nb<5>(d_packed, L, n, q_count, d_ctf, d_cep, plan, d_x, d_gamma_part, s); break;
+    case 6: launch_half_nb<6>(d_packed, L, n, q_count, d_ctf, d_cep, plan, d_x, d_gamma_part, s); break;
+    case 7: launch_half_nb<7>(d_packed, L, n, q_count, d_ctf, d_cep, plan, d_x, d_gamma_part, s); break;
+    default: launch_half_nb<8>(d_packed, L, n, q_count, d_ctf, d_cep, plan, d_x, d_gamma_part, s); break;
   }
 }
 

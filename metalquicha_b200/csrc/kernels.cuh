@@ -14,9 +14,10 @@ void launch_pack_tensor(const double *d_full, int n, int q_count, double *d_pack
 void launch_synth_tensor(double *d_packed, int n, int q_global_begin, int q_count, uint64_t seed,
                          double scale, cudaStream_t s);
 // w[L]: the density in packed order with the off-diagonal weight folded in.
-void launch_pack_density(const double *d_density, int n, double *d_w, cudaStream_t s);
+void launch_pack_density(const double *d_density, int n, double *d_w, const int *d_skip_flag, cudaStream_t s);
 // C(n x n_occ, ld) -> fragment-ordered, zero-padded [nt][nib][4][32] operand.
-void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib, double *d_ctf,
+// d_cep (nullable): the same coefficients in accumulator order, for the Coulomb-vector epilogue.
+void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib, double *d_ctf, double *d_cep,
                        cudaStream_t s);
 // Sum the J / K partial buffers in fixed order and unpack to full n x n matrices.
 // Either output may be null.  k_factor multiplies K (2 for RHF, 1 per spin).
@@ -45,8 +46,18 @@ struct JPlan {
   size_t j_partial_elems;      // n_slices * L
 };
 JPlan plan_j(int n, int q_count);
+// d_skip_flag (nullable device int): when it reads non-zero the pass is skipped on the
+// device (gamma comes from the half-transform instead, see launch_gamma_from_x).
 void launch_j_gamma(const double *d_packed, long long L, int q_count, const double *d_w,
-                    const JPlan &plan, double *d_gamma_partial, double *d_gamma, cudaStream_t s);
+                    const JPlan &plan, double *d_gamma_partial, double *d_gamma, const int *d_skip_flag,
+                    cudaStream_t s);
+// gamma[q] = factor * (sum of part_a[q][:] + sum of part_b[q][:]) if *d_flag, else untouched.
+void launch_gamma_from_x(const double *d_part_a, int stride_a, const double *d_part_b, int stride_b,
+                         double factor, int q_count, const int *d_flag, double *d_gamma, cudaStream_t s);
+// *d_flag = 1 iff max|D - f*(Ca Ca^T + Cb Cb^T)| <= 1e-13 * max(1, max|D|).  d_scratch: 16 bytes.
+void launch_density_consistency(const double *d_density, int n, const double *d_ca, int lda, int na,
+                                const double *d_cb, int ldb, int nb, double f, unsigned long long *d_scratch,
+                                int *d_flag, cudaStream_t s);
 void launch_j_accumulate(const double *d_packed, long long L, int q_count, const double *d_gamma,
                          const JPlan &plan, double *d_jpart, cudaStream_t s);
 
@@ -63,12 +74,15 @@ struct KPlan {
   int n_splits;    // split of the auxiliary range in the accumulation
   int q_chunk;     // auxiliary functions per half-transform launch
   int sm_count;    // persistent grid size of the half-transform
+  int gamma_stride;  // Coulomb-vector partials per auxiliary function written by the half-transform
   size_t x_elems_per_q;     // doubles of X per auxiliary function
   size_t kpart_elems;       // n_splits * n_ktiles * ktile*ktile
 };
 KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm_count);
+// d_gamma_part (nullable, needs d_cep): [q_count][plan.gamma_stride] partials of sum_{mu,i} X_Q[mu,i] C[mu,i].
 void launch_k_half_transform(const double *d_packed, long long L, int n, int q_count,
-                             const double *d_ctf, const KPlan &plan, double *d_x, cudaStream_t s);
+                             const double *d_ctf, const double *d_cep, const KPlan &plan, double *d_x,
+                             double *d_gamma_part, cudaStream_t s);
 void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, double *d_kpart,
                          int accumulate, cudaStream_t s);
 // One-time opt-in to large dynamic shared memory for the K kernels.

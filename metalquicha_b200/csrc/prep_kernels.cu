@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(256) synth_tensor_kernel(double *__restrict__ 
 }
 
 __global__ void __launch_bounds__(256) pack_density_kernel(const double *__restrict__ d, int n, int nt,
-                                                           double *__restrict__ w) {
+                                                           double *__restrict__ w,
+                                                           const int *__restrict__ skip_flag) {
+  if (skip_flag != nullptr && *skip_flag != 0) return;
   int tr, tc;
   tile_coords(blockIdx.x, nt, tr, tc);
   const int r = threadIdx.x & 15, c = threadIdx.x >> 4;
@@ -72,18 +74,29 @@ __global__ void __launch_bounds__(256) pack_density_kernel(const double *__restr
   w[(size_t)blockIdx.x * TILE_ELEMS + in_tile_offset(r, c)] = v;
 }
 
-// ctf[((kc*nib + ib)*4 + ks)*32 + g*4 + t] = C[nu = 16kc + 4ks + t][i = 8ib + g]
+// ctf[((kc*nib + ib)*4 + ks)*32 + g*4 + t] = C[nu = 16kc + 4ks + t][i = 8ib + g]      (B operand of the
+//                                                                     half-transform, fragment order)
+// cep[(((tr*nib + ib)*2 + rh)*32 + g*4 + t)*2 + e] = C[mu = 16tr + 8rh + g][i = 8ib + 2t + e]
+//   (the same matrix in m8n8 ACCUMULATOR order: the half-transform's epilogue dots its X tile with it,
+//    one coalesced 16-byte load per accumulator pair)
 __global__ void __launch_bounds__(256) pack_coeff_kernel(const double *__restrict__ coeff, int ldc, int n,
                                                          int n_occ, int nib, int nt,
-                                                         double *__restrict__ ctf) {
+                                                         double *__restrict__ ctf, double *__restrict__ cep) {
   const size_t total = (size_t)nt * nib * 128;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (size_t)gridDim.x * blockDim.x) {
-    const int t = e & 3, g = (e >> 2) & 7, ks = (e >> 5) & 3;
     const size_t blk = e >> 7;
     const int ib = (int)(blk % nib), kc = (int)(blk / nib);
-    const int nu = kc * 16 + ks * 4 + t, i = ib * 8 + g;
-    ctf[e] = (nu < n && i < n_occ) ? coeff[(size_t)nu + (size_t)ldc * i] : 0.0;
+    {
+      const int t = e & 3, g = (e >> 2) & 7, ks = (e >> 5) & 3;
+      const int nu = kc * 16 + ks * 4 + t, i = ib * 8 + g;
+      ctf[e] = (nu < n && i < n_occ) ? coeff[(size_t)nu + (size_t)ldc * i] : 0.0;
+    }
+    if (cep != nullptr) {
+      const int el = e & 1, t = (e >> 1) & 3, g = (e >> 3) & 7, rh = (e >> 6) & 1;
+      const int mu = kc * 16 + rh * 8 + g, i = ib * 8 + 2 * t + el;
+      cep[e] = (mu < n && i < n_occ) ? coeff[(size_t)mu + (size_t)ldc * i] : 0.0;
+    }
   }
 }
 
@@ -176,18 +189,61 @@ void launch_synth_tensor(double *d_packed, int n, int q_global_begin, int q_coun
   }
 }
 
-void launch_pack_density(const double *d_density, int n, double *d_w, cudaStream_t s) {
+void launch_pack_density(const double *d_density, int n, double *d_w, const int *d_skip_flag, cudaStream_t s) {
   const int nt = num_tiles(n);
-  pack_density_kernel<<<(unsigned)num_lower_tiles(nt), 256, 0, s>>>(d_density, n, nt, d_w);
+  pack_density_kernel<<<(unsigned)num_lower_tiles(nt), 256, 0, s>>>(d_density, n, nt, d_w, d_skip_flag);
 }
 
-void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib, double *d_ctf,
+// max |D - f (Ca Ca^T + Cb Cb^T)| and max |D| over the matrix (order-independent maxima,
+// so the result -- and with it the choice of Coulomb-vector path -- is deterministic).
+__global__ void __launch_bounds__(256) density_consistency_kernel(const double *__restrict__ d, int n,
+                                                                  const double *__restrict__ ca, int lda, int na,
+                                                                  const double *__restrict__ cb, int ldb, int nb,
+                                                                  double f, unsigned long long *__restrict__ out) {
+  const int mu = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int nu = blockIdx.y * 16 + (threadIdx.x >> 4);
+  double resid = 0.0, dabs = 0.0;
+  if (mu < n && nu < n) {
+    double s = 0.0;
+    for (int i = 0; i < na; ++i) s = fma(ca[(size_t)mu + (size_t)lda * i], ca[(size_t)nu + (size_t)lda * i], s);
+    for (int i = 0; i < nb; ++i) s = fma(cb[(size_t)mu + (size_t)ldb * i], cb[(size_t)nu + (size_t)ldb * i], s);
+    const double dv = d[(size_t)mu + (size_t)n * nu];
+    resid = fabs(dv - f * s);
+    dabs = fabs(dv);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    resid = fmax(resid, __shfl_xor_sync(0xffffffffu, resid, o));
+    dabs = fmax(dabs, __shfl_xor_sync(0xffffffffu, dabs, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, (unsigned long long)__double_as_longlong(resid));       // non-negative doubles order as integers
+    atomicMax(out + 1, (unsigned long long)__double_as_longlong(dabs));
+  }
+}
+
+__global__ void consistency_flag_kernel(const unsigned long long *__restrict__ in, int *__restrict__ flag) {
+  const double resid = __longlong_as_double((long long)in[0]);
+  const double dmax = __longlong_as_double((long long)in[1]);
+  *flag = (resid <= 1.0e-13 * fmax(1.0, dmax)) ? 1 : 0;
+}
+
+void launch_density_consistency(const double *d_density, int n, const double *d_ca, int lda, int na,
+                                const double *d_cb, int ldb, int nb, double f, unsigned long long *d_scratch,
+                                int *d_flag, cudaStream_t s) {
+  cudaMemsetAsync(d_scratch, 0, 2 * sizeof(unsigned long long), s);
+  const int nt = num_tiles(n);
+  dim3 grid((unsigned)nt, (unsigned)nt);
+  density_consistency_kernel<<<grid, 256, 0, s>>>(d_density, n, d_ca, lda, na, d_cb, ldb, nb, f, d_scratch);
+  consistency_flag_kernel<<<1, 1, 0, s>>>(d_scratch, d_flag);
+}
+
+void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib, double *d_ctf, double *d_cep,
                        cudaStream_t s) {
   const int nt = num_tiles(n);
   const size_t total = (size_t)nt * nib * 128;
   unsigned blocks = (unsigned)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_coeff_kernel<<<blocks, 256, 0, s>>>(d_coeff, ldc, n, n_occ, nib, nt, d_ctf);
+  pack_coeff_kernel<<<blocks, 256, 0, s>>>(d_coeff, ldc, n, n_occ, nib, nt, d_ctf, d_cep);
 }
 
 void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits, int ktile,

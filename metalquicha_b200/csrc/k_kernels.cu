@@ -262,7 +262,7 @@ struct SyrkCfg {
 template <int TILE>
 __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads, SyrkCfg<TILE>::kMinBlocks)
 k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count, int n_ktiles, int n_splits,
-                    double *__restrict__ kpart, int accumulate) {
+                    double *__restrict__ kpart, int accumulate, int ks_last) {
   using Cfg = SyrkCfg<TILE>;
   constexpr int PB = Cfg::kPanelBlocks;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -339,8 +339,13 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
     mbar_wait(&full_bar[0], 0);
     load_frags(fa[0], fb[0], 0, 0);
   }
+  int kc_idx = 0;                                   // position of this step inside its auxiliary function
   for (int step = 0; step < n_steps; ++step) {
     const int st = step % Cfg::kStages;
+    // the last 16-wide chunk of the padded occupied range may hold fewer than four valid
+    // 4-wide k-subs (n_occ = 241: one): the rest is zero padding, skip its DMMAs
+    const int ks_lim = (kc_idx == nkc - 1) ? ks_last : 4;
+    kc_idx = (kc_idx + 1 == nkc) ? 0 : kc_idx + 1;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       if (ks < 3) {
@@ -350,10 +355,12 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
         mbar_wait(&full_bar[st1], ((step + 1) / Cfg::kStages) & 1);
         load_frags(fa[0], fb[0], st1, 0);
       }
+      if (ks < ks_lim) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) dmma884(acc[m][j][0], acc[m][j][1], fa[ks & 1][m], fb[ks & 1][j]);
+          for (int j = 0; j < TN; ++j) dmma884(acc[m][j][0], acc[m][j][1], fa[ks & 1][m], fb[ks & 1][j]);
+      }
     }
     release_stage(&empty_bar[st], lane);
   }
@@ -397,6 +404,10 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
   p.nib = p.n_ntiles * 2 * p.nb;
   p.nkc = p.nib / 2;
   p.nmb = 2 * nt;
+  {
+    const int valid_last = (n_occ > 0 ? n_occ : 1) - 16 * (p.nkc - 1);   // may be <= 0 when N tiles pad a whole chunk
+    p.ks_last = valid_last >= 16 ? 4 : (valid_last <= 0 ? 0 : (valid_last + 3) / 4);
+  }
   // K tile edge: 64 trims the diagonal/padding waste of the SYRK; 128 halves the operand
   // traffic per flop and wins once n is large enough that the waste is small.
   p.ktile = ktile_override() ? ktile_override() : 64;
@@ -468,10 +479,10 @@ void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, doub
   const int splits = plan.n_splits;
   if (plan.ktile == 128)
     k_accumulate_kernel<128><<<(unsigned)(splits * plan.n_ktiles), SyrkCfg<128>::kThreads, SyrkCfg<128>::kSmemBytes, s>>>(
-        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, d_kpart, accumulate);
+        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, d_kpart, accumulate, plan.ks_last);
   else
     k_accumulate_kernel<64><<<(unsigned)(splits * plan.n_ktiles), SyrkCfg<64>::kThreads, SyrkCfg<64>::kSmemBytes, s>>>(
-        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, d_kpart, accumulate);
+        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, d_kpart, accumulate, plan.ks_last);
 }
 
 template <int NB>

@@ -68,6 +68,7 @@ struct KPlan {
   int nib;         // padded occupied count / 8   (= n_ntiles * 2 * nb)
   int nkc;         // padded occupied count / 16
   int nmb;         // 8-row blocks of X per (q, kc): 2*nt
+  int ks_last;     // valid 4-wide k-subs in the last 16-wide chunk of the occupied range
   int ktile;       // edge of the square K tiles of the accumulation (64 or 128)
   int n_panels;    // ktile-row panels of K
   int n_ktiles;    // lower-triangular ktile x ktile tiles of K

@@ -56,6 +56,11 @@ int mqcb200_get_stream(void *handle, void **stream);
 /* Upper bound (bytes) of the K half-transform scratch (cf. DF_EXCHANGE_BUFFER_BYTES,
  * backends/cuest/backend/mqc_cuest_integrals.f90:122). Default 4 GiB. */
 int mqcb200_set_workspace_limit(void *handle, size_t bytes);
+/* Packed-tensor size (bytes per handle) from which a build whose density equals f*C*C^T
+ * takes its Coulomb vector from the half-transform instead of a pass over the tensor.
+ * Default 256 MiB (below that the pass is cheaper than the extra launches); 0 = always try,
+ * SIZE_MAX = never. Either path gives the reference's J to rounding. */
+int mqcb200_set_fuse_threshold(void *handle, size_t bytes);
 
 /* ---- the fitted tensor ---------------------------------------------------
  * Replaces the host array `bmat(nao*nao, naux)` that run_libcint_rhf receives
@@ -175,6 +180,9 @@ int mqcb200_queue_destroy(void *queue);
 int mqcb200_set_profiling(void *handle, int on);
 int mqcb200_last_timings(void *handle, double ms[MQCB200_NUM_TIMERS]);
 int mqcb200_last_launches(void *handle, int *n_kernels);
+/* 1 when the last build took its Coulomb vector from the half-transform (the density was
+ * verified on the device to be f*C*C^T), 0 when it made the general pass over the tensor. */
+int mqcb200_last_gamma_fused(void *handle, int *fused);
 /* Device time (ms) of the whitening GEMM of the last mqcb200_set_tensor_from_3c and its
  * flop count 2*naux^2*L ("timed separately", not part of builds/sec). */
 int mqcb200_last_whiten(void *handle, double *ms, double *flops);

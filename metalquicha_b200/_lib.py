@@ -30,6 +30,7 @@ SIGNATURES = {
     "mqcb200_version": (c_int, []),
     "mqcb200_get_stream": (c_int, [c_void_p, POINTER(c_void_p)]),
     "mqcb200_set_workspace_limit": (c_int, [c_void_p, c_size_t]),
+    "mqcb200_set_fuse_threshold": (c_int, [c_void_p, c_size_t]),
     "mqcb200_set_tensor": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "mqcb200_set_tensor_shard": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mqcb200_set_tensor_from_3c": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -61,6 +62,7 @@ SIGNATURES = {
     "mqcb200_last_timings": (c_int, [c_void_p, _dp]),
     "mqcb200_last_launches": (c_int, [c_void_p, POINTER(c_int)]),
     "mqcb200_last_whiten": (c_int, [c_void_p, _dp, _dp]),
+    "mqcb200_last_gamma_fused": (c_int, [c_void_p, POINTER(c_int)]),
 }
 
 _lib = None

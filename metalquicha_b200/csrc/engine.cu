@@ -121,6 +121,7 @@ struct Engine {
   cudaStream_t stream = nullptr;
   TensorSlot slots[MQCB200_NUM_SLOTS];
   size_t workspace_limit = (size_t)4 << 30;
+  size_t fuse_threshold = (size_t)256 << 20;
 
   // per-build device operands and scratch (grow-only)
   DevBuf d_h, d_density, d_coeff, d_coeff_b, d_w, d_ctf, d_gamma_partial, d_gamma, d_jpart, d_x, d_kpart;
@@ -129,6 +130,7 @@ struct Engine {
   DevBuf d_jk;       // [J | K | K_beta] contiguous so one all-reduce covers them
   DevBuf d_fock, d_fock_b, d_scalar, d_stage;
   double whiten_ms = 0.0, whiten_flops = 0.0;
+  bool last_fuse_attempted = false;
   int last_n = 0;    // shape of the operands of the last build_fock (for last_energy)
   bool have_last_fock = false;
 
@@ -340,10 +342,11 @@ static void build(Engine *e, const BuildArgs &a) {
   // general pass over B instead.  Only worth its three extra tiny launches on tensors
   // whose pass over B is not itself tiny.
   const bool fuse = do_j && do_ka && have && fuse_gamma_enabled() &&
-                    (size_t)sl.L * (size_t)sl.q_count * sizeof(double) >= ((size_t)256 << 20) &&
+                    (size_t)sl.L * (size_t)sl.q_count * sizeof(double) >= e->fuse_threshold &&
                     (!a.two_spin || do_kb || a.n_b == 0);
   int *d_flag = nullptr;
   KPlan kp{}, kpb{};
+  e->last_fuse_attempted = fuse;
   if (fuse) {
     unsigned long long *scratch = reinterpret_cast<unsigned long long *>(static_cast<char *>(e->d_scalar.ptr) + 16);
     d_flag = reinterpret_cast<int *>(static_cast<char *>(e->d_scalar.ptr) + 32);
@@ -597,6 +600,12 @@ int mqcb200_set_workspace_limit(void *handle, size_t bytes) {
   GET_ENGINE(handle)
   if (bytes < ((size_t)1 << 20)) { g_last_error = "mqcb200: workspace limit below 1 MiB"; return MQCB200_FAIL; }
   e->workspace_limit = bytes;
+  return MQCB200_OK;
+}
+
+int mqcb200_set_fuse_threshold(void *handle, size_t bytes) {
+  GET_ENGINE(handle)
+  e->fuse_threshold = bytes;
   return MQCB200_OK;
 }
 
@@ -941,6 +950,22 @@ int mqcb200_last_whiten(void *handle, double *ms, double *flops) {
   *ms = e->whiten_ms;
   *flops = e->whiten_flops;
   return MQCB200_OK;
+}
+
+int mqcb200_last_gamma_fused(void *handle, int *fused) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!fused) throw Failure("mqcb200: null output pointer");
+  *fused = 0;
+  if (e->last_fuse_attempted) {
+    e->bind();
+    int flag = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&flag, static_cast<char *>(e->d_scalar.ptr) + 32, sizeof(int), cudaMemcpyDeviceToHost,
+                               e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    *fused = flag != 0 ? 1 : 0;
+  }
+  API_END
 }
 
 int mqcb200_last_launches(void *handle, int *n_kernels) {

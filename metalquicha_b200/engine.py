@@ -102,6 +102,9 @@ class B200FockEngine:
     def set_workspace_limit(self, n_bytes: int) -> None:
         _check(self._lib.mqcb200_set_workspace_limit(self._h, c_size_t(int(n_bytes))))
 
+    def set_fuse_threshold(self, n_bytes: int) -> None:
+        _check(self._lib.mqcb200_set_fuse_threshold(self._h, c_size_t(int(n_bytes))))
+
     # -- the fitted tensor ------------------------------------------------------------
     def set_tensor(self, b, n: int | None = None, slot: int = SLOT_FULL_RANGE) -> None:
         """``b`` is the reference's ``bmat(nao*nao, naux)`` (column-major)."""
@@ -348,6 +351,12 @@ class B200FockEngine:
         ms, fl = c_double(0.0), c_double(0.0)
         _check(self._lib.mqcb200_last_whiten(self._h, byref(ms), byref(fl)))
         return ms.value, fl.value
+
+    def last_gamma_fused(self) -> bool:
+        """True when the last build took its Coulomb vector from the half-transform."""
+        f = c_int(0)
+        _check(self._lib.mqcb200_last_gamma_fused(self._h, byref(f)))
+        return bool(f.value)
 
     def last_launches(self) -> int:
         n = c_int(0)

@@ -65,7 +65,15 @@ def test_linearity_invariance_and_definiteness(engine, c2):
 def test_fock_energy_and_bit_reproducibility(engine, c2):
     scale, h, d, c = c2
     f1 = engine.build_fock_df(h, d, c, NOCC)
+    assert engine.last_gamma_fused()            # 3.5 GB tensor, D = 2CC^T: gamma from the half-transform
     e1 = engine.last_energy()
+    try:                                        # ... and the general pass over B gives the same Fock matrix
+        engine.set_fuse_threshold(2 ** 62)
+        f_general = engine.build_fock_df(h, d, c, NOCC)
+        assert not engine.last_gamma_fused()
+        assert np.max(np.abs(f_general - f1)) <= 1e-11
+    finally:
+        engine.set_fuse_threshold(256 << 20)
     j, k = engine.build_jk(d, c, NOCC)
     assert np.max(np.abs(f1 - (h + j - 0.5 * k))) <= 1e-10
     assert abs(e1 - 0.5 * np.sum(d * (h + f1))) <= 1e-9 * max(1.0, abs(e1))

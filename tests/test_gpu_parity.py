@@ -230,6 +230,41 @@ def test_singular_metric_is_refused():
         metric_inverse_sqrt(np.zeros((5, 5)))
 
 
+@pytest.mark.parametrize("n,n_occ,naux", [(24, 5, 116), (72, 15, 340), (130, 33, 64), (200, 50, 96),
+                                          (257, 128, 12), (140, 130, 10), (33, 16, 40)])
+def test_coulomb_vector_from_half_transform(engine, n, n_occ, naux):
+    """When the density is the orbitals' own (D = 2CC^T) the engine may take gamma_Q from the
+    half-transformed tensor instead of a pass over B; forced on here (threshold 0).  Both
+    paths must give the oracle's J, and an inconsistent density must fall back by itself."""
+    b, h, density, coeff = synth.synth_problem(300 + n, n, n_occ, naux)
+    ref = oracle.build_fock_df(h, b, density, coeff, n_occ)
+    engine.set_tensor(b)
+    try:
+        engine.set_fuse_threshold(0)
+        f_fused = engine.build_fock_df(h, density, coeff, n_occ)
+        assert engine.last_gamma_fused()
+        assert _maxabs(f_fused, ref) <= TOL
+        assert np.array_equal(f_fused, engine.build_fock_df(h, density, coeff, n_occ))    # bit-reproducible
+        # a density that is NOT 2CC^T: the device-side check must refuse the shortcut
+        d2 = np.asfortranarray(density + 1e-9 * np.eye(n))
+        f2 = engine.build_fock_df(h, d2, coeff, n_occ)
+        assert not engine.last_gamma_fused()
+        assert _maxabs(f2, oracle.build_fock_df(h, b, d2, coeff, n_occ)) <= TOL
+        # two-spin: D_total = Ca Ca^T + Cb Cb^T
+        nb_ = max(1, n_occ - 1)
+        cb = synth.synth_orbitals(900 + n, n, nb_)
+        da, db = oracle.build_density_spin(coeff, n_occ), oracle.build_density_spin(cb, nb_)
+        j, ka, kb = engine.build_jk_uhf(da + db, coeff, n_occ, cb, nb_)
+        assert engine.last_gamma_fused()
+        j_ref, ka_ref, kb_ref = oracle.jk_df_uhf(b, da + db, coeff, n_occ, cb, nb_)
+        assert _maxabs(j, j_ref) <= TOL and _maxabs(ka, ka_ref) <= TOL and _maxabs(kb, kb_ref) <= TOL
+    finally:
+        engine.set_fuse_threshold(256 << 20)
+    f_general = engine.build_fock_df(h, density, coeff, n_occ)
+    assert not engine.last_gamma_fused()
+    assert _maxabs(f_general, ref) <= TOL and _maxabs(f_general, f_fused) <= 1e-11
+
+
 def test_device_generator_matches_host_generator(engine):
     """mqcb200_synth_tensor == synth.synth_tensor bit for bit (checked through a build)."""
     n, n_occ, naux = 70, 11, 50

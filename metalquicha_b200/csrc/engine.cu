@@ -187,6 +187,15 @@ static Engine *as_engine(void *h) {
   return e;
 }
 
+static bool fragment_path_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *env = getenv("MQCB200_NO_FRAGMENT_PATH");   // development switch: always take the general kernels
+    v = (env && env[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool fuse_gamma_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -335,6 +344,52 @@ static void build(Engine *e, const BuildArgs &a) {
   const bool have = sl.q_count > 0;
   const double kfac = a.two_spin ? 1.0 : 2.0;
   JPlan jp = plan_j(n, sl.q_count);
+  int n_jslices = jp.n_slices;          // partial-buffer shapes handed to finalize below
+  int n_ksplits = 0, ktile = 64;
+  bool ka_finalized = false;
+  const int max_occ = std::max(do_ka ? a.n_a : 0, do_kb ? a.n_b : 0);
+  const bool frag = have && (do_j || do_ka || do_kb) && fragment_path_enabled() &&
+                    fragment_path_applies(n, std::max(max_occ, 1));
+
+  if (frag) {
+    // ---- fragment-sized problem: J and K in ONE kernel, each slab read once
+    e->last_fuse_attempted = false;
+    auto run_frag = [&](const double *d_c, int ldc, int n_occ, bool wj, bool wk) {
+      FragPlan fp = plan_fragment(n, std::max(n_occ, 1), sl.q_count, e->sm_count);
+      if (wj) {
+        e->d_w.ensure((size_t)sl.L * sizeof(double));
+        e->d_jpart.ensure(fp.jpart_elems * sizeof(double));
+        launch_pack_density(d_density, n, e->d_w.d(), nullptr, e->stream);
+        e->launches += 1;
+      }
+      if (wk) {
+        e->d_ctf.ensure((size_t)fp.nt * fp.nib * 128 * sizeof(double));
+        e->d_kpart.ensure(fp.kpart_elems * sizeof(double));
+        launch_pack_coeff(d_c, ldc, n, n_occ, fp.nib, e->d_ctf.d(), nullptr, e->stream);
+        e->launches += 1;
+      }
+      e->phase_begin(wk ? T_K1 : T_J1);
+      launch_fragment_jk(sl.packed.d(), sl.q_count, e->d_w.d(), e->d_ctf.d(), fp, wj, wk, e->d_jpart.d(), e->d_kpart.d(),
+                         e->stream);
+      e->phase_end(wk ? T_K1 : T_J1);
+      e->launches += 1;
+      return fp;
+    };
+    FragPlan fa = run_frag(d_ca, lda, a.n_a, do_j, do_ka);
+    n_jslices = fa.grid;
+    n_ksplits = fa.grid;
+    if (do_kb) {
+      if (do_ka) {
+        launch_finalize_jk(nullptr, 0, e->d_kpart.d(), fa.grid, 64, n, kfac, nullptr, d_ka, e->stream);
+        e->launches += 1;
+        ka_finalized = true;
+      }
+      FragPlan fb = run_frag(d_cb, ldb, a.n_b, false, true);   // stream-ordered after the finalize above
+      launch_finalize_jk(nullptr, 0, e->d_kpart.d(), fb.grid, 64, n, kfac, nullptr, d_kb, e->stream);
+      e->launches += 1;
+    }
+    CUDA_CHECK(cudaGetLastError());
+  } else {
 
   // ---- Coulomb vector from the half-transform when the density is the orbitals' own
   // (D = f C C^T: every SCF iteration).  Decided on the device by an exact consistency
@@ -358,7 +413,6 @@ static void build(Engine *e, const BuildArgs &a) {
   }
 
   // ---- K (alpha / closed shell); K (beta) reuses the scratch after alpha has been finalized
-  bool ka_finalized = false;
   if (do_ka && have) {
     KPlan probe = plan_k(n, a.n_a, sl.q_count, e->workspace_limit, e->sm_count);
     e->d_kpart.ensure(probe.kpart_elems * sizeof(double));
@@ -410,13 +464,23 @@ static void build(Engine *e, const BuildArgs &a) {
     e->launches += 1;
   }
 
-  // ---- fixed-order sums of the partial buffers -> full matrices
+    n_ksplits = kp.n_splits;
+    ktile = kp.ktile ? kp.ktile : 64;
+  }
+
+  // ---- fixed-order sums of the partial buffers -> full matrices (and, for a closed-shell
+  // single-GPU build_fock, the Fock matrix itself in the same pass)
+  const bool will_reduce = sharded && e->n_ranks > 1;
+  const bool fused_assemble = a.assemble && !a.two_spin && !will_reduce && have;
+  double *d_fa_early = nullptr;
+  if (fused_assemble) d_fa_early = a.device_operands ? a.fock_a : (e->d_fock.ensure(nn * sizeof(double)), e->d_fock.d());
   e->phase_begin(T_FINAL);
   if (have) {
     const bool fin_k = do_ka && !ka_finalized;
-    if (do_j || fin_k) {
-      launch_finalize_jk(do_j ? e->d_jpart.d() : nullptr, jp.n_slices, fin_k ? e->d_kpart.d() : nullptr, kp.n_splits,
-                         kp.ktile ? kp.ktile : 64, n, kfac, do_j ? d_j : nullptr, fin_k ? d_ka : nullptr, e->stream);
+    if (do_j || fin_k || fused_assemble) {
+      launch_finalize_jk(do_j ? e->d_jpart.d() : nullptr, n_jslices, fin_k ? e->d_kpart.d() : nullptr, n_ksplits,
+                         ktile, n, kfac, do_j ? d_j : nullptr, fin_k ? d_ka : nullptr, e->stream,
+                         fused_assemble ? d_h : nullptr, a.j_scale, 0.5 * a.k_scale, d_fa_early);
       e->launches += 1;
     }
   } else {
@@ -447,8 +511,10 @@ static void build(Engine *e, const BuildArgs &a) {
     e->phase_begin(T_FINAL);
     const double kf_a = a.two_spin ? a.k_scale : 0.5 * a.k_scale;
     double *d_fa = a.device_operands ? a.fock_a : (e->d_fock.ensure(nn * sizeof(double)), e->d_fock.d());
-    launch_assemble_fock(d_h, do_j ? d_j : nullptr, do_ka ? d_ka : nullptr, a.j_scale, kf_a, n, d_fa, e->stream);
-    e->launches += 1;
+    if (!fused_assemble) {
+      launch_assemble_fock(d_h, do_j ? d_j : nullptr, do_ka ? d_ka : nullptr, a.j_scale, kf_a, n, d_fa, e->stream);
+      e->launches += 1;
+    }
     double *d_fb = nullptr;
     if (a.two_spin && a.fock_b) {
       d_fb = a.device_operands ? a.fock_b : (e->d_fock_b.ensure(nn * sizeof(double)), e->d_fock_b.d());

@@ -421,9 +421,10 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
   if (qc < 1) qc = 1;
   if (qc > (size_t)(q_count > 0 ? q_count : 1)) qc = (size_t)(q_count > 0 ? q_count : 1);
   p.q_chunk = (int)qc;
-  // Split of the contraction range over CTAs.  Cost model: waves * (steps per unit + a fixed
-  // per-CTA overhead worth ~12 pipeline steps); small problems get many short units, big
-  // ones whole waves.  The partial buffer is capped at 256 MiB.
+  // Split of the contraction range over CTAs.  Cost model (in pipeline steps of ~0.25 us):
+  // waves * (steps per unit + ~12 of fixed per-CTA overhead) + what the later fixed-order sum
+  // over the splits costs; small problems get a few dozen short units, big ones whole waves.
+  // The partial buffer is capped at 256 MiB.
   int best = 1;
   double best_cost = 1e300;
   const size_t tile_bytes = (size_t)p.ktile * p.ktile * sizeof(double);
@@ -432,7 +433,8 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
     const long long units = (long long)s * p.n_ktiles;
     const long long waves = (units + slots - 1) / slots;
     const long long steps = (long long)((p.q_chunk + s - 1) / s) * p.nkc;
-    const double cost = (double)waves * ((double)steps + 12.0);
+    // + the fixed-order sum over the splits in finalize_jk_kernel (~3/4 of a step per split)
+    const double cost = (double)waves * ((double)steps + 12.0) + 0.75 * (double)s;
     if (cost < best_cost * 0.995) { best_cost = cost; best = s; }
   }
   if (const char *e = getenv("MQCB200_KSPLITS")) {   // development override

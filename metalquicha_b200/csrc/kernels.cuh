@@ -21,8 +21,10 @@ void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib
                        cudaStream_t s);
 // Sum the J / K partial buffers in fixed order and unpack to full n x n matrices.
 // Either output may be null.  k_factor multiplies K (2 for RHF, 1 per spin).
+// With d_fock non-null the Fock matrix F = H + jf*J - kf*K is assembled in the same pass.
 void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits,
-                        int ktile, int n, double k_factor, double *d_j, double *d_k, cudaStream_t s);
+                        int ktile, int n, double k_factor, double *d_j, double *d_k, cudaStream_t s,
+                        const double *d_h = nullptr, double jf = 0.0, double kf = 0.0, double *d_fock = nullptr);
 // F = H + jf*J - kf*K  (any of J/K may be null == zero).
 void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf,
                           int n, double *d_fock, cudaStream_t s);
@@ -60,6 +62,19 @@ void launch_density_consistency(const double *d_density, int n, const double *d_
                                 int *d_flag, cudaStream_t s);
 void launch_j_accumulate(const double *d_packed, long long L, int q_count, const double *d_gamma,
                          const JPlan &plan, double *d_jpart, cudaStream_t s);
+
+// ---- fragment-sized problems: J and K in one pass over the tensor ---------------
+struct FragPlan {
+  int nt, nib, L, grid, n_ktiles;
+  size_t smem_bytes, jpart_elems, kpart_elems;
+};
+bool fragment_path_applies(int n, int n_occ);       // n <= 80 and n_occ <= 64
+FragPlan plan_fragment(int n, int n_occ, int q_count, int sm_count);
+// d_ctf: coefficients packed with nib = ceil(n_occ/8).  Partials: jpart [grid][L],
+// kpart [grid][n_ktiles][64*64] -- the layouts launch_finalize_jk sums (ktile = 64).
+void launch_fragment_jk(const double *d_packed, int q_count, const double *d_w, const double *d_ctf,
+                        const FragPlan &p, bool want_j, bool want_k, double *d_jpart, double *d_kpart,
+                        cudaStream_t s);
 
 // ---- K: half-transform + symmetric accumulation on the FP64 tensor pipe -----
 struct KPlan {

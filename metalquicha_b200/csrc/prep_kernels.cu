@@ -100,29 +100,63 @@ __global__ void __launch_bounds__(256) pack_coeff_kernel(const double *__restric
   }
 }
 
-// One thread per (mu, nu) of the full matrices; the lower-triangle element is the
-// source of both (mu,nu) and (nu,mu), so the outputs are exactly symmetric.
+// One CTA per 16x16 tile of the LOWER triangle, one thread per element (a >= b) with the
+// lanes running along b: both partial buffers are then read in 32-byte sectors that are
+// fully used (the K tiles are row-major in b, the packed J rows hold 4 consecutive b per
+// fragment row).  Each thread writes its value to (a,b) and to (b,a), so the outputs are
+// exactly symmetric.  The sums run over the partials in fixed order.
 __global__ void __launch_bounds__(256) finalize_jk_kernel(const double *__restrict__ jpart, int n_jslices,
                                                           long long L, const double *__restrict__ kpart,
                                                           int n_ksplits, int n_ktiles, int ktile_log2, int n, int nt,
                                                           double k_factor, double *__restrict__ j_out,
-                                                          double *__restrict__ k_out) {
-  const int mu = blockIdx.x * 16 + (threadIdx.x & 15);
-  const int nu = blockIdx.y * 16 + (threadIdx.x >> 4);
-  if (mu >= n || nu >= n) return;
-  const int a = mu > nu ? mu : nu, b = mu > nu ? nu : mu;  // a >= b
-  if (j_out) {
-    const size_t off = (size_t)tile_index(a >> 4, b >> 4, nt) * TILE_ELEMS + in_tile_offset(a & 15, b & 15);
+                                                          double *__restrict__ k_out,
+                                                          const double *__restrict__ h, double jf, double kf,
+                                                          double *__restrict__ fock_out) {
+  int tr, tc;
+  tile_coords(blockIdx.x, nt, tr, tc);
+  const int a = tr * 16 + (threadIdx.x >> 4);
+  const int b = tc * 16 + (threadIdx.x & 15);
+  if (a >= n || b >= n || a < b) return;
+  double jv = 0.0, kv = 0.0;
+  if (jpart) {
+    const size_t off = (size_t)blockIdx.x * TILE_ELEMS + in_tile_offset(a & 15, b & 15);
+    // fixed summation order; the loads are independent, so keep many of them in flight
     double s = 0.0;
-    for (int sl = 0; sl < n_jslices; ++sl) s += jpart[(size_t)sl * L + off];
-    j_out[(size_t)mu + (size_t)n * nu] = s;
+    int sl = 0;
+    for (; sl + 16 <= n_jslices; sl += 16) {
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = jpart[(size_t)(sl + u) * L + off];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s += v[u];
+    }
+    for (; sl < n_jslices; ++sl) s += jpart[(size_t)sl * L + off];
+    jv = s;
   }
-  if (k_out) {
+  if (kpart) {
     const int mp = a >> ktile_log2, np = b >> ktile_log2, msk = (1 << ktile_log2) - 1;
     const size_t off = ((size_t)(mp * (mp + 1) / 2 + np) << (2 * ktile_log2)) + ((size_t)(a & msk) << ktile_log2) + (b & msk);
     double s = 0.0;
-    for (int sp = 0; sp < n_ksplits; ++sp) s += kpart[((size_t)sp * n_ktiles << (2 * ktile_log2)) + off];
-    k_out[(size_t)mu + (size_t)n * nu] = k_factor * s;
+    const size_t stride = (size_t)n_ktiles << (2 * ktile_log2);
+    int sp = 0;
+    for (; sp + 16 <= n_ksplits; sp += 16) {
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = kpart[(size_t)(sp + u) * stride + off];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s += v[u];
+    }
+    for (; sp < n_ksplits; ++sp) s += kpart[(size_t)sp * stride + off];
+    kv = k_factor * s;
+  }
+  const size_t lo = (size_t)a + (size_t)n * b, up = (size_t)b + (size_t)n * a;
+  if (j_out) { j_out[lo] = jv; j_out[up] = jv; }
+  if (k_out) { k_out[lo] = kv; k_out[up] = kv; }
+  // optional fused assembly F = H + jf*J - kf*K (single-GPU closed-shell builds: saves a launch)
+  if (fock_out) {
+    const double g2 = jf * jv - kf * kv;
+    fock_out[lo] = (h ? h[lo] : 0.0) + g2;
+    if (lo != up) fock_out[up] = (h ? h[up] : 0.0) + g2;
   }
 }
 
@@ -247,13 +281,14 @@ void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib
 }
 
 void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits, int ktile,
-                        int n, double k_factor, double *d_j, double *d_k, cudaStream_t s) {
+                        int n, double k_factor, double *d_j, double *d_k, cudaStream_t s, const double *d_h,
+                        double jf, double kf, double *d_fock) {
   const int nt = num_tiles(n);
   const int ktile_log2 = ktile == 128 ? 7 : 6;
   const int np = (n + ktile - 1) / ktile;
-  dim3 grid((unsigned)nt, (unsigned)nt);
-  finalize_jk_kernel<<<grid, 256, 0, s>>>(d_jpart, n_jslices, packed_row_len(n), d_kpart, n_ksplits,
-                                          np * (np + 1) / 2, ktile_log2, n, nt, k_factor, d_j, d_k);
+  finalize_jk_kernel<<<(unsigned)num_lower_tiles(nt), 256, 0, s>>>(d_jpart, n_jslices, packed_row_len(n), d_kpart, n_ksplits,
+                                          np * (np + 1) / 2, ktile_log2, n, nt, k_factor, d_j, d_k, d_h, jf, kf,
+                                          d_fock);
 }
 
 void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf, int n,

@@ -230,12 +230,13 @@ def test_singular_metric_is_refused():
         metric_inverse_sqrt(np.zeros((5, 5)))
 
 
-@pytest.mark.parametrize("n,n_occ,naux", [(24, 5, 116), (72, 15, 340), (130, 33, 64), (200, 50, 96),
-                                          (257, 128, 12), (140, 130, 10), (33, 16, 40)])
+@pytest.mark.parametrize("n,n_occ,naux", [(81, 5, 116), (96, 65, 40), (130, 33, 64), (200, 50, 96),
+                                          (257, 128, 12), (140, 130, 10), (100, 16, 40)])
 def test_coulomb_vector_from_half_transform(engine, n, n_occ, naux):
     """When the density is the orbitals' own (D = 2CC^T) the engine may take gamma_Q from the
     half-transformed tensor instead of a pass over B; forced on here (threshold 0).  Both
-    paths must give the oracle's J, and an inconsistent density must fall back by itself."""
+    paths must give the oracle's J, and an inconsistent density must fall back by itself.
+    (Shapes are above the one-pass fragment kernel's range, n > 80 or n_occ > 64.)"""
     b, h, density, coeff = synth.synth_problem(300 + n, n, n_occ, naux)
     ref = oracle.build_fock_df(h, b, density, coeff, n_occ)
     engine.set_tensor(b)

@@ -54,6 +54,26 @@ struct DevBuf {
   double *d() const { return static_cast<double *>(ptr); }
 };
 
+// grow-only pinned host buffer (staging of small operand sets: one DMA instead of several)
+struct PinnedBuf {
+  void *ptr = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes) {
+    if (bytes <= cap) return;
+    if (ptr) CUDA_CHECK(cudaFreeHost(ptr));
+    ptr = nullptr;
+    cap = 0;
+    CUDA_CHECK(cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault));
+    cap = bytes;
+  }
+  void release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+  double *d() const { return static_cast<double *>(ptr); }
+};
+
 struct TensorSlot {
   DevBuf packed;
   int n = 0;
@@ -124,15 +144,19 @@ struct Engine {
   size_t fuse_threshold = (size_t)256 << 20;
 
   // per-build device operands and scratch (grow-only)
-  DevBuf d_h, d_density, d_coeff, d_coeff_b, d_w, d_ctf, d_gamma_partial, d_gamma, d_jpart, d_x, d_kpart;
+  DevBuf d_w, d_ctf, d_gamma_partial, d_gamma, d_jpart, d_x, d_kpart;
   DevBuf d_gpart_a, d_gpart_b;   // Coulomb-vector partials written by the half-transform
   DevBuf d_cep;                  // coefficients in accumulator order for that epilogue
   DevBuf d_jk;       // [J | K | K_beta] contiguous so one all-reduce covers them
-  DevBuf d_fock, d_fock_b, d_scalar, d_stage;
+  DevBuf d_scalar, d_stage, d_escratch;
+  DevBuf d_in;                   // [H | D | C_a | C_b] of a host-operand build, contiguous
+  DevBuf d_out;                  // [8 scalars | F_a | F_b] of a host-operand build, contiguous
+  PinnedBuf h_in, h_out;         // pinned staging for operand sets up to kSmallIoBytes
   double whiten_ms = 0.0, whiten_flops = 0.0;
   bool last_fuse_attempted = false;
   int last_n = 0;    // shape of the operands of the last build_fock (for last_energy)
   bool have_last_fock = false;
+  double last_energy_host = 0.0;   // E = 1/2 sum D (H + F) of the last closed-shell build_fock (host-operand path)
 
   // multi-GPU
   void *comm = nullptr;
@@ -205,6 +229,8 @@ static bool fuse_gamma_enabled() {
   return v == 1;
 }
 
+constexpr size_t kSmallIoBytes = (size_t)1 << 20;
+
 enum { T_UPLOAD = 0, T_J1, T_J2, T_K1, T_K2, T_FINAL, T_ALLREDUCE, T_DOWNLOAD };
 
 // ------------------------------- tensor set-up ------------------------------------------
@@ -264,16 +290,6 @@ struct BuildArgs {
   bool sync = true;
 };
 
-static void upload_matrix(Engine *e, DevBuf &dst, const double *src, int rows, int cols, int ld) {
-  dst.ensure(std::max<size_t>(16, (size_t)rows * cols * sizeof(double)));
-  if (cols == 0) return;
-  if (ld == rows)
-    CUDA_CHECK(cudaMemcpyAsync(dst.ptr, src, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  else
-    CUDA_CHECK(cudaMemcpy2DAsync(dst.ptr, (size_t)rows * sizeof(double), src, (size_t)ld * sizeof(double),
-                                 (size_t)rows * sizeof(double), cols, cudaMemcpyHostToDevice, e->stream));
-}
-
 static void run_k(Engine *e, const TensorSlot &sl, const double *d_coeff, int ldc, int n_occ, double *d_kpart_out,
                   double *d_gamma_part, KPlan &plan) {
   const int n = sl.n;
@@ -320,16 +336,41 @@ static void build(Engine *e, const BuildArgs &a) {
   // ---- operands on the device
   const double *d_h = nullptr, *d_density = nullptr, *d_ca = nullptr, *d_cb = nullptr;
   int lda = n, ldb = n;
+  bool small_io = false;
   {
     e->phase_begin(T_UPLOAD);
     if (a.device_operands) {
       d_h = a.h; d_density = a.density; d_ca = a.coeff_a; d_cb = a.coeff_b;
       lda = a.lda; ldb = a.ldb;
     } else {
-      if (a.h) { upload_matrix(e, e->d_h, a.h, n, n, n); d_h = e->d_h.d(); }
-      if (a.density) { upload_matrix(e, e->d_density, a.density, n, n, n); d_density = e->d_density.d(); }
-      if (a.want_k && a.n_a > 0) { upload_matrix(e, e->d_coeff, a.coeff_a, n, a.n_a, a.lda); d_ca = e->d_coeff.d(); }
-      if (a.want_k && a.two_spin && a.n_b > 0) { upload_matrix(e, e->d_coeff_b, a.coeff_b, n, a.n_b, a.ldb); d_cb = e->d_coeff_b.d(); }
+      // all operands go into one device block; small sets are first gathered in pinned
+      // memory so that the whole upload is ONE DMA (a fragment's 72x72 matrices would
+      // otherwise pay the driver's per-copy overhead three times)
+      const bool up_ca = a.want_k && a.n_a > 0, up_cb = a.want_k && a.two_spin && a.n_b > 0;
+      const size_t o_h = 0, o_d = o_h + (a.h ? nn : 0), o_ca = o_d + (a.density ? nn : 0);
+      const size_t o_cb = o_ca + (up_ca ? (size_t)n * a.n_a : 0), in_elems = o_cb + (up_cb ? (size_t)n * a.n_b : 0);
+      e->d_in.ensure(std::max<size_t>(16, in_elems * sizeof(double)));
+      double *din = e->d_in.d();
+      small_io = in_elems * sizeof(double) <= kSmallIoBytes;
+      auto put = [&](size_t off, const double *src, int rows, int cols, int ld) {
+        if (small_io) {
+          double *dst = e->h_in.d() + off;
+          if (ld == rows) std::memcpy(dst, src, (size_t)rows * cols * sizeof(double));
+          else for (int c = 0; c < cols; ++c) std::memcpy(dst + (size_t)rows * c, src + (size_t)ld * c, (size_t)rows * sizeof(double));
+        } else if (ld == rows) {
+          CUDA_CHECK(cudaMemcpyAsync(din + off, src, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        } else {
+          CUDA_CHECK(cudaMemcpy2DAsync(din + off, (size_t)rows * sizeof(double), src, (size_t)ld * sizeof(double),
+                                       (size_t)rows * sizeof(double), cols, cudaMemcpyHostToDevice, e->stream));
+        }
+      };
+      if (small_io) e->h_in.ensure(std::max<size_t>(16, in_elems * sizeof(double)));
+      if (a.h) { put(o_h, a.h, n, n, n); d_h = din + o_h; }
+      if (a.density) { put(o_d, a.density, n, n, n); d_density = din + o_d; }
+      if (up_ca) { put(o_ca, a.coeff_a, n, a.n_a, a.lda); d_ca = din + o_ca; }
+      if (up_cb) { put(o_cb, a.coeff_b, n, a.n_b, a.ldb); d_cb = din + o_cb; }
+      if (small_io && in_elems > 0)
+        CUDA_CHECK(cudaMemcpyAsync(din, e->h_in.ptr, in_elems * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     }
     e->phase_end(T_UPLOAD);
   }
@@ -472,8 +513,15 @@ static void build(Engine *e, const BuildArgs &a) {
   // single-GPU build_fock, the Fock matrix itself in the same pass)
   const bool will_reduce = sharded && e->n_ranks > 1;
   const bool fused_assemble = a.assemble && !a.two_spin && !will_reduce && have;
+  // host-operand builds put their results in one block: [8 scalars | F_a | F_b]
+  double *d_fa_host = nullptr, *d_fb_host = nullptr;
+  if (!a.device_operands && (a.assemble || a.combine)) {
+    e->d_out.ensure((8 + 2 * nn) * sizeof(double));
+    d_fa_host = e->d_out.d() + 8;
+    d_fb_host = d_fa_host + nn;
+  }
   double *d_fa_early = nullptr;
-  if (fused_assemble) d_fa_early = a.device_operands ? a.fock_a : (e->d_fock.ensure(nn * sizeof(double)), e->d_fock.d());
+  if (fused_assemble) d_fa_early = a.device_operands ? a.fock_a : d_fa_host;
   e->phase_begin(T_FINAL);
   if (have) {
     const bool fin_k = do_ka && !ka_finalized;
@@ -507,43 +555,78 @@ static void build(Engine *e, const BuildArgs &a) {
 
   // ---- assemble and return
   e->have_last_fock = false;
+  struct Pending { double *dst; const double *src; size_t bytes; };
+  Pending pending[4];
+  int n_pending = 0;
+  bool energy_pending = false;
   if (a.assemble) {
     e->phase_begin(T_FINAL);
     const double kf_a = a.two_spin ? a.k_scale : 0.5 * a.k_scale;
-    double *d_fa = a.device_operands ? a.fock_a : (e->d_fock.ensure(nn * sizeof(double)), e->d_fock.d());
+    double *d_fa = a.device_operands ? a.fock_a : d_fa_host;
     if (!fused_assemble) {
       launch_assemble_fock(d_h, do_j ? d_j : nullptr, do_ka ? d_ka : nullptr, a.j_scale, kf_a, n, d_fa, e->stream);
       e->launches += 1;
     }
     double *d_fb = nullptr;
     if (a.two_spin && a.fock_b) {
-      d_fb = a.device_operands ? a.fock_b : (e->d_fock_b.ensure(nn * sizeof(double)), e->d_fock_b.d());
+      d_fb = a.device_operands ? a.fock_b : d_fb_host;
       launch_assemble_fock(d_h, do_j ? d_j : nullptr, do_kb ? d_kb : nullptr, a.j_scale, a.k_scale, n, d_fb, e->stream);
       e->launches += 1;
     }
     e->phase_end(T_FINAL);
     if (!a.device_operands) {
+      const bool with_energy = !a.two_spin && d_h && d_density;
+      if (with_energy) {
+        // the energy the caller takes next (assemble_fock, rhf.f90:1207) rides along: one tiny
+        // kernel and 8 bytes in the same stream instead of a second round trip
+        launch_energy(d_density, d_h, d_fa, n, e->d_escratch.d(), e->d_out.d(), e->stream);
+        e->launches += 1;
+        e->last_n = n;
+        e->have_last_fock = true;
+      }
       e->phase_begin(T_DOWNLOAD);
-      CUDA_CHECK(cudaMemcpyAsync(a.fock_a, d_fa, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-      if (d_fb) CUDA_CHECK(cudaMemcpyAsync(a.fock_b, d_fb, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      if (small_io) {
+        // [scalars | F_a | F_b] in one DMA to pinned memory, handed to the caller after the sync
+        const size_t out_elems = 8 + nn * (d_fb ? 2 : 1);
+        e->h_out.ensure(out_elems * sizeof(double));
+        CUDA_CHECK(cudaMemcpyAsync(e->h_out.ptr, e->d_out.ptr, out_elems * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        pending[n_pending++] = {a.fock_a, e->h_out.d() + 8, nn * sizeof(double)};
+        if (d_fb) pending[n_pending++] = {a.fock_b, e->h_out.d() + 8 + nn, nn * sizeof(double)};
+        energy_pending = with_energy;
+      } else {
+        CUDA_CHECK(cudaMemcpyAsync(a.fock_a, d_fa, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (d_fb) CUDA_CHECK(cudaMemcpyAsync(a.fock_b, d_fb, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (with_energy)
+          CUDA_CHECK(cudaMemcpyAsync(&e->last_energy_host, e->d_out.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      }
       e->phase_end(T_DOWNLOAD);
-      if (!a.two_spin && d_h && d_density) { e->last_n = n; e->have_last_fock = true; }
     }
   } else if (a.combine) {
     e->phase_begin(T_FINAL);
-    e->d_fock.ensure(nn * sizeof(double));
     launch_combine_g(do_j ? d_j : nullptr, do_ka ? d_ka : nullptr, do_kb ? d_kb : nullptr, a.ka_coef, a.kb_coef, n,
-                     e->d_fock.d(), e->stream);
+                     d_fa_host, e->stream);
     e->launches += 1;
     e->phase_end(T_FINAL);
     e->phase_begin(T_DOWNLOAD);
-    CUDA_CHECK(cudaMemcpyAsync(a.fock_a, e->d_fock.d(), nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(a.fock_a, d_fa_host, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     e->phase_end(T_DOWNLOAD);
   } else if (!a.device_operands) {
     e->phase_begin(T_DOWNLOAD);
-    if (a.j && do_j) CUDA_CHECK(cudaMemcpyAsync(a.j, d_j, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    if (a.k_a && do_ka) CUDA_CHECK(cudaMemcpyAsync(a.k_a, d_ka, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    if (a.k_b && do_kb) CUDA_CHECK(cudaMemcpyAsync(a.k_b, d_kb, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    const bool get_j = a.j && do_j, get_ka = a.k_a && do_ka, get_kb = a.k_b && do_kb;
+    if (small_io && (get_j || get_ka || get_kb)) {
+      // J, K_a, K_b are adjacent on the device: one DMA over the span that is wanted
+      const size_t first = get_j ? 0 : (get_ka ? 1 : 2), last = get_kb ? 3 : (get_ka ? 2 : 1);
+      e->h_out.ensure((last - first) * nn * sizeof(double));
+      CUDA_CHECK(cudaMemcpyAsync(e->h_out.ptr, d_j + first * nn, (last - first) * nn * sizeof(double),
+                                 cudaMemcpyDeviceToHost, e->stream));
+      if (get_j) pending[n_pending++] = {a.j, e->h_out.d(), nn * sizeof(double)};
+      if (get_ka) pending[n_pending++] = {a.k_a, e->h_out.d() + (1 - first) * nn, nn * sizeof(double)};
+      if (get_kb) pending[n_pending++] = {a.k_b, e->h_out.d() + (2 - first) * nn, nn * sizeof(double)};
+    } else {
+      if (get_j) CUDA_CHECK(cudaMemcpyAsync(a.j, d_j, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      if (get_ka) CUDA_CHECK(cudaMemcpyAsync(a.k_a, d_ka, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      if (get_kb) CUDA_CHECK(cudaMemcpyAsync(a.k_b, d_kb, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    }
     // K of an empty closed-shell / alpha channel is zero, not "untouched": only the two-spin
     // beta channel has skip semantics (mqc_cuest_integrals.f90:1694-1701)
     e->phase_end(T_DOWNLOAD);
@@ -551,6 +634,8 @@ static void build(Engine *e, const BuildArgs &a) {
   CUDA_CHECK(cudaGetLastError());
   if (a.sync) {
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < n_pending; ++i) std::memcpy(pending[i].dst, pending[i].src, pending[i].bytes);
+    if (energy_pending) e->last_energy_host = e->h_out.d()[0];
     if (!a.device_operands && !a.assemble && a.k_a && a.want_k && !do_ka) std::memset(a.k_a, 0, nn * sizeof(double));
   }
 }
@@ -623,6 +708,8 @@ int mqcb200_create(int device_rank, void **handle) {
     e->sm_count = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->d_scalar.ensure(64);
+    e->d_escratch.ensure(160 * sizeof(double));
+    CUDA_CHECK(cudaMemsetAsync(e->d_escratch.ptr, 0, 160 * sizeof(double), e->stream));
     configure_kernels();
     CUDA_CHECK(cudaGetLastError());
   } catch (...) {
@@ -640,11 +727,12 @@ int mqcb200_destroy(void *handle) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto &sl : e->slots) sl.packed.release();
-  DevBuf *bufs[] = {&e->d_h, &e->d_density, &e->d_coeff, &e->d_coeff_b, &e->d_w, &e->d_ctf, &e->d_gamma_partial,
-                    &e->d_gamma, &e->d_jpart, &e->d_x, &e->d_kpart, &e->d_gpart_a, &e->d_gpart_b, &e->d_cep, &e->d_jk, &e->d_fock,
-                    &e->d_fock_b,
-                    &e->d_scalar, &e->d_stage};
+  DevBuf *bufs[] = {&e->d_w, &e->d_ctf, &e->d_gamma_partial,
+                    &e->d_gamma, &e->d_jpart, &e->d_x, &e->d_kpart, &e->d_gpart_a, &e->d_gpart_b, &e->d_cep, &e->d_jk, &e->d_in, &e->d_out,
+                    &e->d_scalar, &e->d_stage, &e->d_escratch};
   for (DevBuf *b : bufs) b->release();
+  e->h_in.release();
+  e->h_out.release();
   for (auto &sp : e->spans) {
     cudaEventDestroy(sp.a);
     cudaEventDestroy(sp.b);
@@ -896,11 +984,7 @@ int mqcb200_last_energy(void *handle, double *e_elec) {
   API_BEGIN
   if (!e_elec) throw Failure("mqcb200: null energy pointer");
   if (!e->have_last_fock) throw Failure("mqcb200: no closed-shell build_fock has run on this handle yet");
-  e->bind();
-  launch_energy(e->d_density.d(), e->d_h.d(), e->d_fock.d(), e->last_n, e->d_scalar.d(), e->stream);
-  CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaMemcpyAsync(e_elec, e->d_scalar.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  *e_elec = e->last_energy_host;   // computed on the device by that build, already on the host
   API_END
 }
 

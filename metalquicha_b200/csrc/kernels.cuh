@@ -31,9 +31,10 @@ void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_
 // G = J + ka*Ka + kb*Kb (null operands are skipped).
 void launch_combine_g(const double *d_j, const double *d_ka, const double *d_kb, double ka, double kb, int n,
                       double *d_g, cudaStream_t s);
-// e = 1/2 sum D (H + F), deterministic single-block reduction into d_out[0].
+// e = 1/2 sum D (H + F) into d_out[0]; fixed-order two-level reduction.  d_scratch: 129 doubles,
+// zero-initialised once (the kernel leaves its counter at zero).
 void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n,
-                   double *d_out, cudaStream_t s);
+                   double *d_scratch, double *d_out, cudaStream_t s);
 
 // ---- whitening: Bp = half . Tp on the packed tensor (build_df_tensor's GEMM) ----
 size_t whiten_half_elems(int naux);   // doubles of the fragment-ordered copy of `half`

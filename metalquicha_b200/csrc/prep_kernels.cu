@@ -183,19 +183,36 @@ __global__ void __launch_bounds__(256) combine_g_kernel(const double *__restrict
   }
 }
 
-__global__ void __launch_bounds__(1024) energy_kernel(const double *__restrict__ d, const double *__restrict__ h,
-                                                      const double *__restrict__ f, size_t nn,
-                                                      double *__restrict__ out) {
-  __shared__ double red[32];
+// E = 1/2 sum D (H + F).  Each block reduces a fixed slice of the matrix to one partial; the
+// block that finishes last adds the partials in index order, so the result does not depend
+// on scheduling.  scratch: [128 partial slots | 1 counter at a FIXED slot (left at 0)].
+__global__ void __launch_bounds__(256) energy_kernel(const double *__restrict__ d, const double *__restrict__ h,
+                                                     const double *__restrict__ f, size_t nn,
+                                                     double *__restrict__ scratch, double *__restrict__ out) {
+  __shared__ double red[8];
+  __shared__ bool last;
   double s = 0.0;
-  for (size_t e = threadIdx.x; e < nn; e += blockDim.x) s += d[e] * (h[e] + f[e]);
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.x * blockDim.x)
+    s += d[e] * (h[e] + f[e]);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    s = red[threadIdx.x];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) out[0] = 0.5 * s;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    scratch[blockIdx.x] = t;
+    __threadfence();
+    unsigned int *counter = reinterpret_cast<unsigned int *>(scratch + 128);
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) t += reinterpret_cast<volatile double *>(scratch)[b];
+    out[0] = 0.5 * t;
+    *reinterpret_cast<unsigned int *>(scratch + 128) = 0u;   // ready for the next build
   }
 }
 
@@ -307,9 +324,13 @@ void launch_combine_g(const double *d_j, const double *d_ka, const double *d_kb,
   combine_g_kernel<<<blocks, 256, 0, s>>>(d_j, d_ka, d_kb, ka, kb, nn, d_g);
 }
 
-void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n, double *d_out,
-                   cudaStream_t s) {
-  energy_kernel<<<1, 1024, 0, s>>>(d_density, d_h, d_fock, (size_t)n * n, d_out);
+void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n, double *d_scratch,
+                   double *d_out, cudaStream_t s) {
+  const size_t nn = (size_t)n * n;
+  unsigned blocks = (unsigned)((nn + 4095) / 4096);
+  if (blocks > 128) blocks = 128;
+  if (blocks < 1) blocks = 1;
+  energy_kernel<<<blocks, 256, 0, s>>>(d_density, d_h, d_fock, nn, d_scratch, d_out);
 }
 
 }  // namespace mqcb200

@@ -139,6 +139,8 @@ struct Engine {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H and D ride up here while the K kernels (which need only C) run
+  cudaEvent_t ev_late_upload = nullptr;
   TensorSlot slots[MQCB200_NUM_SLOTS];
   size_t workspace_limit = (size_t)4 << 30;
   size_t fuse_threshold = (size_t)256 << 20;
@@ -337,6 +339,17 @@ static void build(Engine *e, const BuildArgs &a) {
   const double *d_h = nullptr, *d_density = nullptr, *d_ca = nullptr, *d_cb = nullptr;
   int lda = n, ldb = n;
   bool small_io = false;
+  const double *late_h = nullptr, *late_d = nullptr;   // host H / D still to be uploaded (large operand sets)
+  size_t late_oh = 0, late_od = 0;
+  auto late_upload = [&]() {
+    if (!late_h && !late_d) return;
+    double *din = e->d_in.d();
+    if (late_d) CUDA_CHECK(cudaMemcpyAsync(din + late_od, late_d, nn * sizeof(double), cudaMemcpyHostToDevice, e->copy_stream));
+    if (late_h) CUDA_CHECK(cudaMemcpyAsync(din + late_oh, late_h, nn * sizeof(double), cudaMemcpyHostToDevice, e->copy_stream));
+    CUDA_CHECK(cudaEventRecord(e->ev_late_upload, e->copy_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_late_upload, 0));
+    late_h = late_d = nullptr;
+  };
   {
     e->phase_begin(T_UPLOAD);
     if (a.device_operands) {
@@ -352,23 +365,33 @@ static void build(Engine *e, const BuildArgs &a) {
       e->d_in.ensure(std::max<size_t>(16, in_elems * sizeof(double)));
       double *din = e->d_in.d();
       small_io = in_elems * sizeof(double) <= kSmallIoBytes;
-      auto put = [&](size_t off, const double *src, int rows, int cols, int ld) {
+      auto put = [&](size_t off, const double *src, int rows, int cols, int ld, cudaStream_t st) {
         if (small_io) {
           double *dst = e->h_in.d() + off;
           if (ld == rows) std::memcpy(dst, src, (size_t)rows * cols * sizeof(double));
           else for (int c = 0; c < cols; ++c) std::memcpy(dst + (size_t)rows * c, src + (size_t)ld * c, (size_t)rows * sizeof(double));
         } else if (ld == rows) {
-          CUDA_CHECK(cudaMemcpyAsync(din + off, src, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+          CUDA_CHECK(cudaMemcpyAsync(din + off, src, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, st));
         } else {
           CUDA_CHECK(cudaMemcpy2DAsync(din + off, (size_t)rows * sizeof(double), src, (size_t)ld * sizeof(double),
-                                       (size_t)rows * sizeof(double), cols, cudaMemcpyHostToDevice, e->stream));
+                                       (size_t)rows * sizeof(double), cols, cudaMemcpyHostToDevice, st));
         }
       };
       if (small_io) e->h_in.ensure(std::max<size_t>(16, in_elems * sizeof(double)));
-      if (a.h) { put(o_h, a.h, n, n, n); d_h = din + o_h; }
-      if (a.density) { put(o_d, a.density, n, n, n); d_density = din + o_d; }
-      if (up_ca) { put(o_ca, a.coeff_a, n, a.n_a, a.lda); d_ca = din + o_ca; }
-      if (up_cb) { put(o_cb, a.coeff_b, n, a.n_b, a.ldb); d_cb = din + o_cb; }
+      // The coefficients go first: the K kernels need nothing else.  For operand sets too
+      // large for the single staged DMA, H and D are issued later (late_upload below), after
+      // the K kernels have been launched, on a second stream -- their transfer (and, for
+      // pageable host memory, the driver's staging) then overlaps the exchange build.
+      if (up_ca) { put(o_ca, a.coeff_a, n, a.n_a, a.lda, e->stream); d_ca = din + o_ca; }
+      if (up_cb) { put(o_cb, a.coeff_b, n, a.n_b, a.ldb, e->stream); d_cb = din + o_cb; }
+      if (a.h) d_h = din + o_h;
+      if (a.density) d_density = din + o_d;
+      late_h = a.h; late_d = a.density; late_oh = o_h; late_od = o_d;
+      if (small_io) {
+        if (a.h) put(o_h, a.h, n, n, n, e->stream);
+        if (a.density) put(o_d, a.density, n, n, n, e->stream);
+        late_h = late_d = nullptr;
+      }
       if (small_io && in_elems > 0)
         CUDA_CHECK(cudaMemcpyAsync(din, e->h_in.ptr, in_elems * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     }
@@ -395,6 +418,7 @@ static void build(Engine *e, const BuildArgs &a) {
   if (frag) {
     // ---- fragment-sized problem: J and K in ONE kernel, each slab read once
     e->last_fuse_attempted = false;
+    late_upload();
     auto run_frag = [&](const double *d_c, int ldc, int n_occ, bool wj, bool wk) {
       FragPlan fp = plan_fragment(n, std::max(n_occ, 1), sl.q_count, e->sm_count);
       if (wj) {
@@ -443,16 +467,6 @@ static void build(Engine *e, const BuildArgs &a) {
   int *d_flag = nullptr;
   KPlan kp{}, kpb{};
   e->last_fuse_attempted = fuse;
-  if (fuse) {
-    unsigned long long *scratch = reinterpret_cast<unsigned long long *>(static_cast<char *>(e->d_scalar.ptr) + 16);
-    d_flag = reinterpret_cast<int *>(static_cast<char *>(e->d_scalar.ptr) + 32);
-    e->phase_begin(T_J1);
-    launch_density_consistency(d_density, n, d_ca, lda, a.n_a, do_kb ? d_cb : nullptr, ldb, do_kb ? a.n_b : 0, kfac,
-                               scratch, d_flag, e->stream);
-    e->phase_end(T_J1);
-    e->launches += 2;
-  }
-
   // ---- K (alpha / closed shell); K (beta) reuses the scratch after alpha has been finalized
   if (do_ka && have) {
     KPlan probe = plan_k(n, a.n_a, sl.q_count, e->workspace_limit, e->sm_count);
@@ -480,6 +494,18 @@ static void build(Engine *e, const BuildArgs &a) {
     } else {
       CUDA_CHECK(cudaMemsetAsync(d_kb, 0, nn * sizeof(double), e->stream));
     }
+  }
+
+  // ---- H and D arrive now (they were not needed by the exchange kernels launched above)
+  late_upload();
+  if (fuse) {
+    unsigned long long *scratch = reinterpret_cast<unsigned long long *>(static_cast<char *>(e->d_scalar.ptr) + 16);
+    d_flag = reinterpret_cast<int *>(static_cast<char *>(e->d_scalar.ptr) + 32);
+    e->phase_begin(T_J1);
+    launch_density_consistency(d_density, n, d_ca, lda, a.n_a, do_kb ? d_cb : nullptr, ldb, do_kb ? a.n_b : 0, kfac,
+                               scratch, d_flag, e->stream);
+    e->phase_end(T_J1);
+    e->launches += 2;
   }
 
   // ---- J
@@ -707,6 +733,8 @@ int mqcb200_create(int device_rank, void **handle) {
       throw Failure(std::string("mqcb200: device '") + prop.name + "' is not sm_100-class; the kernels are built for sm_100a only");
     e->sm_count = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_late_upload, cudaEventDisableTiming));
     e->d_scalar.ensure(64);
     e->d_escratch.ensure(160 * sizeof(double));
     CUDA_CHECK(cudaMemsetAsync(e->d_escratch.ptr, 0, 160 * sizeof(double), e->stream));
@@ -737,6 +765,8 @@ int mqcb200_destroy(void *handle) {
     cudaEventDestroy(sp.a);
     cudaEventDestroy(sp.b);
   }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->ev_late_upload) cudaEventDestroy(e->ev_late_upload);
   if (e->stream) cudaStreamDestroy(e->stream);
   e->magic = 0;
   delete e;

@@ -21,7 +21,8 @@ module mqc_b200_iface
 
    public :: mqcb200_create, mqcb200_destroy, mqcb200_last_error, mqcb200_version
    public :: mqcb200_set_workspace_limit
-   public :: mqcb200_set_tensor, mqcb200_set_tensor_shard, mqcb200_clear_tensor
+   public :: mqcb200_set_tensor, mqcb200_set_tensor_shard, mqcb200_set_tensor_from_3c, mqcb200_clear_tensor
+   public :: mqcb200_build_g_two_factor
    public :: mqcb200_build_fock, mqcb200_build_jk, mqcb200_build_jk_uhf, mqcb200_build_fock_uhf
    public :: mqcb200_last_energy
    public :: mqcb200_comm_unique_id, mqcb200_comm_init, mqcb200_comm_destroy
@@ -75,6 +76,25 @@ module mqc_b200_iface
          type(c_ptr), value :: handle
          integer(c_int), value :: slot, n, naux_total, q_begin, q_count
          real(c_double), intent(in) :: b_shard(*)
+         integer(c_int) :: status
+      end function
+      function mqcb200_set_tensor_from_3c(handle, slot, n, naux, three, half) &
+         bind(C, name="mqcb200_set_tensor_from_3c") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot, n, naux
+         real(c_double), intent(in) :: three(*)      !! (nao*nao, naux), build_df_tensor's `three`
+         real(c_double), intent(in) :: half(*)       !! (naux, naux), metric_inverse_sqrt's result
+         integer(c_int) :: status
+      end function
+      function mqcb200_build_g_two_factor(handle, slot, density, coeff_a, lda, n_a, coeff_b, ldb, n_b, ka, kb, g) &
+         bind(C, name="mqcb200_build_g_two_factor") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot, lda, n_a, ldb, n_b
+         real(c_double), intent(in) :: density(*), coeff_a(*), coeff_b(*)
+         real(c_double), value :: ka, kb
+         real(c_double), intent(out) :: g(*)
          integer(c_int) :: status
       end function
       function mqcb200_clear_tensor(handle, slot) bind(C, name="mqcb200_clear_tensor") result(status)

@@ -58,7 +58,7 @@ int mqcb200_get_stream(void *handle, void **stream);
 int mqcb200_set_workspace_limit(void *handle, size_t bytes);
 /* Packed-tensor size (bytes per handle) from which a build whose density equals f*C*C^T
  * takes its Coulomb vector from the half-transform instead of a pass over the tensor.
- * Default 256 MiB (below that the pass is cheaper than the extra launches); 0 = always try,
+ * Default 1 GiB (below that the pass over B is cheaper than the check + epilogue); 0 = always try,
  * SIZE_MAX = never. Either path gives the reference's J to rounding. */
 int mqcb200_set_fuse_threshold(void *handle, size_t bytes);
 

@@ -143,7 +143,7 @@ struct Engine {
   cudaEvent_t ev_late_upload = nullptr;
   TensorSlot slots[MQCB200_NUM_SLOTS];
   size_t workspace_limit = (size_t)4 << 30;
-  size_t fuse_threshold = (size_t)256 << 20;
+  size_t fuse_threshold = (size_t)1 << 30;   // measured break-even: the check + epilogue cost ~ a pass over 0.6 GB
 
   // per-build device operands and scratch (grow-only)
   DevBuf d_w, d_ctf, d_gamma_partial, d_gamma, d_jpart, d_x, d_kpart;

@@ -73,7 +73,7 @@ def test_fock_energy_and_bit_reproducibility(engine, c2):
         assert not engine.last_gamma_fused()
         assert np.max(np.abs(f_general - f1)) <= 1e-11
     finally:
-        engine.set_fuse_threshold(256 << 20)
+        engine.set_fuse_threshold(1 << 30)
     j, k = engine.build_jk(d, c, NOCC)
     assert np.max(np.abs(f1 - (h + j - 0.5 * k))) <= 1e-10
     assert abs(e1 - 0.5 * np.sum(d * (h + f1))) <= 1e-9 * max(1.0, abs(e1))

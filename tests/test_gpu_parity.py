@@ -260,7 +260,7 @@ def test_coulomb_vector_from_half_transform(engine, n, n_occ, naux):
         j_ref, ka_ref, kb_ref = oracle.jk_df_uhf(b, da + db, coeff, n_occ, cb, nb_)
         assert _maxabs(j, j_ref) <= TOL and _maxabs(ka, ka_ref) <= TOL and _maxabs(kb, kb_ref) <= TOL
     finally:
-        engine.set_fuse_threshold(256 << 20)
+        engine.set_fuse_threshold(1 << 30)
     f_general = engine.build_fock_df(h, density, coeff, n_occ)
     assert not engine.last_gamma_fused()
     assert _maxabs(f_general, ref) <= TOL and _maxabs(f_general, f_fused) <= 1e-11

@@ -315,6 +315,28 @@ def test_n_occ_zero_and_k_scale_zero(engine):
     assert _maxabs(j, j_ref) <= TOL and not k.any()
 
 
+@pytest.mark.parametrize("n,n_occ,naux", [(200, 150, 20), (300, 257, 8), (81, 65, 30), (96, 96, 17), (128, 1, 40)])
+def test_wide_occupied_spaces_and_fragment_path_boundary(engine, n, n_occ, naux):
+    """Two and three N tiles in the half-transform (n_occ > 128, > 256), shapes just outside
+    the one-pass fragment kernel (n = 81, n_occ = 65), n_occ == n and n_occ == 1."""
+    b, h, density, coeff = synth.synth_problem(500 + n, n, n_occ, naux)
+    engine.set_tensor(b)
+    ref = oracle.build_fock_df(h, b, density, coeff, n_occ)
+    scale = max(1.0, float(np.max(np.abs(ref))))
+    assert _maxabs(engine.build_fock_df(h, density, coeff, n_occ), ref) <= TOL * scale
+
+
+def test_empty_shard_contributes_nothing(engine):
+    """A rank that holds no auxiliary function (more GPUs than naux slabs) returns H."""
+    n, n_occ, naux = 30, 4, 5
+    b, h, density, coeff = synth.synth_problem(6, n, n_occ, naux)
+    engine.set_tensor_shard(b[:, 0:0], n, naux, 3)
+    assert engine.tensor_bytes() == 0
+    assert np.array_equal(engine.build_fock_df(h, density, coeff, n_occ), h)
+    j, k = engine.build_jk(density, coeff, n_occ)
+    assert not j.any() and not k.any()
+
+
 def test_sharded_tensor_partial_sums(engine):
     """A shard holds auxiliary functions [q_begin, q_begin+q_count); partial J/K add up."""
     n, n_occ, naux = 64, 12, 90

@@ -154,8 +154,9 @@ int mqcb200_build_fock_uhf_device(void *handle, int slot, const double *d_h,
 /* ---- multi-GPU (whole-molecule builds sharded by auxiliary index) ---------
  * New behaviour relative to the reference, which never splits one Fock build
  * (SURVEY 2.2).  One process per GPU; each holds a shard set with
- * mqcb200_set_tensor_shard; every build ends in one sum all-reduce of [J;K]
- * over NCCL.  The 128-byte id is created on rank 0 and carried to the other
+ * mqcb200_set_tensor_shard; every build ends in one sum exchange of [J;K]: a single
+ * kernel over NVLink peer memory (buffers mapped with CUDA IPC at comm_init), with the
+ * NCCL all-reduce as fallback (MQCB200_P2P_ALLREDUCE=0 forces it).  The 128-byte id is created on rank 0 and carried to the other
  * ranks by the host program's own transport (MPI bcast in the reference,
  * src/parallel/mqc_bcast.f90). */
 int mqcb200_comm_unique_id(char id[128]);

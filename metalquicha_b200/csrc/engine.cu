@@ -93,6 +93,7 @@ struct NcclApi {
   int (*GetUniqueId)(void *) = nullptr;
   int (*CommInitRank)(void **, int, Id128 /* ncclUniqueId, passed by value */, int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
   int (*CommDestroy)(void *) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
@@ -117,6 +118,7 @@ static void load_nccl() {
   g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(sym("ncclGetUniqueId"));
   g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(sym("ncclCommInitRank"));
   g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(sym("ncclAllReduce"));
+  g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(sym("ncclAllGather"));
   g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(sym("ncclCommDestroy"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
   g_nccl.lib = lib;
@@ -130,6 +132,7 @@ static void load_nccl() {
   } while (0)
 constexpr int kNcclFloat64 = 8;  // ncclDouble
 constexpr int kNcclSum = 0;
+constexpr int kNcclChar = 0;     // ncclInt8 / ncclChar
 
 // ---- the engine ------------------------------------------------------------------------
 constexpr uint32_t kMagic = 0x4D51B200u;
@@ -163,6 +166,17 @@ struct Engine {
   // multi-GPU
   void *comm = nullptr;
   int n_ranks = 1, rank = 0;
+  // NVLink peer-memory exchange (xgpu_kernels.cu): every rank's partial/reduced [J|K] buffers and
+  // arrival flags are mapped into every other rank through CUDA IPC
+  struct P2P {
+    bool ready = false;
+    XgpuPeers peers{};
+    void *flags = nullptr, *misc = nullptr;       // own flags [2*XGPU_MAX_RANKS] u64; misc: counter, error
+    void *in = nullptr, *out = nullptr;           // own partial / reduced buffers
+    size_t cap = 0;                               // bytes of each of in/out
+    unsigned long long epoch = 0;
+    int host_error = 0;
+  } p2p;
 
   // instrumentation: every occurrence of a phase gets its own event pair; a build's
   // per-phase time is the sum over its occurrences (K runs once per Q-chunk and spin)
@@ -234,6 +248,117 @@ static bool fuse_gamma_enabled() {
 constexpr size_t kSmallIoBytes = (size_t)1 << 20;
 
 enum { T_UPLOAD = 0, T_J1, T_J2, T_K1, T_K2, T_FINAL, T_ALLREDUCE, T_DOWNLOAD };
+
+// ------------------------------- NVLink peer-memory exchange -------------------------------
+static bool p2p_enabled_by_env() {
+  const char *env = getenv("MQCB200_P2P_ALLREDUCE");    // "0" = use the NCCL all-reduce instead
+  return !(env && env[0] == '0');
+}
+
+// All ranks call this together: every rank learns device-addressable pointers to the buffer
+// `local` of every other rank (CUDA IPC handles carried by a 64-byte NCCL all-gather).
+static void p2p_exchange(Engine *e, void *local, void **mapped /*[n_ranks]*/) {
+  cudaIpcMemHandle_t mine;
+  CUDA_CHECK(cudaIpcGetMemHandle(&mine, local));
+  const size_t hs = sizeof(cudaIpcMemHandle_t);
+  DevBuf sendb, recvb;
+  sendb.ensure(hs);
+  recvb.ensure(hs * e->n_ranks);
+  std::vector<cudaIpcMemHandle_t> all(e->n_ranks);
+  try {
+    CUDA_CHECK(cudaMemcpyAsync(sendb.ptr, &mine, hs, cudaMemcpyHostToDevice, e->stream));
+    NCCL_CHECK(g_nccl.AllGather(sendb.ptr, recvb.ptr, hs, kNcclChar, e->comm, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), recvb.ptr, hs * e->n_ranks, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  } catch (...) {
+    sendb.release();
+    recvb.release();
+    throw;
+  }
+  sendb.release();
+  recvb.release();
+  for (int k = 0; k < e->n_ranks; ++k) {
+    if (k == e->rank) { mapped[k] = local; continue; }
+    void *p = nullptr;
+    CUDA_CHECK(cudaIpcOpenMemHandle(&p, all[k], cudaIpcMemLazyEnablePeerAccess));
+    mapped[k] = p;
+  }
+}
+
+static void p2p_unmap(Engine *e, void **mapped) {
+  for (int k = 0; k < e->n_ranks; ++k) {
+    if (k != e->rank && mapped[k]) cudaIpcCloseMemHandle(mapped[k]);
+    mapped[k] = nullptr;
+  }
+}
+
+// Collective: called by comm_init on every rank.  Failure leaves p2p.ready false (NCCL is used).
+static void p2p_setup(Engine *e) {
+  Engine::P2P &x = e->p2p;
+  x.ready = false;
+  if (e->n_ranks < 2 || e->n_ranks > XGPU_MAX_RANKS || !p2p_enabled_by_env()) return;
+  const size_t fbytes = 2 * XGPU_MAX_RANKS * sizeof(unsigned long long);
+  CUDA_CHECK(cudaMalloc(&x.flags, fbytes));
+  CUDA_CHECK(cudaMalloc(&x.misc, 64));
+  CUDA_CHECK(cudaMemsetAsync(x.flags, 0, fbytes, e->stream));
+  CUDA_CHECK(cudaMemsetAsync(x.misc, 0, 64, e->stream));
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  void *mapped[XGPU_MAX_RANKS] = {};
+  p2p_exchange(e, x.flags, mapped);
+  for (int k = 0; k < e->n_ranks; ++k) x.peers.flags[k] = static_cast<unsigned long long *>(mapped[k]);
+  x.cap = 0;
+  x.epoch = 0;
+  x.ready = true;
+}
+
+// Collective: make sure every rank's partial/reduced buffers hold `bytes` and are mapped
+// everywhere.  Growth is rare (grow-only, with headroom) and is itself a collective:
+// unmap everywhere -> (the all-gather inside p2p_exchange is the barrier) -> free, allocate, map.
+static void p2p_ensure_buffers(Engine *e, size_t bytes) {
+  Engine::P2P &x = e->p2p;
+  if (bytes <= x.cap) return;
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  void *old_in[XGPU_MAX_RANKS], *old_out[XGPU_MAX_RANKS];
+  for (int k = 0; k < e->n_ranks; ++k) {
+    old_in[k] = const_cast<double *>(x.peers.in[k]);
+    old_out[k] = x.peers.out[k];
+  }
+  if (x.cap > 0) { p2p_unmap(e, old_in); p2p_unmap(e, old_out); }
+  const size_t new_cap = std::max(bytes, 2 * x.cap);
+  void *new_in = nullptr, *new_out = nullptr;
+  CUDA_CHECK(cudaMalloc(&new_in, new_cap));
+  CUDA_CHECK(cudaMalloc(&new_out, new_cap));
+  void *mapped[XGPU_MAX_RANKS] = {};
+  p2p_exchange(e, new_in, mapped);                 // also a barrier: every rank has unmapped the old buffers
+  for (int k = 0; k < e->n_ranks; ++k) x.peers.in[k] = static_cast<const double *>(mapped[k]);
+  p2p_exchange(e, new_out, mapped);
+  for (int k = 0; k < e->n_ranks; ++k) x.peers.out[k] = static_cast<double *>(mapped[k]);
+  if (x.in) cudaFree(x.in);
+  if (x.out) cudaFree(x.out);
+  x.in = new_in;
+  x.out = new_out;
+  x.cap = new_cap;
+}
+
+static void p2p_teardown(Engine *e) {
+  Engine::P2P &x = e->p2p;
+  if (x.flags) {
+    void *m[XGPU_MAX_RANKS];
+    for (int k = 0; k < e->n_ranks; ++k) m[k] = x.peers.flags[k];
+    p2p_unmap(e, m);
+    if (x.cap > 0) {
+      for (int k = 0; k < e->n_ranks; ++k) m[k] = const_cast<double *>(x.peers.in[k]);
+      p2p_unmap(e, m);
+      for (int k = 0; k < e->n_ranks; ++k) m[k] = x.peers.out[k];
+      p2p_unmap(e, m);
+    }
+    cudaFree(x.flags);
+    cudaFree(x.misc);
+    if (x.in) cudaFree(x.in);
+    if (x.out) cudaFree(x.out);
+  }
+  x = Engine::P2P{};
+}
 
 // ------------------------------- tensor set-up ------------------------------------------
 static void slot_prepare(Engine *e, TensorSlot &sl, int n, int naux_total, int q_begin, int q_count) {
@@ -401,9 +526,12 @@ static void build(Engine *e, const BuildArgs &a) {
   const bool do_j = a.want_j;
   const bool do_ka = a.want_k && a.n_a > 0;
   const bool do_kb = a.want_k && a.two_spin && a.n_b > 0;
-  // [J | K_a | K_b] in one buffer: a single all-reduce covers whatever was built
-  e->d_jk.ensure(3 * nn * sizeof(double));
-  double *d_j = e->d_jk.d(), *d_ka = d_j + nn, *d_kb = d_j + 2 * nn;
+  // [J | K_a | K_b] in one buffer: a single exchange covers whatever was built.  With the
+  // NVLink peer-memory exchange the partials live in the IPC-mapped buffer instead.
+  const bool use_p2p = sharded && e->n_ranks > 1 && e->p2p.ready;
+  if (use_p2p) p2p_ensure_buffers(e, 3 * nn * sizeof(double));
+  else e->d_jk.ensure(3 * nn * sizeof(double));
+  double *d_j = use_p2p ? static_cast<double *>(e->p2p.in) : e->d_jk.d(), *d_ka = d_j + nn, *d_kb = d_j + 2 * nn;
 
   const bool have = sl.q_count > 0;
   const double kfac = a.two_spin ? 1.0 : 2.0;
@@ -564,7 +692,8 @@ static void build(Engine *e, const BuildArgs &a) {
   e->phase_end(T_FINAL);
   CUDA_CHECK(cudaGetLastError());
 
-  // ---- multi-GPU: one sum all-reduce over whatever was built
+  // ---- multi-GPU: one sum exchange over whatever was built
+  bool p2p_used = false;
   if (sharded && e->n_ranks > 1) {
     e->phase_begin(T_ALLREDUCE);
     // J, K_a, K_b are adjacent; reduce the smallest contiguous span that covers the built ones
@@ -573,8 +702,22 @@ static void build(Engine *e, const BuildArgs &a) {
     if (!do_j && !do_ka && !do_kb) { first = 0; last = 0; }
     if (last > first) {
       if (!do_ka && do_kb && do_j) CUDA_CHECK(cudaMemsetAsync(d_ka, 0, nn * sizeof(double), e->stream));
-      NCCL_CHECK(g_nccl.AllReduce(d_j + first * nn, d_j + first * nn, (last - first) * nn, kNcclFloat64, kNcclSum,
-                                  e->comm, e->stream));
+      if (use_p2p) {
+        // one kernel: wait for the peers, sum my slice over all ranks in rank order, push it everywhere
+        Engine::P2P &x = e->p2p;
+        ++x.epoch;
+        launch_xgpu_allreduce(x.peers, e->n_ranks, e->rank, x.epoch, first * nn, (last - first) * nn,
+                              static_cast<unsigned int *>(x.misc), reinterpret_cast<int *>(static_cast<char *>(x.misc) + 16),
+                              e->stream);
+        e->launches += 1;
+        d_j = static_cast<double *>(x.out);
+        d_ka = d_j + nn;
+        d_kb = d_j + 2 * nn;
+        p2p_used = true;
+      } else {
+        NCCL_CHECK(g_nccl.AllReduce(d_j + first * nn, d_j + first * nn, (last - first) * nn, kNcclFloat64, kNcclSum,
+                                    e->comm, e->stream));
+      }
     }
     e->phase_end(T_ALLREDUCE);
   }
@@ -658,8 +801,13 @@ static void build(Engine *e, const BuildArgs &a) {
     e->phase_end(T_DOWNLOAD);
   }
   CUDA_CHECK(cudaGetLastError());
+  if (p2p_used && a.sync)
+    CUDA_CHECK(cudaMemcpyAsync(&e->p2p.host_error, static_cast<char *>(e->p2p.misc) + 16, sizeof(int),
+                               cudaMemcpyDeviceToHost, e->stream));
   if (a.sync) {
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (p2p_used && e->p2p.host_error)
+      throw Failure("mqcb200: the cross-GPU exchange timed out waiting for a peer rank (a rank failed or fell behind by > 2 s)");
     for (int i = 0; i < n_pending; ++i) std::memcpy(pending[i].dst, pending[i].src, pending[i].bytes);
     if (energy_pending) e->last_energy_host = e->h_out.d()[0];
     if (!a.device_operands && !a.assemble && a.k_a && a.want_k && !do_ka) std::memset(a.k_a, 0, nn * sizeof(double));
@@ -753,6 +901,7 @@ int mqcb200_destroy(void *handle) {
   API_BEGIN
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->comm) p2p_teardown(e);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto &sl : e->slots) sl.packed.release();
   DevBuf *bufs[] = {&e->d_w, &e->d_ctf, &e->d_gamma_partial,
@@ -1041,6 +1190,30 @@ int mqcb200_comm_init(void *handle, int n_ranks, int rank, const char id[128]) {
   e->comm = comm;
   e->n_ranks = n_ranks;
   e->rank = rank;
+  // NVLink peer-memory exchange: set up collectively, then agree -- unless EVERY rank mapped its
+  // peers the build uses the NCCL all-reduce (a mixed choice would deadlock)
+  int mine_ok = 0;
+  try {
+    p2p_setup(e);
+    mine_ok = e->p2p.ready ? 1 : 0;
+  } catch (const std::exception &) {
+    mine_ok = 0;
+  }
+  {
+    DevBuf sb, rb;
+    sb.ensure(sizeof(int));
+    rb.ensure(sizeof(int) * n_ranks);
+    std::vector<int> all(n_ranks, 0);
+    CUDA_CHECK(cudaMemcpyAsync(sb.ptr, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    NCCL_CHECK(g_nccl.AllGather(sb.ptr, rb.ptr, sizeof(int), kNcclChar, e->comm, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), rb.ptr, sizeof(int) * n_ranks, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    sb.release();
+    rb.release();
+    bool everyone = true;
+    for (int v : all) everyone = everyone && v == 1;
+    e->p2p.ready = everyone && mine_ok == 1;
+  }
   API_END
 }
 
@@ -1050,6 +1223,7 @@ int mqcb200_comm_destroy(void *handle) {
   if (e->comm) {
     e->bind();
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    p2p_teardown(e);
     NCCL_CHECK(g_nccl.CommDestroy(e->comm));
     e->comm = nullptr;
     e->n_ranks = 1;

@@ -41,6 +41,17 @@ size_t whiten_half_elems(int naux);   // doubles of the fragment-ordered copy of
 void launch_whiten(const double *d_half, int naux, const double *d_tp, int n, double *d_af, double *d_bp,
                    cudaStream_t s);
 
+// ---- cross-GPU sum of [J|K] over NVLink peer memory (sharded builds) ----------
+constexpr int XGPU_MAX_RANKS = 8;
+struct XgpuPeers {                         // device-addressable pointers of every rank (own entry included)
+  const double *in[XGPU_MAX_RANKS];        // partial [J|K_a|K_b]
+  double *out[XGPU_MAX_RANKS];             // reduced [J|K_a|K_b]
+  unsigned long long *flags[XGPU_MAX_RANKS];   // [2*XGPU_MAX_RANKS] arrival epochs per rank
+};
+// out[k][first..first+count) = sum_r in[r][first..first+count) on every rank k, in rank order.
+void launch_xgpu_allreduce(const XgpuPeers &peers, int n_ranks, int rank, unsigned long long epoch, size_t first,
+                           size_t count, unsigned int *d_counter, int *d_error, cudaStream_t s);
+
 // ---- J: two passes over the packed tensor -----------------------------------
 struct JPlan {
   int n_seg;      // pass 1: segments of a packed row

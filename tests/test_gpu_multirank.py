@@ -49,7 +49,10 @@ sys.exit(0 if ok else 1)
 '''
 
 
-def test_two_gpu_sharded_build(tmp_path):
+@pytest.mark.parametrize("exchange", ["nvlink_peer_memory", "nccl_allreduce"])
+def test_two_gpu_sharded_build(tmp_path, exchange):
+    """Both exchange paths: the one-kernel sum over NVLink peer memory (default) and the NCCL
+    all-reduce fallback (MQCB200_P2P_ALLREDUCE=0)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -59,6 +62,8 @@ def test_two_gpu_sharded_build(tmp_path):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     env = dict(os.environ, MQC_ROOT=ROOT)
+    if exchange == "nccl_allreduce":
+        env["MQCB200_P2P_ALLREDUCE"] = "0"
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          env=env, capture_output=True, text=True, timeout=600)

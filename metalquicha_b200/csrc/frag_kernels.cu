@@ -217,6 +217,14 @@ fragment_jk_kernel(const double *__restrict__ packed, int L, int q_count,
   }
 }
 
+void configure_fragment_kernels() {
+  cudaFuncSetAttribute(fragment_jk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(fragment_jk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(fragment_jk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(fragment_jk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(fragment_jk_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 bool fragment_path_applies(int n, int n_occ) {
   const int nt = num_tiles(n);
   const int nib = ((n_occ > 0 ? n_occ : 1) + 7) / 8;
@@ -252,15 +260,6 @@ FragPlan plan_fragment(int n, int n_occ, int q_count, int sm_count) {
 void launch_fragment_jk(const double *d_packed, int q_count, const double *d_w, const double *d_ctf,
                         const FragPlan &p, bool want_j, bool want_k, double *d_jpart, double *d_kpart,
                         cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(fragment_jk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(fragment_jk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(fragment_jk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(fragment_jk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(fragment_jk_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
   // only the lower-triangular 8x8 blocks of the K partial tiles are written -- exactly the
   // elements finalize_jk_kernel reads (row >= col), so no clearing is needed
 #define MQCB200_LAUNCH_FRAG(NT_)                                                                              \

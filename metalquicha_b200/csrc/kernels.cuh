@@ -113,7 +113,9 @@ void launch_k_half_transform(const double *d_packed, long long L, int n, int q_c
                              double *d_gamma_part, cudaStream_t s);
 void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, double *d_kpart,
                          int accumulate, cudaStream_t s);
-// One-time opt-in to large dynamic shared memory for the K kernels.
-void configure_kernels();
+// One-time (per process and device) opt-in to large dynamic shared memory.
+void configure_kernels();            // K kernels; calls the two below
+void configure_fragment_kernels();
+void configure_whiten_kernels();
 
 }  // namespace mqcb200

@@ -140,6 +140,10 @@ whiten_gemm_kernel(const double *__restrict__ af, int nmb, int nkc, const double
   }
 }
 
+void configure_whiten_kernels() {
+  cudaFuncSetAttribute(whiten_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WhitenCfg::kSmemBytes);
+}
+
 size_t whiten_half_elems(int naux) {
   const int nmb = (naux + 7) / 8, nkc = (naux + 15) / 16;
   return (size_t)nkc * nmb * 128;
@@ -153,11 +157,6 @@ void launch_whiten(const double *d_half, int naux, const double *d_tp, int n, do
   unsigned blocks = (unsigned)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_half_kernel<<<blocks, 256, 0, s>>>(d_half, naux, nmb, nkc, d_af);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(whiten_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WhitenCfg::kSmemBytes);
-    configured = true;
-  }
   const unsigned mtiles = (unsigned)((naux + 127) / 128);
   const long long ntiles = L / 128;
   for (long long y0 = 0; y0 < ntiles; y0 += 65535) {

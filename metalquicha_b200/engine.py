@@ -175,6 +175,8 @@ class B200FockEngine:
         n = h.shape[0]
         if h.shape != (n, n) or density.shape != (n, n):
             raise ValueError("h and density must both be n x n")
+        if slot in self.n and self.n[slot] != n:
+            raise ValueError(f"the resident tensor has n = {self.n[slot]}, the operands have n = {n}")
         coeff, ldc = self._coeff(coeff, n, n_occ)
         fock = out if out is not None else np.empty((n, n), dtype=np.float64, order="F")
         _check(self._lib.mqcb200_build_fock(

@@ -259,10 +259,72 @@ struct SyrkCfg {
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageElems * sizeof(double) + 2 * kStages * sizeof(uint64_t);
 };
 
+// Consumer side of a DIAGONAL 64x64 tile: only the lower triangle is ever read back, so the
+// 36 lower-triangular 8x8 blocks are dealt evenly -- warp W takes block-rows W and 7-W, nine
+// blocks -- instead of 16 per warp on a full tile.  Same pipeline protocol as the full path.
+template <int W, class Cfg>
+__device__ __forceinline__ void syrk_diag_warp(const double *stage_base, uint64_t *full_bar, uint64_t *empty_bar,
+                                               int n_steps, int nkc, int ks_last, int lane, double *out,
+                                               int accumulate) {
+  constexpr int R0 = W, R1 = 7 - W;               // the two 8-row blocks of this warp
+  constexpr int NB0 = R0 + 1, NB1 = R1 + 1;       // their column blocks 0..R (NB1 > NB0)
+  double acc0[NB0][2], acc1[NB1][2];
+#pragma unroll
+  for (int j = 0; j < NB0; ++j) { acc0[j][0] = 0.0; acc0[j][1] = 0.0; }
+#pragma unroll
+  for (int j = 0; j < NB1; ++j) { acc1[j][0] = 0.0; acc1[j][1] = 0.0; }
+  double fa[2][2], fb[2][NB1];
+  auto load_frags = [&](double (&a)[2], double (&b)[NB1], int st, int ks) {
+    const double *p = stage_base + (size_t)st * Cfg::kStageElems + lane;
+    a[0] = p[(R0 * 4 + ks) * 32];
+    a[1] = p[(R1 * 4 + ks) * 32];
+#pragma unroll
+    for (int j = 0; j < NB1; ++j) b[j] = p[(j * 4 + ks) * 32];
+  };
+  if (n_steps > 0) {
+    mbar_wait(&full_bar[0], 0);
+    load_frags(fa[0], fb[0], 0, 0);
+  }
+  int kc_idx = 0;
+  for (int step = 0; step < n_steps; ++step) {
+    const int st = step % Cfg::kStages;
+    const int ks_lim = (kc_idx == nkc - 1) ? ks_last : 4;
+    kc_idx = (kc_idx + 1 == nkc) ? 0 : kc_idx + 1;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      if (ks < 3) {
+        load_frags(fa[(ks + 1) & 1], fb[(ks + 1) & 1], st, ks + 1);
+      } else if (step + 1 < n_steps) {
+        const int st1 = (step + 1) % Cfg::kStages;
+        mbar_wait(&full_bar[st1], ((step + 1) / Cfg::kStages) & 1);
+        load_frags(fa[0], fb[0], st1, 0);
+      }
+      if (ks < ks_lim) {
+#pragma unroll
+        for (int j = 0; j < NB0; ++j) dmma884(acc0[j][0], acc0[j][1], fa[ks & 1][0], fb[ks & 1][j]);
+#pragma unroll
+        for (int j = 0; j < NB1; ++j) dmma884(acc1[j][0], acc1[j][1], fa[ks & 1][1], fb[ks & 1][j]);
+      }
+    }
+    release_stage(&empty_bar[st], lane);
+  }
+  const int g = lane >> 2, t = lane & 3;
+  auto store = [&](int rb, int cb, double v0, double v1) {
+    double2 *p = reinterpret_cast<double2 *>(out + (8 * rb + g) * 64 + 8 * cb + 2 * t);
+    double2 v = make_double2(v0, v1);
+    if (accumulate) { const double2 o = *p; v.x += o.x; v.y += o.y; }
+    *p = v;
+  };
+#pragma unroll
+  for (int j = 0; j < NB0; ++j) store(R0, j, acc0[j][0], acc0[j][1]);
+#pragma unroll
+  for (int j = 0; j < NB1; ++j) store(R1, j, acc1[j][0], acc1[j][1]);
+}
+
 template <int TILE>
 __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads, SyrkCfg<TILE>::kMinBlocks)
 k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count, int n_ktiles, int n_splits,
-                    double *__restrict__ kpart, int accumulate, int ks_last) {
+                    int n_splits_diag, int n_panels, double *__restrict__ kpart, int accumulate, int ks_last) {
   using Cfg = SyrkCfg<TILE>;
   constexpr int PB = Cfg::kPanelBlocks;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -271,13 +333,32 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
   uint64_t *empty_bar = full_bar + Cfg::kStages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x % n_ktiles, split = blockIdx.x / n_ktiles;
-  int mp = 0;
-  while ((mp + 1) * (mp + 2) / 2 <= tile) ++mp;
-  const int np = tile - mp * (mp + 1) / 2;
+  // Units: every tile for the first n_splits_diag splits, then only the off-diagonal tiles.
+  // A diagonal tile does 9/16 of the DMMAs (lower triangle only, evenly dealt to the four
+  // warps), so it gets proportionally longer auxiliary ranges: all units take the same time.
+  int tile, split, mp = 0, np;
+  {
+    const int u_full = n_splits_diag * n_ktiles;
+    if ((int)blockIdx.x < u_full) {
+      split = blockIdx.x / n_ktiles;
+      tile = blockIdx.x % n_ktiles;
+      while ((mp + 1) * (mp + 2) / 2 <= tile) ++mp;
+      np = tile - mp * (mp + 1) / 2;
+    } else {
+      const int n_off = n_ktiles - n_panels;
+      const int v = blockIdx.x - u_full;
+      split = n_splits_diag + v / n_off;
+      const int oi = v % n_off;                       // off-diagonal tiles: oi = mp*(mp-1)/2 + np, np < mp
+      mp = 1;
+      while ((mp + 1) * mp / 2 <= oi) ++mp;
+      np = oi - mp * (mp - 1) / 2;
+      tile = mp * (mp + 1) / 2 + np;
+    }
+  }
   const bool diag = mp == np;
-  const int qa = (int)((long long)split * q_count / n_splits);
-  const int qb = (int)((long long)(split + 1) * q_count / n_splits);
+  const int my_splits = diag ? n_splits_diag : n_splits;
+  const int qa = (int)((long long)split * q_count / my_splits);
+  const int qb = (int)((long long)(split + 1) * q_count / my_splits);
   const int n_steps = (qb - qa) * nkc;
   const int valid_a = nmb - PB * mp < PB ? nmb - PB * mp : PB;   // 8-row blocks present in each panel
   const int valid_b = nmb - PB * np < PB ? nmb - PB * np : PB;
@@ -316,6 +397,16 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
   }
 
   if (TILE == 128) reg_alloc_consumer();
+  if (TILE == 64 && diag) {
+    double *out_d = kpart + ((size_t)split * n_ktiles + tile) * (TILE * TILE);
+    switch (warp) {
+      case 0: syrk_diag_warp<0, Cfg>(stage_base, full_bar, empty_bar, n_steps, nkc, ks_last, lane, out_d, accumulate); break;
+      case 1: syrk_diag_warp<1, Cfg>(stage_base, full_bar, empty_bar, n_steps, nkc, ks_last, lane, out_d, accumulate); break;
+      case 2: syrk_diag_warp<2, Cfg>(stage_base, full_bar, empty_bar, n_steps, nkc, ks_last, lane, out_d, accumulate); break;
+      default: syrk_diag_warp<3, Cfg>(stage_base, full_bar, empty_bar, n_steps, nkc, ks_last, lane, out_d, accumulate); break;
+    }
+    return;
+  }
   const int wm = warp % Cfg::kWarpsM, wn = warp / Cfg::kWarpsM;
   const int g = lane >> 2, t = lane & 3;
   constexpr int TN = Cfg::kTN;
@@ -428,13 +519,26 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
   int best = 1;
   double best_cost = 1e300;
   const size_t tile_bytes = (size_t)p.ktile * p.ktile * sizeof(double);
+  const int n_diag = p.n_panels, n_off = p.n_ktiles - p.n_panels;
+  auto diag_splits = [&](int s) {           // 64-wide diagonal tiles cost 9/16 of a full tile
+    if (p.ktile != 64) return s;
+    int sd = (9 * s + 8) / 16;
+    return sd < 1 ? 1 : sd;
+  };
   for (int s = 1; s <= 512 && s <= p.q_chunk; ++s) {
     if ((size_t)s * p.n_ktiles * tile_bytes > ((size_t)256 << 20) && s > 1) break;
-    const long long units = (long long)s * p.n_ktiles;
+    const int sd = diag_splits(s);
+    const long long units = (long long)s * n_off + (long long)sd * n_diag;
     const long long waves = (units + slots - 1) / slots;
-    const long long steps = (long long)((p.q_chunk + s - 1) / s) * p.nkc;
+    const double steps_off = (double)((p.q_chunk + s - 1) / s) * p.nkc;
+    const double steps_diag = (double)((p.q_chunk + sd - 1) / sd) * p.nkc * (p.ktile == 64 ? 9.0 / 16.0 : 1.0);
+    const double steps = n_off > 0 ? (steps_off > steps_diag ? steps_off : steps_diag) : steps_diag;
     // + the fixed-order sum over the splits in finalize_jk_kernel (~3/4 of a step per split)
-    const double cost = (double)waves * ((double)steps + 12.0) + 0.75 * (double)s;
+    double cost = (double)waves * (steps + 12.0) + 0.75 * (double)s;
+    // a single wave of long units measures ~5 % slower than the same work in two waves of
+    // shorter ones (c2: 2.28 vs 2.18 ms; co-resident CTAs in lockstep, no second wave to
+    // absorb the stragglers)
+    if (waves == 1 && units > slots / 2) cost *= 1.05;
     if (cost < best_cost * 0.995) { best_cost = cost; best = s; }
   }
   if (const char *e = getenv("MQCB200_KSPLITS")) {   // development override
@@ -442,6 +546,7 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
     if (v >= 1) best = v < p.q_chunk ? v : p.q_chunk;
   }
   p.n_splits = best;
+  p.n_splits_diag = diag_splits(best);
   p.kpart_elems = (size_t)p.n_splits * p.n_ktiles * p.ktile * p.ktile;
   return p;
 }
@@ -479,12 +584,16 @@ void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, doub
   // A short last chunk still touches every (split, tile) partial -- splits with an empty
   // auxiliary range write (or add) zeros -- so the fixed-order sum in finalize is defined.
   const int splits = plan.n_splits;
+  const unsigned units = (unsigned)(plan.n_splits_diag * plan.n_ktiles +
+                                    (plan.n_splits - plan.n_splits_diag) * (plan.n_ktiles - plan.n_panels));
   if (plan.ktile == 128)
-    k_accumulate_kernel<128><<<(unsigned)(splits * plan.n_ktiles), SyrkCfg<128>::kThreads, SyrkCfg<128>::kSmemBytes, s>>>(
-        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, d_kpart, accumulate, plan.ks_last);
+    k_accumulate_kernel<128><<<units, SyrkCfg<128>::kThreads, SyrkCfg<128>::kSmemBytes, s>>>(
+        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, plan.n_splits_diag, plan.n_panels, d_kpart, accumulate,
+        plan.ks_last);
   else
-    k_accumulate_kernel<64><<<(unsigned)(splits * plan.n_ktiles), SyrkCfg<64>::kThreads, SyrkCfg<64>::kSmemBytes, s>>>(
-        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, d_kpart, accumulate, plan.ks_last);
+    k_accumulate_kernel<64><<<units, SyrkCfg<64>::kThreads, SyrkCfg<64>::kSmemBytes, s>>>(
+        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, plan.n_splits_diag, plan.n_panels, d_kpart, accumulate,
+        plan.ks_last);
 }
 
 template <int NB>

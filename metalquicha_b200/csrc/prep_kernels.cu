@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) pack_coeff_kernel(const double *__restric
 // exactly symmetric.  The sums run over the partials in fixed order.
 __global__ void __launch_bounds__(256) finalize_jk_kernel(const double *__restrict__ jpart, int n_jslices,
                                                           long long L, const double *__restrict__ kpart,
-                                                          int n_ksplits, int n_ktiles, int ktile_log2, int n, int nt,
+                                                          int n_ksplits, int n_ksplits_diag, int n_ktiles,
+                                                          int ktile_log2, int n, int nt,
                                                           double k_factor, double *__restrict__ j_out,
                                                           double *__restrict__ k_out,
                                                           const double *__restrict__ h, double jf, double kf,
@@ -138,15 +139,16 @@ __global__ void __launch_bounds__(256) finalize_jk_kernel(const double *__restri
     const size_t off = ((size_t)(mp * (mp + 1) / 2 + np) << (2 * ktile_log2)) + ((size_t)(a & msk) << ktile_log2) + (b & msk);
     double s = 0.0;
     const size_t stride = (size_t)n_ktiles << (2 * ktile_log2);
+    const int n_sp = mp == np ? n_ksplits_diag : n_ksplits;    // diagonal tiles hold fewer partials
     int sp = 0;
-    for (; sp + 16 <= n_ksplits; sp += 16) {
+    for (; sp + 16 <= n_sp; sp += 16) {
       double v[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) v[u] = kpart[(size_t)(sp + u) * stride + off];
 #pragma unroll
       for (int u = 0; u < 16; ++u) s += v[u];
     }
-    for (; sp < n_ksplits; ++sp) s += kpart[(size_t)sp * stride + off];
+    for (; sp < n_sp; ++sp) s += kpart[(size_t)sp * stride + off];
     kv = k_factor * s;
   }
   const size_t lo = (size_t)a + (size_t)n * b, up = (size_t)b + (size_t)n * a;
@@ -299,11 +301,12 @@ void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib
 
 void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits, int ktile,
                         int n, double k_factor, double *d_j, double *d_k, cudaStream_t s, const double *d_h,
-                        double jf, double kf, double *d_fock) {
+                        double jf, double kf, double *d_fock, int n_ksplits_diag) {
   const int nt = num_tiles(n);
   const int ktile_log2 = ktile == 128 ? 7 : 6;
   const int np = (n + ktile - 1) / ktile;
   finalize_jk_kernel<<<(unsigned)num_lower_tiles(nt), 256, 0, s>>>(d_jpart, n_jslices, packed_row_len(n), d_kpart, n_ksplits,
+                                          n_ksplits_diag < 0 ? n_ksplits : n_ksplits_diag,
                                           np * (np + 1) / 2, ktile_log2, n, nt, k_factor, d_j, d_k, d_h, jf, kf,
                                           d_fock);
 }

@@ -342,7 +342,7 @@ def main():
     n, n_occ, naux = cfg["n"], cfg["n_occ"], cfg["naux"]
     n_beta = cfg.get("n_beta", 0)
     # defaults sized so that a default run finishes within minutes and the timed region is ~1 s
-    flops_per_build = 3.0 * n * n * (n_occ + n_beta) * naux
+    flops_per_build = 3.0 * n * n * (n_occ + n_beta) * naux / max(1, _env_int("WORLD_SIZE", 1))   # per rank
     if args.steps is None:
         args.steps = 5 if args.workload == "c3" else int(min(200, max(5, 1.0 / (flops_per_build / 28e12 + 2e-4))))
     if args.cpu_sample is None:

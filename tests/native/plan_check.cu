@@ -1,0 +1,147 @@
+// Host-side invariants of the launch planners and of the packed-layout arithmetic, over a
+// grid of shapes far wider than the GPU parity suite.  Built and run on the CPU by
+// tests/test_native_planners.py (links libmqcb200.so; launches nothing).
+#include <cstdio>
+#include <cstdlib>
+#include <set>
+#include <utility>
+#include <vector>
+
+#include "../../metalquicha_b200/csrc/common.cuh"
+#include "../../metalquicha_b200/csrc/kernels.cuh"
+
+using namespace mqcb200;
+
+static int failures = 0;
+#define CHECK(cond, ...)                                  \
+  do {                                                    \
+    if (!(cond)) {                                        \
+      ++failures;                                         \
+      if (failures < 20) { printf("FAIL %s: ", #cond); printf(__VA_ARGS__); printf("\n"); } \
+    }                                                     \
+  } while (0)
+
+static void check_layout() {
+  std::set<int> seen;
+  for (int r = 0; r < 16; ++r)
+    for (int c = 0; c < 16; ++c) {
+      const int o = in_tile_offset(r, c);
+      CHECK(o >= 0 && o < 256, "offset %d", o);
+      seen.insert(o);
+    }
+  CHECK(seen.size() == 256, "in_tile_offset is not a permutation");
+  for (int nt = 1; nt <= 100; ++nt) {
+    std::set<int> ids;
+    for (int tc = 0; tc < nt; ++tc)
+      for (int tr = tc; tr < nt; ++tr) ids.insert(tile_index(tr, tc, nt));
+    CHECK((long long)ids.size() == num_lower_tiles(nt) && *ids.begin() == 0 &&
+              *ids.rbegin() == (int)num_lower_tiles(nt) - 1,
+          "tile_index not a bijection at nt=%d", nt);
+  }
+  CHECK(packed_row_len(688) == 946LL * 256 && packed_row_len(1450) == 4186LL * 256, "row lengths");
+}
+
+// the unit -> (tile, split) decode of k_accumulate_kernel, restated on the host
+static void decode_unit(int u, const KPlan &p, int &tile, int &split, bool &diag) {
+  const int u_full = p.n_splits_diag * p.n_ktiles;
+  int mp = 0, np = 0;
+  if (u < u_full) {
+    split = u / p.n_ktiles;
+    tile = u % p.n_ktiles;
+    while ((mp + 1) * (mp + 2) / 2 <= tile) ++mp;
+    np = tile - mp * (mp + 1) / 2;
+  } else {
+    const int n_off = p.n_ktiles - p.n_panels;
+    const int v = u - u_full;
+    split = p.n_splits_diag + v / n_off;
+    const int oi = v % n_off;
+    mp = 1;
+    while ((mp + 1) * mp / 2 <= oi) ++mp;
+    np = oi - mp * (mp - 1) / 2;
+    tile = mp * (mp + 1) / 2 + np;
+  }
+  diag = mp == np;
+}
+
+static void check_plan_k() {
+  const int ns[] = {1, 8, 16, 17, 24, 63, 64, 65, 72, 81, 100, 127, 128, 129, 200, 257, 688, 1000, 1450, 2047, 4096};
+  const int os[] = {1, 5, 8, 15, 16, 17, 64, 65, 80, 96, 113, 128, 129, 144, 241, 256, 257, 400};
+  const int qs[] = {1, 3, 7, 64, 225, 340, 1800, 6800};
+  const size_t wss[] = {(size_t)1 << 20, (size_t)64 << 20, (size_t)4 << 30};
+  for (int n : ns)
+    for (int o : os) {
+      if (o > n) continue;
+      for (int q : qs)
+        for (size_t ws : wss) {
+          const KPlan p = plan_k(n, o, q, ws, 148);
+          const int nt = num_tiles(n);
+          CHECK(p.nb >= 1 && p.nb <= 8, "nb=%d (n=%d o=%d)", p.nb, n, o);
+          CHECK(p.nib == p.n_ntiles * 2 * p.nb && p.nib * 8 >= o, "nib=%d ntiles=%d nb=%d o=%d", p.nib, p.n_ntiles, p.nb, o);
+          CHECK(p.nkc * 2 == p.nib, "nkc=%d nib=%d", p.nkc, p.nib);
+          CHECK(p.nib * 8 - o < 16 * p.n_ntiles + 16, "padding of the occupied range too large: nib=%d o=%d", p.nib, o);
+          CHECK(p.nmb == 2 * nt, "nmb");
+          CHECK(p.ks_last >= 0 && p.ks_last <= 4, "ks_last=%d", p.ks_last);
+          // the k-subs the accumulation kernel skips must all be padding
+          CHECK(16 * (p.nkc - 1) + 4 * p.ks_last >= o || p.ks_last == 4, "ks_last=%d skips valid columns (o=%d nkc=%d)", p.ks_last, o, p.nkc);
+          CHECK(p.ktile == 64 || p.ktile == 128, "ktile");
+          CHECK(p.n_panels == (n + p.ktile - 1) / p.ktile && p.n_ktiles == p.n_panels * (p.n_panels + 1) / 2, "tiles");
+          CHECK(p.n_splits >= 1 && p.n_splits <= q && p.n_splits_diag >= 1 && p.n_splits_diag <= p.n_splits,
+                "splits %d/%d q=%d", p.n_splits, p.n_splits_diag, q);
+          CHECK(p.q_chunk >= 1 && p.q_chunk <= q, "q_chunk=%d", p.q_chunk);
+          CHECK(p.q_chunk == 1 || p.x_elems_per_q * (size_t)p.q_chunk * 8 <= ws, "workspace overrun");
+          CHECK(p.x_elems_per_q == (size_t)p.nkc * p.nmb * 128, "x size");
+          CHECK(p.kpart_elems == (size_t)p.n_splits * p.n_ktiles * p.ktile * p.ktile, "kpart size");
+          CHECK(p.kpart_elems * 8 <= ((size_t)256 << 20) || p.n_splits == 1, "partial buffer cap");
+          CHECK(p.gamma_stride == nt * p.n_ntiles * 2, "gamma stride");
+          // every (tile, split < its split count) is produced by exactly one unit
+          const int units = p.n_splits_diag * p.n_ktiles + (p.n_splits - p.n_splits_diag) * (p.n_ktiles - p.n_panels);
+          if ((long long)units <= 200000) {
+            std::set<std::pair<int, int>> got;
+            bool ok = true;
+            for (int u = 0; u < units; ++u) {
+              int tile, split;
+              bool diag;
+              decode_unit(u, p, tile, split, diag);
+              ok = ok && tile >= 0 && tile < p.n_ktiles && split >= 0 && split < (diag ? p.n_splits_diag : p.n_splits);
+              ok = ok && got.insert({tile, split}).second;
+            }
+            const int expect = p.n_panels * p.n_splits_diag + (p.n_ktiles - p.n_panels) * p.n_splits;
+            CHECK(ok && (int)got.size() == expect && units == expect, "unit decode (n=%d o=%d q=%d): %d units, %d distinct, %d expected",
+                  n, o, q, units, (int)got.size(), expect);
+          }
+        }
+    }
+}
+
+static void check_plan_j_and_fragment() {
+  for (int n : {1, 16, 24, 72, 80, 81, 688, 1450})
+    for (int q : {1, 7, 64, 340, 1800, 6800}) {
+      const JPlan p = plan_j(n, q);
+      const long long L = packed_row_len(n);
+      CHECK(p.n_seg >= 1 && p.n_slices >= 1 && p.n_slices <= (q > 0 ? q : 1), "j plan n=%d q=%d", n, q);
+      CHECK(p.gamma_partial_elems == (size_t)p.n_seg * q && p.j_partial_elems == (size_t)p.n_slices * L, "j buffers");
+    }
+  for (int n = 1; n <= 80; ++n)
+    for (int o : {1, 5, 8, 9, 15, 33, 64}) {
+      if (o > n) continue;
+      CHECK(fragment_path_applies(n, o), "fragment path refused n=%d o=%d", n, o);
+      for (int q : {1, 5, 113, 340, 5000}) {
+        const FragPlan p = plan_fragment(n, o, q, 148);
+        CHECK(p.nt == num_tiles(n) && p.nt <= 5 && p.nib == (o + 7) / 8 && p.nib <= 8, "fragment shape");
+        CHECK(p.grid >= 1 && p.grid <= 148 && p.grid <= q, "fragment grid %d (q=%d)", p.grid, q);
+        CHECK(p.smem_bytes <= 200 * 1024, "fragment smem %zu", p.smem_bytes);
+        CHECK(p.L == (int)packed_row_len(n) && p.jpart_elems == (size_t)p.grid * p.L, "fragment buffers");
+        CHECK(p.kpart_elems == (size_t)p.grid * p.n_ktiles * 4096, "fragment K buffer");
+      }
+    }
+  CHECK(!fragment_path_applies(81, 5) && !fragment_path_applies(72, 65), "fragment path limits");
+}
+
+int main() {
+  check_layout();
+  check_plan_k();
+  check_plan_j_and_fragment();
+  if (failures) { printf("%d planner/layout checks FAILED\n", failures); return 1; }
+  printf("planner and layout invariants hold\n");
+  return 0;
+}

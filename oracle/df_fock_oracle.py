@@ -169,6 +169,23 @@ def fitted_exchange_general(b, density):
     return k
 
 
+def build_fock_eri(h, eri, density, k_scale=None):
+    """The reference's in-core build from a four-index tensor, ``build_fock``
+    (mqc_libcint_rhf.f90:1491-1574):  J(a,b) = sum_cd D(c,d) (ab|cd)  (:1553-1559),
+    K(a,c) = sum_bd (ab|cd) D(b,d)  (the gemv at :1561),  F = H + J - kf K with
+    kf = 0.5 (* k_scale)  (:1533-1534, :1572).  Used only to tie the fitted oracle to the
+    reference's exact-integral routine on the fitted integrals (ab|cd) = sum_P B_P(ab) B_P(cd)."""
+    n = h.shape[0]
+    kf = 0.5 if k_scale is None else 0.5 * k_scale
+    j_mat = np.zeros((n, n))
+    k_mat = np.zeros((n, n))
+    for c in range(n):
+        for d in range(n):
+            j_mat = j_mat + density[c, d] * eri[:, :, c, d]
+            k_mat[:, c] = eri[:, :, c, d] @ density[:, d] + k_mat[:, c]
+    return h + j_mat - kf * k_mat
+
+
 def response_operator_df(b, x, c_occ, dtilde, k_scale=None):
     """g = J[dtilde] - kf/2 * sum_P [(B_P X)(B_P C)^T + (B_P C)(B_P X)^T]
     backends/libcint/mqc_libcint_cphf.F90:499-566, loop for loop (:551-562)."""

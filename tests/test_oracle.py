@@ -97,6 +97,20 @@ def test_identity_iv_whitening_reproduces_metric_inverse():
     assert np.max(np.abs(b @ b.T - three @ np.linalg.inv(metric) @ three.T)) <= 1e-9
 
 
+def test_identity_v_fitted_build_equals_exact_build_on_fitted_integrals():
+    """build_fock_df(h, B, D, C) == build_fock(h, eri, D) for (ab|cd) = sum_P B_P(ab) B_P(cd):
+    the reference's two Fock routines (rhf.f90:1576-1646 and :1491-1574) must agree on the
+    integrals the fit defines -- the statement its docstring derives K from (:1586-1593)."""
+    n, o, q = 9, 3, 14
+    b, h, density, coeff = synth.synth_problem(12, n, o, q)
+    slabs = b.T.reshape(q, n, n)                                  # symmetric slabs
+    eri = np.einsum("pab,pcd->abcd", slabs, slabs)
+    for ks in (None, 0.2):
+        f_df = oracle.build_fock_df(h, b, density, coeff, o, k_scale=ks)
+        f_eri = oracle.build_fock_eri(h, eri, density, k_scale=ks)
+        assert np.max(np.abs(f_df - f_eri)) <= 1e-12
+
+
 def test_metric_inverse_sqrt_drops_null_modes():
     """Eigenvalues <= 1e-10 are zeroed, not errored (integrals.F90:1002,1027-1033)."""
     _, metric = synth.synth_physical_like_tensor(7, 4, 12, n_null=3)

@@ -370,13 +370,13 @@ def main():
             dist.destroy_process_group()
         return
 
-    from oracle import df_fock_oracle as oracle   # checker only: cpu_baseline + in-bench parity
     k_scale = args.k_scale if args.k_scale is not None else (0.2 if args.workload == "c4" else 1.0)
     scale = synth.default_scale(n, naux)
     _, h, density, coeff = synth.synth_problem(SEED, n, n_occ, naux, with_tensor=False)
     coeff_b = synth.synth_orbitals(SEED + 1, n, n_beta) if two_spin else None
     if two_spin:
-        density = np.asfortranarray(oracle.build_density_spin(coeff, n_occ) + oracle.build_density_spin(coeff_b, n_beta))
+        # D_total = C_a C_a^T + C_b C_b^T (input generation; src/scf/mqc_scf_common.f90:98-109)
+        density = np.asfortranarray(coeff @ coeff.T + coeff_b @ coeff_b.T)
 
     eng = B200FockEngine(local_rank)
     q_begin, q_count = synth.shard_range(naux, world, rank)
@@ -555,6 +555,7 @@ def main():
     cpu_baseline = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import df_fock_oracle as oracle   # the checker: CPU baseline + in-bench parity only
         cores = os.cpu_count() or 1
         qs = min(args.cpu_sample, naux)
         b_s = synth.synth_tensor(SEED, n, naux, scale, q_begin=0, q_count=qs)

@@ -346,7 +346,9 @@ def main():
     if args.steps is None:
         args.steps = 5 if args.workload == "c3" else int(min(200, max(5, 1.0 / (flops_per_build / 28e12 + 2e-4))))
     if args.cpu_sample is None:
-        args.cpu_sample = int(min(naux, max(8, 2.0e10 / (4.0 * n * n * max(n_occ + n_beta, 1)))))
+        # ~1e11 reference-count flops per CPU build: 10-20 s of host work in all (generating the
+        # sampled slabs + two timed builds), a third of the auxiliary range at c2
+        args.cpu_sample = int(min(naux, max(8, 1.0e11 / (4.0 * n * n * max(n_occ + n_beta, 1)))))
     if args.impl == "reference":
         run_reference(args, cfg)
         return

@@ -58,9 +58,15 @@ int mqcb200_get_stream(void *handle, void **stream);
 int mqcb200_set_workspace_limit(void *handle, size_t bytes);
 /* Packed-tensor size (bytes per handle) from which a build whose density equals f*C*C^T
  * takes its Coulomb vector from the half-transform instead of a pass over the tensor.
- * Default 1 GiB (below that the pass over B is cheaper than the check + epilogue); 0 = always try,
- * SIZE_MAX = never. Either path gives the reference's J to rounding. */
+ * Default 32 MiB (below that the pass over B is cheaper than the extra launch); 0 = always try,
+ * SIZE_MAX = never.  The decision is made on the device, per build: max|D - f*C*C^T| (both
+ * triangles) <= 4*2^-53*max(n_occ,16)*max(1,max|D|) and every element finite.  The fused
+ * Coulomb vector then differs from the reference's sum(B_P*D) by at most that tolerance times
+ * sum|B_P| -- the size of the rounding error of the reference's own n^2-term sum. */
 int mqcb200_set_fuse_threshold(void *handle, size_t bytes);
+/* 1 (default): the HBM-bound Coulomb kernels run on a second stream, concurrently with the
+ * tensor-bound exchange kernels; 0: one stream.  Results are bit-identical either way. */
+int mqcb200_set_overlap(void *handle, int on);
 
 /* ---- the fitted tensor ---------------------------------------------------
  * Replaces the host array `bmat(nao*nao, naux)` that run_libcint_rhf receives
@@ -86,6 +92,11 @@ int mqcb200_set_tensor_from_3c(void *handle, int slot, int n, int naux,
 int mqcb200_synth_tensor(void *handle, int slot, int n, int naux_total,
                          int q_begin, int q_count, uint64_t seed, double scale);
 int mqcb200_clear_tensor(void *handle, int slot);
+/* Shape of the tensor resident on a slot (all zero when empty): lets a binding check that the
+ * operands it is about to pass (n x n, no size travels with the build calls) belong to the
+ * tensor that is resident -- a stale tensor from another fragment would otherwise be read out
+ * of bounds.  Any output pointer may be NULL. */
+int mqcb200_tensor_shape(void *handle, int slot, int *n, int *naux_total, int *q_begin, int *q_count);
 /* Packed device bytes held by a slot (0 when empty). */
 int mqcb200_tensor_bytes(void *handle, int slot, size_t *bytes);
 
@@ -106,9 +117,9 @@ int mqcb200_build_jk(void *handle, int slot, const double *density,
                      const double *coeff, int ldc, int n_occ, double *j, double *k);
 /* Two-spin build (conventions of
  * backends/cuest/backend/mqc_cuest_scf.f90:48-57, :826-838): J from the total
- * density, K_sigma = sum_P (B_P C_sigma)(B_P C_sigma)^T with no factor 2.  A
- * channel with n_sigma == 0 is skipped and its output left untouched
- * (mqc_cuest_integrals.f90:1694-1701). */
+ * density, K_sigma = sum_P (B_P C_sigma)(B_P C_sigma)^T with no factor 2.  An
+ * empty BETA channel (n_beta == 0) is skipped and k_beta left untouched
+ * (mqc_cuest_integrals.f90:1694-1701); an empty alpha channel gives k_alpha = 0. */
 int mqcb200_build_jk_uhf(void *handle, int slot, const double *density_total,
                          const double *coeff_a, int lda, int n_alpha,
                          const double *coeff_b, int ldb, int n_beta,
@@ -155,8 +166,11 @@ int mqcb200_build_fock_uhf_device(void *handle, int slot, const double *d_h,
  * New behaviour relative to the reference, which never splits one Fock build
  * (SURVEY 2.2).  One process per GPU; each holds a shard set with
  * mqcb200_set_tensor_shard; every build ends in one sum exchange of [J;K]: a single
- * kernel over NVLink peer memory (buffers mapped with CUDA IPC at comm_init), with the
- * NCCL all-reduce as fallback (MQCB200_P2P_ALLREDUCE=0 forces it).  The 128-byte id is created on rank 0 and carried to the other
+ * kernel over NVLink peer memory (buffers mapped with CUDA IPC at comm_init -- or addressed
+ * directly with peer access when several ranks are threads of one process), with the
+ * NCCL all-reduce as fallback (MQCB200_P2P_ALLREDUCE=0 forces it).  A rank that waits longer than
+ * MQCB200_XGPU_TIMEOUT_S (default 30) for a peer fails that build (an asynchronous build's failure
+ * is returned by the next call on the handle); the next sharded build resynchronises the ranks.  The 128-byte id is created on rank 0 and carried to the other
  * ranks by the host program's own transport (MPI bcast in the reference,
  * src/parallel/mqc_bcast.f90). */
 int mqcb200_comm_unique_id(char id[128]);
@@ -184,6 +198,9 @@ int mqcb200_last_launches(void *handle, int *n_kernels);
 /* 1 when the last build took its Coulomb vector from the half-transform (the density was
  * verified on the device to be f*C*C^T), 0 when it made the general pass over the tensor. */
 int mqcb200_last_gamma_fused(void *handle, int *fused);
+/* Stream time (ms, host gathers included) and PCIe bytes of the last mqcb200_set_tensor[_shard]:
+ * only the lower triangles cross the bus, double-buffered ("timed separately"). */
+int mqcb200_last_set_tensor(void *handle, double *ms, double *h2d_bytes);
 /* Device time (ms) of the whitening GEMM of the last mqcb200_set_tensor_from_3c and its
  * flop count 2*naux^2*L ("timed separately", not part of builds/sec). */
 int mqcb200_last_whiten(void *handle, double *ms, double *flops);

@@ -31,6 +31,9 @@ SIGNATURES = {
     "mqcb200_get_stream": (c_int, [c_void_p, POINTER(c_void_p)]),
     "mqcb200_set_workspace_limit": (c_int, [c_void_p, c_size_t]),
     "mqcb200_set_fuse_threshold": (c_int, [c_void_p, c_size_t]),
+    "mqcb200_set_overlap": (c_int, [c_void_p, c_int]),
+    "mqcb200_tensor_shape": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "mqcb200_last_set_tensor": (c_int, [c_void_p, _dp, _dp]),
     "mqcb200_set_tensor": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "mqcb200_set_tensor_shard": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mqcb200_set_tensor_from_3c": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -15,6 +16,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace mqcb200 {
@@ -143,10 +145,12 @@ struct Engine {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // H and D ride up here while the K kernels (which need only C) run
-  cudaEvent_t ev_late_upload = nullptr;
+  cudaStream_t j_stream = nullptr;      // the HBM-bound Coulomb kernels, concurrent with the tensor-bound exchange kernels
+  cudaEvent_t ev_late_upload = nullptr, ev_fork = nullptr, ev_k1_done = nullptr, ev_j_done = nullptr;
+  bool overlap_j = true;
   TensorSlot slots[MQCB200_NUM_SLOTS];
   size_t workspace_limit = (size_t)4 << 30;
-  size_t fuse_threshold = (size_t)1 << 30;   // measured break-even: the check + epilogue cost ~ a pass over 0.6 GB
+  size_t fuse_threshold = (size_t)32 << 20;  // below this a pass over B is cheaper than the extra launch of the fused route
 
   // per-build device operands and scratch (grow-only)
   DevBuf d_w, d_ctf, d_gamma_partial, d_gamma, d_jpart, d_x, d_kpart;
@@ -157,7 +161,11 @@ struct Engine {
   DevBuf d_in;                   // [H | D | C_a | C_b] of a host-operand build, contiguous
   DevBuf d_out;                  // [8 scalars | F_a | F_b] of a host-operand build, contiguous
   PinnedBuf h_in, h_out;         // pinned staging for operand sets up to kSmallIoBytes
+  PinnedBuf h_stage[2];          // double-buffered pinned staging of lower-triangle slabs (set_tensor)
+  DevBuf d_stage_lower[2];
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
   double whiten_ms = 0.0, whiten_flops = 0.0;
+  double set_tensor_ms = 0.0, set_tensor_h2d_bytes = 0.0;   // last host -> packed upload (stream time incl. host gathers)
   bool last_fuse_attempted = false;
   int last_n = 0;    // shape of the operands of the last build_fock (for last_energy)
   bool have_last_fock = false;
@@ -170,12 +178,15 @@ struct Engine {
   // arrival flags are mapped into every other rank through CUDA IPC
   struct P2P {
     bool ready = false;
+    bool failed = false;                          // an exchange timed out: the next sharded build resynchronises the ranks
     XgpuPeers peers{};
-    void *flags = nullptr, *misc = nullptr;       // own flags [2*XGPU_MAX_RANKS] u64; misc: counter, error
+    void *flags = nullptr, *misc = nullptr;       // own flags [2*XGPU_MAX_RANKS] u64; misc: CTA counter
+    int *host_error = nullptr, *dev_error = nullptr;   // pinned host int the exchange kernel raises, and its device alias
     void *in = nullptr, *out = nullptr;           // own partial / reduced buffers
     size_t cap = 0;                               // bytes of each of in/out
     unsigned long long epoch = 0;
-    int host_error = 0;
+    unsigned long long timeout_ns = 30000000000ull;
+    bool same_process[XGPU_MAX_RANKS] = {};       // peer k lives in this process: raw pointer + peer access, no IPC handle
   } p2p;
 
   // instrumentation: every occurrence of a phase gets its own event pair; a build's
@@ -189,8 +200,9 @@ struct Engine {
 
   void bind() { CUDA_CHECK(cudaSetDevice(device)); }
 
-  void phase_begin(int idx) {
+  void phase_begin(int idx, cudaStream_t on = nullptr) {
     if (!profiling) return;
+    if (!on) on = stream;
     if (n_spans == spans.size()) {
       Span sp{idx, nullptr, nullptr};
       CUDA_CHECK(cudaEventCreate(&sp.a));
@@ -198,14 +210,15 @@ struct Engine {
       spans.push_back(sp);
     }
     spans[n_spans].idx = idx;
-    CUDA_CHECK(cudaEventRecord(spans[n_spans].a, stream));
+    CUDA_CHECK(cudaEventRecord(spans[n_spans].a, on));
     ++n_spans;
   }
-  void phase_end(int idx) {
+  void phase_end(int idx, cudaStream_t on = nullptr) {
     if (!profiling) return;
+    if (!on) on = stream;
     for (size_t i = n_spans; i-- > 0;)
       if (spans[i].idx == idx) {
-        CUDA_CHECK(cudaEventRecord(spans[i].b, stream));
+        CUDA_CHECK(cudaEventRecord(spans[i].b, on));
         return;
       }
   }
@@ -255,17 +268,68 @@ static bool p2p_enabled_by_env() {
   return !(env && env[0] == '0');
 }
 
-// All ranks call this together: every rank learns device-addressable pointers to the buffer
-// `local` of every other rank (CUDA IPC handles carried by a 64-byte NCCL all-gather).
-static void p2p_exchange(Engine *e, void *local, void **mapped /*[n_ranks]*/) {
-  cudaIpcMemHandle_t mine;
-  CUDA_CHECK(cudaIpcGetMemHandle(&mine, local));
-  const size_t hs = sizeof(cudaIpcMemHandle_t);
-  DevBuf sendb, recvb;
-  sendb.ensure(hs);
-  recvb.ensure(hs * e->n_ranks);
-  std::vector<cudaIpcMemHandle_t> all(e->n_ranks);
+static unsigned long long p2p_timeout_ns() {
+  const char *env = getenv("MQCB200_XGPU_TIMEOUT_S");   // how long a rank waits for a peer before it gives up
+  double sec = env ? atof(env) : 30.0;
+  if (!(sec > 0.0)) sec = 30.0;
+  return (unsigned long long)(sec * 1.0e9);
+}
+
+// Collective: true iff EVERY rank passed true.  Also a barrier (4-byte NCCL all-gather).
+static bool ranks_agree(Engine *e, bool mine) {
+  DevBuf sb, rb;
+  std::vector<int> all(e->n_ranks, 0);
+  int v = mine ? 1 : 0;
   try {
+    sb.ensure(sizeof(int));
+    rb.ensure(sizeof(int) * e->n_ranks);
+    CUDA_CHECK(cudaMemcpyAsync(sb.ptr, &v, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    NCCL_CHECK(g_nccl.AllGather(sb.ptr, rb.ptr, sizeof(int), kNcclChar, e->comm, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), rb.ptr, sizeof(int) * e->n_ranks, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  } catch (...) {
+    sb.release();
+    rb.release();
+    throw;
+  }
+  sb.release();
+  rb.release();
+  bool everyone = true;
+  for (int x : all) everyone = everyone && x == 1;
+  return everyone;
+}
+
+// What a rank tells the others about one of its buffers.  Ranks in OTHER processes map it through
+// the CUDA IPC handle; ranks that live in the SAME process (one host thread per GPU, the
+// dispatcher shape of SURVEY 3.2) cannot open their own process's handles and use the raw
+// pointer with peer access enabled instead.
+struct PeerInfo {
+  int pid;
+  int device;
+  unsigned long long ptr;
+  cudaIpcMemHandle_t handle;
+};
+
+// All ranks call this together (the all-gather inside is unconditional, so a local failure can
+// never leave the ranks in different collectives): every rank learns a device-addressable
+// pointer to the buffer `local` of every other rank.  Returns false -- with everything it had
+// opened closed again -- when this rank could not map all of its peers.
+static bool p2p_exchange(Engine *e, void *local, void **mapped /*[n_ranks]*/) {
+  PeerInfo mine{};
+  bool ok = true;
+  mine.pid = (int)getpid();
+  mine.device = e->device;
+  mine.ptr = (unsigned long long)(uintptr_t)local;
+  if (!local || cudaIpcGetMemHandle(&mine.handle, local) != cudaSuccess) {
+    ok = false;
+    cudaGetLastError();
+  }
+  const size_t hs = sizeof(PeerInfo);
+  DevBuf sendb, recvb;
+  std::vector<PeerInfo> all(e->n_ranks);
+  try {
+    sendb.ensure(hs);
+    recvb.ensure(hs * e->n_ranks);
     CUDA_CHECK(cudaMemcpyAsync(sendb.ptr, &mine, hs, cudaMemcpyHostToDevice, e->stream));
     NCCL_CHECK(g_nccl.AllGather(sendb.ptr, recvb.ptr, hs, kNcclChar, e->comm, e->stream));
     CUDA_CHECK(cudaMemcpyAsync(all.data(), recvb.ptr, hs * e->n_ranks, cudaMemcpyDeviceToHost, e->stream));
@@ -277,43 +341,89 @@ static void p2p_exchange(Engine *e, void *local, void **mapped /*[n_ranks]*/) {
   }
   sendb.release();
   recvb.release();
-  for (int k = 0; k < e->n_ranks; ++k) {
+  for (int k = 0; k < e->n_ranks; ++k) mapped[k] = nullptr;
+  for (int k = 0; k < e->n_ranks && ok; ++k) {
     if (k == e->rank) { mapped[k] = local; continue; }
-    void *p = nullptr;
-    CUDA_CHECK(cudaIpcOpenMemHandle(&p, all[k], cudaIpcMemLazyEnablePeerAccess));
-    mapped[k] = p;
+    if (all[k].pid == mine.pid) {
+      int can = 0;
+      if (all[k].device != e->device) {
+        if (cudaDeviceCanAccessPeer(&can, e->device, all[k].device) != cudaSuccess || !can) { ok = false; cudaGetLastError(); break; }
+        cudaError_t pe = cudaDeviceEnablePeerAccess(all[k].device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { ok = false; cudaGetLastError(); break; }
+        cudaGetLastError();
+      }
+      mapped[k] = (void *)(uintptr_t)all[k].ptr;
+      e->p2p.same_process[k] = true;
+    } else {
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[k].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+      mapped[k] = p;
+      e->p2p.same_process[k] = false;
+    }
   }
+  if (!ok) {
+    for (int k = 0; k < e->n_ranks; ++k) {
+      if (k != e->rank && mapped[k] && !e->p2p.same_process[k]) cudaIpcCloseMemHandle(mapped[k]);
+      mapped[k] = nullptr;
+    }
+  }
+  return ok;
 }
 
 static void p2p_unmap(Engine *e, void **mapped) {
   for (int k = 0; k < e->n_ranks; ++k) {
-    if (k != e->rank && mapped[k]) cudaIpcCloseMemHandle(mapped[k]);
+    if (k != e->rank && mapped[k] && !e->p2p.same_process[k]) cudaIpcCloseMemHandle(mapped[k]);
     mapped[k] = nullptr;
   }
 }
 
-// Collective: called by comm_init on every rank.  Failure leaves p2p.ready false (NCCL is used).
+static void p2p_free_local(Engine *e) {
+  Engine::P2P &x = e->p2p;
+  if (x.flags) cudaFree(x.flags);
+  if (x.misc) cudaFree(x.misc);
+  if (x.host_error) cudaFreeHost(x.host_error);
+  if (x.in) cudaFree(x.in);
+  if (x.out) cudaFree(x.out);
+  x = Engine::P2P{};
+}
+
+// Collective: called by comm_init on every rank (n_ranks >= 2).  Every fallible local step comes
+// first, then the ranks agree, and only then are handles exchanged; unless EVERY rank mapped all
+// of its peers the build uses the NCCL all-reduce (a mixed choice would deadlock).
 static void p2p_setup(Engine *e) {
   Engine::P2P &x = e->p2p;
-  x.ready = false;
-  if (e->n_ranks < 2 || e->n_ranks > XGPU_MAX_RANKS || !p2p_enabled_by_env()) return;
+  x = Engine::P2P{};
+  bool ok = e->n_ranks <= XGPU_MAX_RANKS && p2p_enabled_by_env();
   const size_t fbytes = 2 * XGPU_MAX_RANKS * sizeof(unsigned long long);
-  CUDA_CHECK(cudaMalloc(&x.flags, fbytes));
-  CUDA_CHECK(cudaMalloc(&x.misc, 64));
-  CUDA_CHECK(cudaMemsetAsync(x.flags, 0, fbytes, e->stream));
-  CUDA_CHECK(cudaMemsetAsync(x.misc, 0, 64, e->stream));
-  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  if (ok) {
+    ok = cudaMalloc(&x.flags, fbytes) == cudaSuccess && cudaMalloc(&x.misc, 64) == cudaSuccess &&
+         cudaHostAlloc(reinterpret_cast<void **>(&x.host_error), sizeof(int), cudaHostAllocMapped) == cudaSuccess;
+    if (ok) {
+      *x.host_error = 0;
+      ok = cudaHostGetDevicePointer(reinterpret_cast<void **>(&x.dev_error), x.host_error, 0) == cudaSuccess &&
+           cudaMemsetAsync(x.flags, 0, fbytes, e->stream) == cudaSuccess &&
+           cudaMemsetAsync(x.misc, 0, 64, e->stream) == cudaSuccess && cudaStreamSynchronize(e->stream) == cudaSuccess;
+    }
+    cudaGetLastError();
+  }
+  if (!ranks_agree(e, ok)) { p2p_free_local(e); return; }
   void *mapped[XGPU_MAX_RANKS] = {};
-  p2p_exchange(e, x.flags, mapped);
+  const bool mapped_ok = p2p_exchange(e, x.flags, mapped);
+  if (!ranks_agree(e, mapped_ok)) {
+    if (mapped_ok) p2p_unmap(e, mapped);
+    p2p_free_local(e);
+    return;
+  }
   for (int k = 0; k < e->n_ranks; ++k) x.peers.flags[k] = static_cast<unsigned long long *>(mapped[k]);
   x.cap = 0;
   x.epoch = 0;
+  x.timeout_ns = p2p_timeout_ns();
   x.ready = true;
 }
 
 // Collective: make sure every rank's partial/reduced buffers hold `bytes` and are mapped
 // everywhere.  Growth is rare (grow-only, with headroom) and is itself a collective:
-// unmap everywhere -> (the all-gather inside p2p_exchange is the barrier) -> free, allocate, map.
+// unmap everywhere -> allocate -> agree -> exchange (the all-gathers are the barriers) -> agree.
 static void p2p_ensure_buffers(Engine *e, size_t bytes) {
   Engine::P2P &x = e->p2p;
   if (bytes <= x.cap) return;
@@ -322,21 +432,39 @@ static void p2p_ensure_buffers(Engine *e, size_t bytes) {
   for (int k = 0; k < e->n_ranks; ++k) {
     old_in[k] = const_cast<double *>(x.peers.in[k]);
     old_out[k] = x.peers.out[k];
+    x.peers.in[k] = nullptr;
+    x.peers.out[k] = nullptr;
   }
   if (x.cap > 0) { p2p_unmap(e, old_in); p2p_unmap(e, old_out); }
   const size_t new_cap = std::max(bytes, 2 * x.cap);
+  x.cap = 0;
   void *new_in = nullptr, *new_out = nullptr;
-  CUDA_CHECK(cudaMalloc(&new_in, new_cap));
-  CUDA_CHECK(cudaMalloc(&new_out, new_cap));
-  void *mapped[XGPU_MAX_RANKS] = {};
-  p2p_exchange(e, new_in, mapped);                 // also a barrier: every rank has unmapped the old buffers
-  for (int k = 0; k < e->n_ranks; ++k) x.peers.in[k] = static_cast<const double *>(mapped[k]);
-  p2p_exchange(e, new_out, mapped);
-  for (int k = 0; k < e->n_ranks; ++k) x.peers.out[k] = static_cast<double *>(mapped[k]);
+  bool ok = cudaMalloc(&new_in, new_cap) == cudaSuccess && cudaMalloc(&new_out, new_cap) == cudaSuccess;
+  cudaGetLastError();
+  // the agreement is also the barrier after which nobody still has the old buffers mapped
+  const bool all_ok = ranks_agree(e, ok);
   if (x.in) cudaFree(x.in);
   if (x.out) cudaFree(x.out);
+  x.in = x.out = nullptr;
+  if (!all_ok) {
+    if (new_in) cudaFree(new_in);
+    if (new_out) cudaFree(new_out);
+    throw Failure("mqcb200: a rank could not allocate the peer-mapped exchange buffers");
+  }
   x.in = new_in;
   x.out = new_out;
+  void *m_in[XGPU_MAX_RANKS] = {}, *m_out[XGPU_MAX_RANKS] = {};
+  const bool ok_in = p2p_exchange(e, new_in, m_in);
+  const bool ok_out = p2p_exchange(e, new_out, m_out);
+  if (!ranks_agree(e, ok_in && ok_out)) {
+    if (ok_in) p2p_unmap(e, m_in);
+    if (ok_out) p2p_unmap(e, m_out);
+    throw Failure("mqcb200: a rank could not map its peers' exchange buffers");
+  }
+  for (int k = 0; k < e->n_ranks; ++k) {
+    x.peers.in[k] = static_cast<const double *>(m_in[k]);
+    x.peers.out[k] = static_cast<double *>(m_out[k]);
+  }
   x.cap = new_cap;
 }
 
@@ -352,12 +480,37 @@ static void p2p_teardown(Engine *e) {
       for (int k = 0; k < e->n_ranks; ++k) m[k] = x.peers.out[k];
       p2p_unmap(e, m);
     }
-    cudaFree(x.flags);
-    cudaFree(x.misc);
-    if (x.in) cudaFree(x.in);
-    if (x.out) cudaFree(x.out);
   }
-  x = Engine::P2P{};
+  p2p_free_local(e);
+}
+
+// A peer that did not arrive in time leaves garbage in this build's [J|K]; the exchange kernel
+// says so in host-mapped memory, so no synchronisation is needed to see it -- also after an
+// asynchronous build, whose failure is reported by the NEXT call on the handle.
+static void p2p_raise_if_failed(Engine *e) {
+  Engine::P2P &x = e->p2p;
+  if (!x.ready || !x.host_error || *x.host_error == 0) return;
+  *x.host_error = 0;
+  x.failed = true;
+  throw Failure("mqcb200: the cross-GPU exchange timed out waiting for a peer rank (a rank failed or fell behind by "
+                "more than MQCB200_XGPU_TIMEOUT_S); the result of that build is invalid");
+}
+
+// Collective, entered by the first sharded build after a failed exchange (every rank of a failed
+// exchange sees the failure: whoever is waited for in vain is itself left waiting for the rank that
+// gave up): zero the arrival flags and the CTA counter, restart the epochs, carry on.
+static void p2p_recover(Engine *e) {
+  Engine::P2P &x = e->p2p;
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  ranks_agree(e, true);                           // nobody is inside an exchange kernel any more
+  const size_t fbytes = 2 * XGPU_MAX_RANKS * sizeof(unsigned long long);
+  CUDA_CHECK(cudaMemsetAsync(x.flags, 0, fbytes, e->stream));
+  CUDA_CHECK(cudaMemsetAsync(x.misc, 0, 64, e->stream));
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  *x.host_error = 0;
+  ranks_agree(e, true);                           // nobody publishes before everyone has zeroed
+  x.epoch = 0;
+  x.failed = false;
 }
 
 // ------------------------------- tensor set-up ------------------------------------------
@@ -375,6 +528,65 @@ static void slot_prepare(Engine *e, TensorSlot &sl, int n, int naux_total, int q
   (void)e;
 }
 
+// Host full-square slabs -> device, lower triangles only: the packed layout never reads
+// mu < nu, so only n(n+1)/2 of the n*n doubles of a slab cross PCIe.  The caller's array is
+// pageable (a Fortran allocatable), which the driver would stage through its own pinned
+// buffer anyway; here the staging copy gathers just the lower-triangle column segments
+// (column nu: rows nu..n-1, contiguous) into one of TWO pinned buffers, so that gathering
+// chunk k+1 on the host overlaps the DMA and the packing kernel of chunk k.
+static size_t lower_len(int n) { return (size_t)n * (n + 1) / 2; }
+
+static void gather_lower(const double *src, int n, size_t q_count, size_t src_slab_stride, double *dst) {
+  const size_t tri = lower_len(n);
+  auto work = [&](size_t q_lo, size_t q_hi) {
+    for (size_t q = q_lo; q < q_hi; ++q) {
+      const double *s_q = src + q * src_slab_stride;
+      double *d_q = dst + q * tri;
+      size_t off = 0;
+      for (int nu = 0; nu < n; ++nu) {
+        std::memcpy(d_q + off, s_q + (size_t)nu * n + nu, (size_t)(n - nu) * sizeof(double));
+        off += (size_t)(n - nu);
+      }
+    }
+  };
+  const size_t bytes = q_count * tri * sizeof(double);
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t n_threads = bytes >= ((size_t)16 << 20) ? std::min<size_t>({(size_t)8, (size_t)(hw ? hw : 1), q_count}) : 1;
+  if (n_threads <= 1) { work(0, q_count); return; }
+  std::vector<std::thread> pool;
+  for (size_t t = 0; t < n_threads; ++t)
+    pool.emplace_back(work, q_count * t / n_threads, q_count * (t + 1) / n_threads);
+  for (auto &th : pool) th.join();
+}
+
+// `consume(d_lower, q0, qc)` is called (stream-ordered) for every staged chunk of lower-packed slabs.
+template <class Consume>
+static void stream_lower_slabs(Engine *e, const double *b, int n, size_t q_count, size_t slab_stride, Consume consume) {
+  if (q_count == 0) return;
+  const size_t tri = lower_len(n);
+  size_t chunk = std::max<size_t>(1, ((size_t)64 << 20) / (tri * sizeof(double)));
+  chunk = std::min(chunk, q_count);
+  const size_t n_chunks = (q_count + chunk - 1) / chunk;
+  const int n_buf = n_chunks > 1 ? 2 : 1;
+  for (int i = 0; i < n_buf; ++i) {
+    e->h_stage[i].ensure(chunk * tri * sizeof(double));
+    e->d_stage_lower[i].ensure(chunk * tri * sizeof(double));
+    if (!e->ev_stage[i]) CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
+  }
+  for (size_t k = 0, q0 = 0; q0 < q_count; ++k, q0 += chunk) {
+    const size_t qc = std::min(chunk, q_count - q0);
+    const int buf = (int)(k % n_buf);
+    if (k >= (size_t)n_buf) CUDA_CHECK(cudaEventSynchronize(e->ev_stage[buf]));   // its previous DMA + packing are done
+    gather_lower(b + q0 * slab_stride, n, qc, slab_stride, e->h_stage[buf].d());
+    CUDA_CHECK(cudaMemcpyAsync(e->d_stage_lower[buf].ptr, e->h_stage[buf].ptr, qc * tri * sizeof(double),
+                               cudaMemcpyHostToDevice, e->stream));
+    consume(e->d_stage_lower[buf].d(), q0, qc);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(e->ev_stage[buf], e->stream));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+}
+
 static void set_tensor_host(Engine *e, int slot, int n, int naux_total, int q_begin, int q_count,
                             const double *b) {
   if (slot < 0 || slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
@@ -382,19 +594,21 @@ static void set_tensor_host(Engine *e, int slot, int n, int naux_total, int q_be
   e->bind();
   TensorSlot &sl = e->slots[slot];
   slot_prepare(e, sl, n, naux_total, q_begin, q_count);
-  const size_t slab = (size_t)n * n;
-  // stage full-square slabs through a bounded device buffer, pack chunk by chunk
-  size_t chunk = std::max<size_t>(1, ((size_t)512 << 20) / (slab * sizeof(double)));
-  chunk = std::min<size_t>(chunk, (size_t)std::max(q_count, 1));
-  e->d_stage.ensure(chunk * slab * sizeof(double));
-  for (size_t q0 = 0; q0 < (size_t)q_count; q0 += chunk) {
-    const size_t qc = std::min(chunk, (size_t)q_count - q0);
-    CUDA_CHECK(cudaMemcpyAsync(e->d_stage.ptr, b + q0 * slab, qc * slab * sizeof(double), cudaMemcpyHostToDevice,
-                               e->stream));
-    launch_pack_tensor(e->d_stage.d(), n, (int)qc, sl.packed.d() + q0 * (size_t)sl.L, e->stream);
-    CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaStreamSynchronize(e->stream));  // the staging buffer is reused
-  }
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  CUDA_CHECK(cudaEventCreate(&t0));
+  CUDA_CHECK(cudaEventCreate(&t1));
+  CUDA_CHECK(cudaEventRecord(t0, e->stream));
+  stream_lower_slabs(e, b, n, (size_t)q_count, (size_t)n * n, [&](const double *d_lower, size_t q0, size_t qc) {
+    launch_pack_tensor_lower(d_lower, n, (int)qc, sl.packed.d() + q0 * (size_t)sl.L, e->stream);
+  });
+  CUDA_CHECK(cudaEventRecord(t1, e->stream));
+  CUDA_CHECK(cudaEventSynchronize(t1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, t0, t1);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  e->set_tensor_ms = ms;
+  e->set_tensor_h2d_bytes = (double)q_count * (double)lower_len(n) * sizeof(double);
   sl.set = true;
 }
 
@@ -418,7 +632,7 @@ struct BuildArgs {
 };
 
 static void run_k(Engine *e, const TensorSlot &sl, const double *d_coeff, int ldc, int n_occ, double *d_kpart_out,
-                  double *d_gamma_part, KPlan &plan) {
+                  double *d_gamma_part, KPlan &plan, cudaEvent_t ev_last_half = nullptr) {
   const int n = sl.n;
   plan = plan_k(n, n_occ, sl.q_count, e->workspace_limit, e->sm_count);
   e->d_ctf.ensure((size_t)num_tiles(n) * plan.nib * 128 * sizeof(double));
@@ -436,6 +650,7 @@ static void run_k(Engine *e, const TensorSlot &sl, const double *d_coeff, int ld
     launch_k_half_transform(sl.packed.d() + (size_t)q0 * sl.L, sl.L, n, qc, e->d_ctf.d(), d_cep, plan, e->d_x.d(),
                             d_gamma_part ? d_gamma_part + (size_t)q0 * plan.gamma_stride : nullptr, e->stream);
     e->phase_end(T_K1);
+    if (ev_last_half && q0 + plan.q_chunk >= sl.q_count) CUDA_CHECK(cudaEventRecord(ev_last_half, e->stream));
     e->phase_begin(T_K2);
     launch_k_accumulate(e->d_x.d(), qc, plan, d_kpart_out, chunk > 0, e->stream);
     e->phase_end(T_K2);
@@ -459,6 +674,10 @@ static void build(Engine *e, const BuildArgs &a) {
   const bool sharded = e->comm != nullptr;
   if (sharded && sl.naux_total == sl.q_count && e->n_ranks > 1)
     throw Failure("mqcb200: a communicator is active but this slot holds the whole tensor; use mqcb200_set_tensor_shard");
+  if (sharded && e->n_ranks > 1 && e->p2p.ready) {
+    p2p_raise_if_failed(e);              // an asynchronous build's exchange gave up since the last call
+    if (e->p2p.failed) p2p_recover(e);   // collective: every rank of a failed exchange comes through here
+  }
 
   // ---- operands on the device
   const double *d_h = nullptr, *d_density = nullptr, *d_ca = nullptr, *d_cb = nullptr;
@@ -466,8 +685,10 @@ static void build(Engine *e, const BuildArgs &a) {
   bool small_io = false;
   const double *late_h = nullptr, *late_d = nullptr;   // host H / D still to be uploaded (large operand sets)
   size_t late_oh = 0, late_od = 0;
+  bool late_issued = false;
   auto late_upload = [&]() {
     if (!late_h && !late_d) return;
+    late_issued = true;
     double *din = e->d_in.d();
     if (late_d) CUDA_CHECK(cudaMemcpyAsync(din + late_od, late_d, nn * sizeof(double), cudaMemcpyHostToDevice, e->copy_stream));
     if (late_h) CUDA_CHECK(cudaMemcpyAsync(din + late_oh, late_h, nn * sizeof(double), cudaMemcpyHostToDevice, e->copy_stream));
@@ -585,22 +806,28 @@ static void build(Engine *e, const BuildArgs &a) {
   } else {
 
   // ---- Coulomb vector from the half-transform when the density is the orbitals' own
-  // (D = f C C^T: every SCF iteration).  Decided on the device by an exact consistency
-  // check, so an arbitrary density (guess, response, user-supplied) silently takes the
-  // general pass over B instead.  Only worth its three extra tiny launches on tensors
-  // whose pass over B is not itself tiny.
+  // (D = f C C^T: every SCF iteration).  Decided on the device by a consistency check fused
+  // into the density packing, so an arbitrary density (guess, response, user-supplied)
+  // silently takes the general pass over B instead.
   const bool fuse = do_j && do_ka && have && fuse_gamma_enabled() &&
                     (size_t)sl.L * (size_t)sl.q_count * sizeof(double) >= e->fuse_threshold &&
                     (!a.two_spin || do_kb || a.n_b == 0);
   int *d_flag = nullptr;
   KPlan kp{}, kpb{};
   e->last_fuse_attempted = fuse;
+  // The Coulomb kernels are HBM-bound, the exchange kernels tensor-bound: with both to do they
+  // run on two streams.  ev_fork orders the Coulomb stream after everything the main stream
+  // held when this build began (operands of a device build, the previous build's consumers).
+  const bool overlap = e->overlap_j && do_j && have && (do_ka || do_kb);
+  cudaStream_t js = overlap ? e->j_stream : e->stream;
+  if (overlap) CUDA_CHECK(cudaEventRecord(e->ev_fork, e->stream));
   // ---- K (alpha / closed shell); K (beta) reuses the scratch after alpha has been finalized
   if (do_ka && have) {
     KPlan probe = plan_k(n, a.n_a, sl.q_count, e->workspace_limit, e->sm_count);
     e->d_kpart.ensure(probe.kpart_elems * sizeof(double));
     if (fuse) e->d_gpart_a.ensure((size_t)probe.gamma_stride * sl.q_count * sizeof(double));
-    run_k(e, sl, d_ca, lda, a.n_a, e->d_kpart.d(), fuse ? e->d_gpart_a.d() : nullptr, kp);
+    run_k(e, sl, d_ca, lda, a.n_a, e->d_kpart.d(), fuse ? e->d_gpart_a.d() : nullptr, kp,
+          (overlap && fuse && !do_kb) ? e->ev_k1_done : nullptr);
   }
   if (do_kb) {
     if (have) {
@@ -615,7 +842,8 @@ static void build(Engine *e, const BuildArgs &a) {
       KPlan probe = plan_k(n, a.n_b, sl.q_count, e->workspace_limit, e->sm_count);
       e->d_kpart.ensure(probe.kpart_elems * sizeof(double));  // stream-ordered: the finalize above has consumed it
       if (fuse) e->d_gpart_b.ensure((size_t)probe.gamma_stride * sl.q_count * sizeof(double));
-      run_k(e, sl, d_cb, ldb, a.n_b, e->d_kpart.d(), fuse ? e->d_gpart_b.d() : nullptr, kpb);
+      run_k(e, sl, d_cb, ldb, a.n_b, e->d_kpart.d(), fuse ? e->d_gpart_b.d() : nullptr, kpb,
+            (overlap && fuse) ? e->ev_k1_done : nullptr);
       e->phase_begin(T_FINAL);
       launch_finalize_jk(nullptr, 0, e->d_kpart.d(), kpb.n_splits, kpb.ktile, n, kfac, nullptr, d_kb, e->stream,
                          nullptr, 0.0, 0.0, nullptr, kpb.n_splits_diag);
@@ -628,37 +856,43 @@ static void build(Engine *e, const BuildArgs &a) {
 
   // ---- H and D arrive now (they were not needed by the exchange kernels launched above)
   late_upload();
-  if (fuse) {
-    unsigned long long *scratch = reinterpret_cast<unsigned long long *>(static_cast<char *>(e->d_scalar.ptr) + 16);
-    d_flag = reinterpret_cast<int *>(static_cast<char *>(e->d_scalar.ptr) + 32);
-    e->phase_begin(T_J1);
-    launch_density_consistency(d_density, n, d_ca, lda, a.n_a, do_kb ? d_cb : nullptr, ldb, do_kb ? a.n_b : 0, kfac,
-                               scratch, d_flag, e->stream);
-    e->phase_end(T_J1);
-    e->launches += 2;
-  }
 
   // ---- J
   if (do_j && have) {
+    if (overlap) {
+      CUDA_CHECK(cudaStreamWaitEvent(js, e->ev_fork, 0));
+      if (late_issued) CUDA_CHECK(cudaStreamWaitEvent(js, e->ev_late_upload, 0));
+    }
     e->d_w.ensure((size_t)sl.L * sizeof(double));
     e->d_gamma_partial.ensure(jp.gamma_partial_elems * sizeof(double));
     e->d_gamma.ensure((size_t)sl.q_count * sizeof(double));
     e->d_jpart.ensure(jp.j_partial_elems * sizeof(double));
-    e->phase_begin(T_J1);
-    launch_pack_density(d_density, n, e->d_w.d(), d_flag, e->stream);
-    launch_j_gamma(sl.packed.d(), sl.L, sl.q_count, e->d_w.d(), jp, e->d_gamma_partial.d(), e->d_gamma.d(), d_flag,
-                   e->stream);
+    e->phase_begin(T_J1, js);
+    if (fuse) {
+      unsigned long long *scratch = reinterpret_cast<unsigned long long *>(static_cast<char *>(e->d_scalar.ptr) + 64);
+      d_flag = reinterpret_cast<int *>(static_cast<char *>(e->d_scalar.ptr) + 32);
+      launch_density_prep(d_density, n, e->d_w.d(), d_ca, lda, a.n_a, do_kb ? d_cb : nullptr, ldb, do_kb ? a.n_b : 0,
+                          kfac, scratch, d_flag, js);
+    } else {
+      launch_pack_density(d_density, n, e->d_w.d(), nullptr, js);
+    }
+    launch_j_gamma(sl.packed.d(), sl.L, sl.q_count, e->d_w.d(), jp, e->d_gamma_partial.d(), e->d_gamma.d(), d_flag, js);
     e->launches += 3;
     if (fuse) {
+      if (overlap) CUDA_CHECK(cudaStreamWaitEvent(js, e->ev_k1_done, 0));
       launch_gamma_from_x(e->d_gpart_a.d(), kp.gamma_stride, do_kb ? e->d_gpart_b.d() : nullptr, kpb.gamma_stride, kfac,
-                          sl.q_count, d_flag, e->d_gamma.d(), e->stream);
+                          sl.q_count, d_flag, e->d_gamma.d(), js);
       e->launches += 1;
     }
-    e->phase_end(T_J1);
-    e->phase_begin(T_J2);
-    launch_j_accumulate(sl.packed.d(), sl.L, sl.q_count, e->d_gamma.d(), jp, e->d_jpart.d(), e->stream);
-    e->phase_end(T_J2);
+    e->phase_end(T_J1, js);
+    e->phase_begin(T_J2, js);
+    launch_j_accumulate(sl.packed.d(), sl.L, sl.q_count, e->d_gamma.d(), jp, e->d_jpart.d(), js);
+    e->phase_end(T_J2, js);
     e->launches += 1;
+    if (overlap) {
+      CUDA_CHECK(cudaEventRecord(e->ev_j_done, js));
+      CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_j_done, 0));
+    }
   }
 
     n_ksplits = kp.n_splits;
@@ -710,8 +944,7 @@ static void build(Engine *e, const BuildArgs &a) {
         Engine::P2P &x = e->p2p;
         ++x.epoch;
         launch_xgpu_allreduce(x.peers, e->n_ranks, e->rank, x.epoch, first * nn, (last - first) * nn,
-                              static_cast<unsigned int *>(x.misc), reinterpret_cast<int *>(static_cast<char *>(x.misc) + 16),
-                              e->stream);
+                              static_cast<unsigned int *>(x.misc), x.dev_error, x.timeout_ns, e->stream);
         e->launches += 1;
         d_j = static_cast<double *>(x.out);
         d_ka = d_j + nn;
@@ -804,13 +1037,9 @@ static void build(Engine *e, const BuildArgs &a) {
     e->phase_end(T_DOWNLOAD);
   }
   CUDA_CHECK(cudaGetLastError());
-  if (p2p_used && a.sync)
-    CUDA_CHECK(cudaMemcpyAsync(&e->p2p.host_error, static_cast<char *>(e->p2p.misc) + 16, sizeof(int),
-                               cudaMemcpyDeviceToHost, e->stream));
   if (a.sync) {
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    if (p2p_used && e->p2p.host_error)
-      throw Failure("mqcb200: the cross-GPU exchange timed out waiting for a peer rank (a rank failed or fell behind by > 2 s)");
+    if (p2p_used) p2p_raise_if_failed(e);
     for (int i = 0; i < n_pending; ++i) std::memcpy(pending[i].dst, pending[i].src, pending[i].bytes);
     if (energy_pending) e->last_energy_host = e->h_out.d()[0];
     if (!a.device_operands && !a.assemble && a.k_a && a.want_k && !do_ka) std::memset(a.k_a, 0, nn * sizeof(double));
@@ -885,8 +1114,18 @@ int mqcb200_create(int device_rank, void **handle) {
     e->sm_count = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    {
+      int least = 0, greatest = 0;
+      CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      CUDA_CHECK(cudaStreamCreateWithPriority(&e->j_stream, cudaStreamNonBlocking, greatest));
+    }
     CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_late_upload, cudaEventDisableTiming));
-    e->d_scalar.ensure(64);
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_k1_done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_j_done, cudaEventDisableTiming));
+    if (const char *env = getenv("MQCB200_OVERLAP_J")) e->overlap_j = !(env[0] == '0');
+    e->d_scalar.ensure(128);
+    CUDA_CHECK(cudaMemsetAsync(e->d_scalar.ptr, 0, 128, e->stream));
     e->d_escratch.ensure(160 * sizeof(double));
     CUDA_CHECK(cudaMemsetAsync(e->d_escratch.ptr, 0, 160 * sizeof(double), e->stream));
     configure_kernels();
@@ -913,12 +1152,19 @@ int mqcb200_destroy(void *handle) {
   for (DevBuf *b : bufs) b->release();
   e->h_in.release();
   e->h_out.release();
+  for (int i = 0; i < 2; ++i) {
+    e->h_stage[i].release();
+    e->d_stage_lower[i].release();
+    if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
+  }
   for (auto &sp : e->spans) {
     cudaEventDestroy(sp.a);
     cudaEventDestroy(sp.b);
   }
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-  if (e->ev_late_upload) cudaEventDestroy(e->ev_late_upload);
+  if (e->j_stream) cudaStreamDestroy(e->j_stream);
+  for (cudaEvent_t ev : {e->ev_late_upload, e->ev_fork, e->ev_k1_done, e->ev_j_done})
+    if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   e->magic = 0;
   delete e;
@@ -942,6 +1188,23 @@ int mqcb200_set_workspace_limit(void *handle, size_t bytes) {
 int mqcb200_set_fuse_threshold(void *handle, size_t bytes) {
   GET_ENGINE(handle)
   e->fuse_threshold = bytes;
+  return MQCB200_OK;
+}
+
+int mqcb200_set_overlap(void *handle, int on) {
+  GET_ENGINE(handle)
+  e->overlap_j = on != 0;
+  return MQCB200_OK;
+}
+
+int mqcb200_tensor_shape(void *handle, int slot, int *n, int *naux_total, int *q_begin, int *q_count) {
+  GET_ENGINE(handle)
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS) { g_last_error = "mqcb200: tensor slot out of range"; return MQCB200_FAIL; }
+  const TensorSlot &sl = e->slots[slot];
+  if (n) *n = sl.set ? sl.n : 0;
+  if (naux_total) *naux_total = sl.set ? sl.naux_total : 0;
+  if (q_begin) *q_begin = sl.set ? sl.q_begin : 0;
+  if (q_count) *q_count = sl.set ? sl.q_count : 0;
   return MQCB200_OK;
 }
 
@@ -972,18 +1235,9 @@ int mqcb200_set_tensor_from_3c(void *handle, int slot, int n, int naux, const do
   slot_prepare(e, sl, n, naux, 0, naux);
   try {
     tp.ensure((size_t)sl.L * (size_t)naux * sizeof(double));
-    const size_t slab = (size_t)n * n;
-    size_t chunk = std::max<size_t>(1, ((size_t)512 << 20) / (slab * sizeof(double)));
-    chunk = std::min<size_t>(chunk, (size_t)naux);
-    e->d_stage.ensure(chunk * slab * sizeof(double));
-    for (size_t q0 = 0; q0 < (size_t)naux; q0 += chunk) {
-      const size_t qc = std::min(chunk, (size_t)naux - q0);
-      CUDA_CHECK(cudaMemcpyAsync(e->d_stage.ptr, three + q0 * slab, qc * slab * sizeof(double),
-                                 cudaMemcpyHostToDevice, e->stream));
-      launch_pack_tensor(e->d_stage.d(), n, (int)qc, tp.d() + q0 * (size_t)sl.L, e->stream);
-      CUDA_CHECK(cudaGetLastError());
-      CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    }
+    stream_lower_slabs(e, three, n, (size_t)naux, (size_t)n * n, [&](const double *d_lower, size_t q0, size_t qc) {
+      launch_pack_tensor_lower(d_lower, n, (int)qc, tp.d() + q0 * (size_t)sl.L, e->stream);
+    });
     // 2. metric^(-1/2) to the device, 3. Bp = half . Tp
     DevBuf d_half, d_af;
     try {
@@ -1193,30 +1447,9 @@ int mqcb200_comm_init(void *handle, int n_ranks, int rank, const char id[128]) {
   e->comm = comm;
   e->n_ranks = n_ranks;
   e->rank = rank;
-  // NVLink peer-memory exchange: set up collectively, then agree -- unless EVERY rank mapped its
-  // peers the build uses the NCCL all-reduce (a mixed choice would deadlock)
-  int mine_ok = 0;
-  try {
-    p2p_setup(e);
-    mine_ok = e->p2p.ready ? 1 : 0;
-  } catch (const std::exception &) {
-    mine_ok = 0;
-  }
-  {
-    DevBuf sb, rb;
-    sb.ensure(sizeof(int));
-    rb.ensure(sizeof(int) * n_ranks);
-    std::vector<int> all(n_ranks, 0);
-    CUDA_CHECK(cudaMemcpyAsync(sb.ptr, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    NCCL_CHECK(g_nccl.AllGather(sb.ptr, rb.ptr, sizeof(int), kNcclChar, e->comm, e->stream));
-    CUDA_CHECK(cudaMemcpyAsync(all.data(), rb.ptr, sizeof(int) * n_ranks, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    sb.release();
-    rb.release();
-    bool everyone = true;
-    for (int v : all) everyone = everyone && v == 1;
-    e->p2p.ready = everyone && mine_ok == 1;
-  }
+  // NVLink peer-memory exchange: set up collectively; unless EVERY rank mapped its peers the
+  // builds use the NCCL all-reduce (p2p_setup agrees on that itself; a mixed choice would deadlock)
+  if (n_ranks > 1) p2p_setup(e);
   API_END
 }
 
@@ -1298,7 +1531,16 @@ int mqcb200_last_timings(void *handle, double ms[MQCB200_NUM_TIMERS]) {
   CUDA_CHECK(cudaStreamSynchronize(e->stream));
   e->collect_timers();
   for (int i = 0; i < MQCB200_NUM_TIMERS; ++i) ms[i] = e->last_ms[i];
+  if (e->comm && e->n_ranks > 1) p2p_raise_if_failed(e);   // an asynchronous build's exchange that gave up
   API_END
+}
+
+int mqcb200_last_set_tensor(void *handle, double *ms, double *h2d_bytes) {
+  GET_ENGINE(handle)
+  if (!ms || !h2d_bytes) { g_last_error = "mqcb200: null output pointer"; return MQCB200_FAIL; }
+  *ms = e->set_tensor_ms;
+  *h2d_bytes = e->set_tensor_h2d_bytes;
+  return MQCB200_OK;
 }
 
 int mqcb200_last_whiten(void *handle, double *ms, double *flops) {

@@ -10,6 +10,9 @@ namespace mqcb200 {
 // ---- layout / preparation -------------------------------------------------
 // Full-square slabs (q_count of them, each n*n column-major) -> packed rows.
 void launch_pack_tensor(const double *d_full, int n, int q_count, double *d_packed, cudaStream_t s);
+// Same from LOWER-packed slabs: slab q holds its columns nu = 0..n-1 one after the other, column
+// nu being rows nu..n-1 (n(n+1)/2 doubles per slab) -- what set_tensor ships over PCIe.
+void launch_pack_tensor_lower(const double *d_lower, int n, int q_count, double *d_packed, cudaStream_t s);
 // Counter-based synthetic tensor written directly in packed form.
 void launch_synth_tensor(double *d_packed, int n, int q_global_begin, int q_count, uint64_t seed,
                          double scale, cudaStream_t s);
@@ -51,8 +54,10 @@ struct XgpuPeers {                         // device-addressable pointers of eve
   unsigned long long *flags[XGPU_MAX_RANKS];   // [2*XGPU_MAX_RANKS] arrival epochs per rank
 };
 // out[k][first..first+count) = sum_r in[r][first..first+count) on every rank k, in rank order.
+// d_error: device-addressable HOST-mapped int, set to 1 when a peer did not arrive within timeout_ns.
 void launch_xgpu_allreduce(const XgpuPeers &peers, int n_ranks, int rank, unsigned long long epoch, size_t first,
-                           size_t count, unsigned int *d_counter, int *d_error, cudaStream_t s);
+                           size_t count, unsigned int *d_counter, int *d_error, unsigned long long timeout_ns,
+                           cudaStream_t s);
 
 // ---- J: two passes over the packed tensor -----------------------------------
 struct JPlan {
@@ -70,10 +75,13 @@ void launch_j_gamma(const double *d_packed, long long L, int q_count, const doub
 // gamma[q] = factor * (sum of part_a[q][:] + sum of part_b[q][:]) if *d_flag, else untouched.
 void launch_gamma_from_x(const double *d_part_a, int stride_a, const double *d_part_b, int stride_b,
                          double factor, int q_count, const int *d_flag, double *d_gamma, cudaStream_t s);
-// *d_flag = 1 iff max|D - f*(Ca Ca^T + Cb Cb^T)| <= 1e-13 * max(1, max|D|).  d_scratch: 16 bytes.
-void launch_density_consistency(const double *d_density, int n, const double *d_ca, int lda, int na,
-                                const double *d_cb, int ldb, int nb, double f, unsigned long long *d_scratch,
-                                int *d_flag, cudaStream_t s);
+// w[L] like launch_pack_density AND, in the same pass, *d_flag = 1 iff the density is the
+// orbitals' own: max|D - f*(Ca Ca^T + Cb Cb^T)| <= 4*2^-53*max(n_a+n_b,16) * max(1, max|D|) over
+// BOTH triangles, every element finite.  d_scratch: 24 bytes, zero before the first call (the
+// kernel leaves it zero).  Maxima are order-independent, so the decision is deterministic.
+void launch_density_prep(const double *d_density, int n, double *d_w, const double *d_ca, int lda, int na,
+                         const double *d_cb, int ldb, int nb, double f, unsigned long long *d_scratch,
+                         int *d_flag, cudaStream_t s);
 void launch_j_accumulate(const double *d_packed, long long L, int q_count, const double *d_gamma,
                          const JPlan &plan, double *d_jpart, cudaStream_t s);
 

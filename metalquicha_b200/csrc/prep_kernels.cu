@@ -39,6 +39,22 @@ __global__ void __launch_bounds__(256) pack_tensor_kernel(const double *__restri
   packed[(size_t)q * L + (size_t)blockIdx.x * TILE_ELEMS + in_tile_offset(r, c)] = v;
 }
 
+__global__ void __launch_bounds__(256) pack_tensor_lower_kernel(const double *__restrict__ lower, int n, int nt,
+                                                                long long L, double *__restrict__ packed) {
+  int tr, tc;
+  tile_coords(blockIdx.x, nt, tr, tc);
+  const int q = blockIdx.y;
+  const int r = threadIdx.x & 15, c = threadIdx.x >> 4;
+  int mu = tr * TILE + r, nu = tc * TILE + c;
+  double v = 0.0;
+  if (mu < n && nu < n) {
+    if (mu < nu) { int t = mu; mu = nu; nu = t; }  // diagonal tile: mirror the lower triangle
+    const size_t tri = (size_t)n * (n + 1) / 2;
+    v = lower[(size_t)q * tri + (size_t)nu * n - ((size_t)nu * (nu - 1)) / 2 + (size_t)(mu - nu)];
+  }
+  packed[(size_t)q * L + (size_t)blockIdx.x * TILE_ELEMS + in_tile_offset(r, c)] = v;
+}
+
 __global__ void __launch_bounds__(256) synth_tensor_kernel(double *__restrict__ packed, int n, int nt,
                                                            long long L, int q_global_begin, uint64_t seed,
                                                            double inv_width, double scale) {
@@ -229,6 +245,17 @@ void launch_pack_tensor(const double *d_full, int n, int q_count, double *d_pack
   }
 }
 
+void launch_pack_tensor_lower(const double *d_lower, int n, int q_count, double *d_packed, cudaStream_t s) {
+  const int nt = num_tiles(n);
+  const long long L = packed_row_len(n);
+  const size_t tri = (size_t)n * (n + 1) / 2;
+  for (int q0 = 0; q0 < q_count; q0 += 65535) {
+    const int qc = q_count - q0 < 65535 ? q_count - q0 : 65535;
+    dim3 grid((unsigned)num_lower_tiles(nt), (unsigned)qc);
+    pack_tensor_lower_kernel<<<grid, 256, 0, s>>>(d_lower + (size_t)q0 * tri, n, nt, L, d_packed + (size_t)q0 * L);
+  }
+}
+
 void launch_synth_tensor(double *d_packed, int n, int q_global_begin, int q_count, uint64_t seed,
                          double scale, cudaStream_t s) {
   const int nt = num_tiles(n);
@@ -247,47 +274,69 @@ void launch_pack_density(const double *d_density, int n, double *d_w, const int 
   pack_density_kernel<<<(unsigned)num_lower_tiles(nt), 256, 0, s>>>(d_density, n, nt, d_w, d_skip_flag);
 }
 
-// max |D - f (Ca Ca^T + Cb Cb^T)| and max |D| over the matrix (order-independent maxima,
-// so the result -- and with it the choice of Coulomb-vector path -- is deterministic).
-__global__ void __launch_bounds__(256) density_consistency_kernel(const double *__restrict__ d, int n,
-                                                                  const double *__restrict__ ca, int lda, int na,
-                                                                  const double *__restrict__ cb, int ldb, int nb,
-                                                                  double f, unsigned long long *__restrict__ out) {
-  const int mu = blockIdx.x * 16 + (threadIdx.x & 15);
-  const int nu = blockIdx.y * 16 + (threadIdx.x >> 4);
-  double resid = 0.0, dabs = 0.0;
+// Density packing (w[L], as pack_density_kernel) fused with the on-device decision whether the
+// density is the orbitals' own, D == f (Ca Ca^T + Cb Cb^T): one CTA per lower-triangular tile,
+// one thread per element, BOTH triangles of D compared (an asymmetric D is not an orbital
+// product).  Block maxima go through integer atomicMax (non-negative doubles order as integers;
+// a NaN/Inf anywhere is mapped to +Inf so it can never be dropped by a max), the block that
+// finishes last turns them into the flag and re-zeroes the scratch for the next build.
+// scratch: [0] max residual, [1] max |D| (u64 each), [2] u32 arrival counter.
+__global__ void __launch_bounds__(256) density_prep_kernel(const double *__restrict__ d, int n, int nt,
+                                                           double *__restrict__ w,
+                                                           const double *__restrict__ ca, int lda, int na,
+                                                           const double *__restrict__ cb, int ldb, int nb,
+                                                           double f, double tol_rel,
+                                                           unsigned long long *__restrict__ scratch,
+                                                           int *__restrict__ flag) {
+  int tr, tc;
+  tile_coords(blockIdx.x, nt, tr, tc);
+  const int r = threadIdx.x & 15, c = threadIdx.x >> 4;
+  const int mu = tr * TILE + r, nu = tc * TILE + c;
+  double v = 0.0, resid = 0.0, dabs = 0.0;
   if (mu < n && nu < n) {
+    const double lo = d[(size_t)mu + (size_t)n * nu];
+    const double up = tr != tc ? d[(size_t)nu + (size_t)n * mu] : lo;
+    v = tr != tc ? lo + up : lo;
     double s = 0.0;
     for (int i = 0; i < na; ++i) s = fma(ca[(size_t)mu + (size_t)lda * i], ca[(size_t)nu + (size_t)lda * i], s);
     for (int i = 0; i < nb; ++i) s = fma(cb[(size_t)mu + (size_t)ldb * i], cb[(size_t)nu + (size_t)ldb * i], s);
-    const double dv = d[(size_t)mu + (size_t)n * nu];
-    resid = fabs(dv - f * s);
-    dabs = fabs(dv);
+    resid = fmax(fabs(lo - f * s), fabs(up - f * s));
+    dabs = fmax(fabs(lo), fabs(up));
+    if (!isfinite(lo) || !isfinite(up) || !isfinite(s)) resid = __longlong_as_double(0x7ff0000000000000ll);
   }
+  w[(size_t)blockIdx.x * TILE_ELEMS + in_tile_offset(r, c)] = v;
   for (int o = 16; o > 0; o >>= 1) {
     resid = fmax(resid, __shfl_xor_sync(0xffffffffu, resid, o));
     dabs = fmax(dabs, __shfl_xor_sync(0xffffffffu, dabs, o));
   }
+  __shared__ bool last;
   if ((threadIdx.x & 31) == 0) {
-    atomicMax(out, (unsigned long long)__double_as_longlong(resid));       // non-negative doubles order as integers
-    atomicMax(out + 1, (unsigned long long)__double_as_longlong(dabs));
+    atomicMax(scratch, (unsigned long long)__double_as_longlong(resid));
+    atomicMax(scratch + 1, (unsigned long long)__double_as_longlong(dabs));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int *>(scratch + 2), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    const double rmax = __longlong_as_double((long long)atomicExch(scratch, 0ull));
+    const double dmax = __longlong_as_double((long long)atomicExch(scratch + 1, 0ull));
+    *flag = (rmax <= tol_rel * fmax(1.0, dmax)) ? 1 : 0;
+    *reinterpret_cast<unsigned int *>(scratch + 2) = 0u;
   }
 }
 
-__global__ void consistency_flag_kernel(const unsigned long long *__restrict__ in, int *__restrict__ flag) {
-  const double resid = __longlong_as_double((long long)in[0]);
-  const double dmax = __longlong_as_double((long long)in[1]);
-  *flag = (resid <= 1.0e-13 * fmax(1.0, dmax)) ? 1 : 0;
-}
-
-void launch_density_consistency(const double *d_density, int n, const double *d_ca, int lda, int na,
-                                const double *d_cb, int ldb, int nb, double f, unsigned long long *d_scratch,
-                                int *d_flag, cudaStream_t s) {
-  cudaMemsetAsync(d_scratch, 0, 2 * sizeof(unsigned long long), s);
+void launch_density_prep(const double *d_density, int n, double *d_w, const double *d_ca, int lda, int na,
+                         const double *d_cb, int ldb, int nb, double f, unsigned long long *d_scratch, int *d_flag,
+                         cudaStream_t s) {
   const int nt = num_tiles(n);
-  dim3 grid((unsigned)nt, (unsigned)nt);
-  density_consistency_kernel<<<grid, 256, 0, s>>>(d_density, n, d_ca, lda, na, d_cb, ldb, nb, f, d_scratch);
-  consistency_flag_kernel<<<1, 1, 0, s>>>(d_scratch, d_flag);
+  const int occ = na + nb > 16 ? na + nb : 16;
+  const double tol_rel = 4.0 * 1.1102230246251565e-16 * (double)occ;   // a few ulp per term of the orbital sum
+  density_prep_kernel<<<(unsigned)num_lower_tiles(nt), 256, 0, s>>>(d_density, n, nt, d_w, d_ca, lda, na, d_cb, ldb, nb, f,
+                                                                    tol_rel, d_scratch, d_flag);
 }
 
 void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib, double *d_ctf, double *d_cep,

@@ -12,7 +12,9 @@
 //      exits the whole reduced [J|K] is in local memory for the assembly kernel that follows.
 // Per rank: (N-1)/N of the span read and written over NVLink, two flag round trips.  The grid
 // is small enough to be co-resident (the CTAs wait on one another's GPUs, never on their own
-// later CTAs).  Spin loops give up after ~2 s and raise an error flag rather than hang.
+// later CTAs).  Spin loops give up after `timeout_ns` of wall time (%globaltimer; 30 s by
+// default, MQCB200_XGPU_TIMEOUT_S) and raise an error flag in HOST-mapped memory rather than
+// hang: the host sees it without a synchronisation, also after an asynchronous build.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -29,11 +31,19 @@ __device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long lon
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned long long epoch) {
-  const long long t0 = clock64();
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned long long epoch,
+                                          unsigned long long timeout_ns) {
+  if (ld_flag(p) >= epoch) return true;
+  const unsigned long long t0 = global_ns();
   while (ld_flag(p) < epoch) {
     __nanosleep(64);
-    if (clock64() - t0 > 4000000000ll) return false;   // ~2 s at 2 GHz
+    if (global_ns() - t0 > timeout_ns) return false;
   }
   return true;
 }
@@ -41,7 +51,8 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned 
 __global__ void __launch_bounds__(XG_THREADS) xgpu_allreduce_kernel(XgpuPeers peers, int n_ranks, int rank,
                                                                     unsigned long long epoch, size_t first,
                                                                     size_t count, unsigned int *counter,
-                                                                    int *error_flag) {
+                                                                    volatile int *error_flag,
+                                                                    unsigned long long timeout_ns) {
   unsigned long long *my_flags = peers.flags[rank];
   __shared__ int ok_s;
   if (threadIdx.x == 0) ok_s = 1;
@@ -52,10 +63,10 @@ __global__ void __launch_bounds__(XG_THREADS) xgpu_allreduce_kernel(XgpuPeers pe
     __threadfence_system();
     st_flag(peers.flags[threadIdx.x] + rank, epoch);
   }
-  if (threadIdx.x < n_ranks && !wait_flag(my_flags + threadIdx.x, epoch)) ok_s = 0;
+  if (threadIdx.x < n_ranks && !wait_flag(my_flags + threadIdx.x, epoch, timeout_ns)) ok_s = 0;
   __syncthreads();
   if (!ok_s) {
-    if (threadIdx.x == 0) *error_flag = 1;
+    if (threadIdx.x == 0) { *error_flag = 1; __threadfence_system(); }
     return;
   }
 
@@ -83,18 +94,20 @@ __global__ void __launch_bounds__(XG_THREADS) xgpu_allreduce_kernel(XgpuPeers pe
       st_flag(peers.flags[threadIdx.x] + XGPU_MAX_RANKS + rank, epoch);
     }
   }
-  if (threadIdx.x < n_ranks && !wait_flag(my_flags + XGPU_MAX_RANKS + threadIdx.x, epoch)) ok_s = 0;
+  if (threadIdx.x < n_ranks && !wait_flag(my_flags + XGPU_MAX_RANKS + threadIdx.x, epoch, timeout_ns)) ok_s = 0;
   __syncthreads();
-  if (!ok_s && threadIdx.x == 0) *error_flag = 1;
+  if (!ok_s && threadIdx.x == 0) { *error_flag = 1; __threadfence_system(); }
 }
 
 void launch_xgpu_allreduce(const XgpuPeers &peers, int n_ranks, int rank, unsigned long long epoch, size_t first,
-                           size_t count, unsigned int *d_counter, int *d_error, cudaStream_t s) {
+                           size_t count, unsigned int *d_counter, int *d_error, unsigned long long timeout_ns,
+                           cudaStream_t s) {
   size_t per = (count + n_ranks - 1) / n_ranks;
   unsigned blocks = (unsigned)((per + XG_THREADS * 4 - 1) / (XG_THREADS * 4));
   if (blocks < 1) blocks = 1;
   if (blocks > 128) blocks = 128;          // co-resident by construction (148 SMs, 256 threads, no smem)
-  xgpu_allreduce_kernel<<<blocks, XG_THREADS, 0, s>>>(peers, n_ranks, rank, epoch, first, count, d_counter, d_error);
+  xgpu_allreduce_kernel<<<blocks, XG_THREADS, 0, s>>>(peers, n_ranks, rank, epoch, first, count, d_counter, d_error,
+                                                      timeout_ns);
 }
 
 }  // namespace mqcb200

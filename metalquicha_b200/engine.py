@@ -44,14 +44,18 @@ def _check(rc: int) -> None:
         raise B200Error(rc, _lib.last_error())
 
 
-def _f64_colmajor(a, name: str) -> np.ndarray:
+def _f64_colmajor(a, name: str, allow_ld: bool = False) -> np.ndarray:
+    """Column-major float64 matrix.  Only the coefficient matrices carry a leading dimension
+    through the C ABI (``allow_ld``): every other operand is read as contiguous n*n, so a
+    strided view (``big[:n, :n]``) is copied."""
     arr = np.asarray(a)
     if arr.dtype != np.float64:
         raise TypeError(f"{name} must be float64 (the reference's real(dp)), got {arr.dtype}")
     if arr.ndim != 2:
         raise ValueError(f"{name} must be a matrix")
     if not arr.flags.f_contiguous:
-        if arr.strides[0] == arr.itemsize and arr.strides[1] >= arr.itemsize * arr.shape[0]:
+        if (allow_ld and arr.strides[0] == arr.itemsize and arr.strides[1] >= arr.itemsize * arr.shape[0]
+                and arr.strides[1] % arr.itemsize == 0):
             return arr                    # a column-major view with a leading dimension
         arr = np.asfortranarray(arr)
     return arr
@@ -104,6 +108,29 @@ class B200FockEngine:
 
     def set_fuse_threshold(self, n_bytes: int) -> None:
         _check(self._lib.mqcb200_set_fuse_threshold(self._h, c_size_t(int(n_bytes))))
+
+    def set_overlap(self, on: bool) -> None:
+        """Coulomb kernels on a second stream, concurrent with the exchange kernels (default on)."""
+        _check(self._lib.mqcb200_set_overlap(self._h, 1 if on else 0))
+
+    def tensor_shape(self, slot: int = SLOT_FULL_RANGE):
+        """``(n, naux_total, q_begin, q_count)`` of the resident tensor, zeros when the slot is empty."""
+        n, nt, qb, qc = c_int(0), c_int(0), c_int(0), c_int(0)
+        _check(self._lib.mqcb200_tensor_shape(self._h, slot, byref(n), byref(nt), byref(qb), byref(qc)))
+        return n.value, nt.value, qb.value, qc.value
+
+    def _check_operand(self, n: int, slot: int) -> None:
+        """The build calls carry no size: refuse operands that do not match the resident tensor
+        (a stale tensor of another fragment/geometry would be read out of bounds)."""
+        n_res = self.tensor_shape(slot)[0]
+        if n_res and n_res != n:
+            raise ValueError(f"the resident tensor has n = {n_res}, the operands have n = {n}")
+
+    def last_set_tensor(self):
+        """``(ms, h2d_bytes)`` of the last host -> packed tensor upload."""
+        ms, by = c_double(0.0), c_double(0.0)
+        _check(self._lib.mqcb200_last_set_tensor(self._h, byref(ms), byref(by)))
+        return ms.value, by.value
 
     # -- the fitted tensor ------------------------------------------------------------
     def set_tensor(self, b, n: int | None = None, slot: int = SLOT_FULL_RANGE) -> None:
@@ -175,8 +202,7 @@ class B200FockEngine:
         n = h.shape[0]
         if h.shape != (n, n) or density.shape != (n, n):
             raise ValueError("h and density must both be n x n")
-        if slot in self.n and self.n[slot] != n:
-            raise ValueError(f"the resident tensor has n = {self.n[slot]}, the operands have n = {n}")
+        self._check_operand(n, slot)
         coeff, ldc = self._coeff(coeff, n, n_occ)
         fock = out if out is not None else np.empty((n, n), dtype=np.float64, order="F")
         _check(self._lib.mqcb200_build_fock(
@@ -190,6 +216,8 @@ class B200FockEngine:
         """J and K of ``build_fock_df`` before scaling (K carries the RHF factor 2)."""
         n = self.n[slot]
         density = _f64_colmajor(density, "density") if density is not None else None
+        if density is not None and density.shape != (n, n):
+            raise ValueError(f"the resident tensor has n = {n}, the density is {density.shape}")
         coeff, ldc = self._coeff(coeff, n, n_occ) if want_k else (None, n)
         j = np.empty((n, n), dtype=np.float64, order="F") if want_j else None
         k = np.empty((n, n), dtype=np.float64, order="F") if want_k else None
@@ -202,6 +230,8 @@ class B200FockEngine:
         """J[Da+Db], K_alpha, K_beta (no factor 2); K_beta is ``None`` when n_beta == 0."""
         n = self.n[slot]
         density_total = _f64_colmajor(density_total, "density_total")
+        if density_total.shape != (n, n):
+            raise ValueError(f"the resident tensor has n = {n}, the density is {density_total.shape}")
         ca, lda = self._coeff(coeff_a, n, n_alpha)
         cb, ldb = self._coeff(coeff_b, n, n_beta) if n_beta > 0 else (None, n)
         j = np.empty((n, n), dtype=np.float64, order="F")
@@ -217,7 +247,10 @@ class B200FockEngine:
         """F_sigma = H + J[Da+Db] - k_scale*K[C_sigma]."""
         h = _f64_colmajor(h, "h")
         n = h.shape[0]
+        self._check_operand(n, slot)
         dt = np.asfortranarray(np.asarray(d_alpha) + np.asarray(d_beta))
+        if h.shape != (n, n) or dt.shape != (n, n):
+            raise ValueError("h and the spin densities must all be n x n")
         ca, lda = self._coeff(coeff_a, n, n_alpha)
         cb, ldb = self._coeff(coeff_b, n, n_beta) if n_beta > 0 else (None, n)
         fa = np.empty((n, n), dtype=np.float64, order="F")
@@ -231,6 +264,8 @@ class B200FockEngine:
     def _g_two_factor(self, density, ca, n_a, cb, n_b, ka, kb, slot):
         n = self.n[slot]
         density = _f64_colmajor(density, "density")
+        if density.shape != (n, n):
+            raise ValueError(f"the resident tensor has n = {n}, the density is {density.shape}")
         ca, lda = self._coeff(ca, n, n_a)
         cb, ldb = self._coeff(cb, n, n_b)
         g = np.empty((n, n), dtype=np.float64, order="F")
@@ -370,7 +405,7 @@ class B200FockEngine:
     def _coeff(coeff, n: int, n_occ: int):
         if n_occ == 0:
             return None, n
-        coeff = _f64_colmajor(coeff, "coeff")
+        coeff = _f64_colmajor(coeff, "coeff", allow_ld=True)
         if coeff.shape[0] != n or coeff.shape[1] < n_occ:
             raise ValueError("coeff must be (n, >= n_occ)")
         ldc = coeff.strides[1] // coeff.itemsize if coeff.shape[1] > 1 else max(n, coeff.shape[0])

@@ -16,23 +16,34 @@ one-thread-per-GPU hosts.
 """
 from __future__ import annotations
 
+import threading
 from typing import Callable, Iterable, Sequence
 
 
 class DistributedWorkQueue:
     """``queue_t`` shared by all ranks of a process group through its store."""
 
-    def __init__(self, ids: Sequence[int], store, name: str = "mqcb200_fragment_queue"):
+    def __init__(self, ids: Sequence[int], store, name: str = "mqcb200_fragment_queue", batch: int = 1):
         self.ids = [int(i) for i in ids]          # identical on every rank
         self.store = store
         self.key = name + "/head"
+        # ``batch`` ids are claimed per round trip to the store (a TCP exchange with rank 0): the
+        # reference's coordinator likewise hands a worker its next fragment while it still
+        # computes (mqc_mbe_mpi_fragment_distribution_scheme.F90:1296-1377).  FIFO order is kept;
+        # a claimed run of ids is worked off locally, in order, by whichever thread pops next.
+        self.batch = max(1, int(batch))
+        self._claimed = []
+        self._lock = threading.Lock()
 
     def pop(self):
         """``queue_pop``: ``(item_idx, has_item)``; ``(-1, False)`` once drained."""
-        head = self.store.add(self.key, 1) - 1    # atomic fetch-and-increment
-        if head >= len(self.ids):
-            return -1, False
-        return self.ids[head], True
+        with self._lock:
+            if not self._claimed:
+                head = self.store.add(self.key, self.batch) - self.batch    # atomic fetch-and-add
+                self._claimed = self.ids[head:head + self.batch] if head < len(self.ids) else []
+            if not self._claimed:
+                return -1, False
+            return self._claimed.pop(0), True
 
 
 class LocalWorkQueue:

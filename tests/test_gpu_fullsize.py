@@ -73,7 +73,7 @@ def test_fock_energy_and_bit_reproducibility(engine, c2):
         assert not engine.last_gamma_fused()
         assert np.max(np.abs(f_general - f1)) <= 1e-11
     finally:
-        engine.set_fuse_threshold(1 << 30)
+        engine.set_fuse_threshold(32 << 20)
     j, k = engine.build_jk(d, c, NOCC)
     assert np.max(np.abs(f1 - (h + j - 0.5 * k))) <= 1e-10
     assert abs(e1 - 0.5 * np.sum(d * (h + f1))) <= 1e-9 * max(1.0, abs(e1))
@@ -91,3 +91,57 @@ def test_device_resident_call_equals_host_call(engine, c2):
     d_f = torch.empty_like(d_h)
     engine.build_fock_device(d_h, d_d, d_c, NOCC, d_f, k_scale=0.2)
     assert np.array_equal(d_f.cpu().numpy().T, f_host)
+
+
+# ---- the other BASELINE shapes: c4 (the ~200-atom def2-SVP shape north_star states its target on)
+# and c5 (two-spin), each on a 16-function auxiliary sub-range synthesised on the device and
+# regenerated on the host for the oracle.  c4 exercises two N tiles of the half-transform
+# (n_occ = 241 -> 2 x 128), the one-valid-k-sub last chunk, and n = 1450 = 90.6 tiles.
+@pytest.mark.parametrize("q_begin", [0, 3001])
+def test_c4_shape_subrange_parity(engine, q_begin):
+    cfg = synth.CONFIGS["c4"]
+    n, n_occ, naux, qs = cfg["n"], cfg["n_occ"], cfg["naux"], 16
+    scale = synth.default_scale(n, naux)
+    _, h, d, c = synth.synth_problem(SEED + 4, n, n_occ, naux, with_tensor=False)
+    b = synth.synth_tensor(SEED + 4, n, naux, scale, q_begin=q_begin, q_count=qs)
+    engine.synth_tensor(n, naux, SEED + 4, scale, q_begin=q_begin, q_count=qs)
+    j_ref, k_ref, _ = oracle.jk_df_fast(b, d, c, n_occ)
+    f_ref = h + j_ref - 0.5 * 0.2 * k_ref                      # B3LYP: k_scale = 0.2
+    f = engine.build_fock_df(h, d, c, n_occ, k_scale=0.2)
+    assert engine.last_gamma_fused()                            # D = 2CC^T, shard above the fuse threshold
+    assert np.max(np.abs(f - f_ref)) <= 1e-10
+    assert abs(engine.last_energy() - oracle.electronic_energy(h, f_ref, d)) <= 1e-9
+    j, k = engine.build_jk(d, c, n_occ)
+    assert np.max(np.abs(j - j_ref)) <= 1e-10 and np.max(np.abs(k - k_ref)) <= 1e-10
+    # one stream and two streams give the same bits; so does the general (unfused) Coulomb pass to 1e-11
+    engine.set_overlap(False)
+    try:
+        assert np.array_equal(engine.build_fock_df(h, d, c, n_occ, k_scale=0.2), f)
+    finally:
+        engine.set_overlap(True)
+    engine.set_fuse_threshold(2 ** 62)
+    try:
+        f_general = engine.build_fock_df(h, d, c, n_occ, k_scale=0.2)
+        assert not engine.last_gamma_fused() and np.max(np.abs(f_general - f)) <= 1e-11
+    finally:
+        engine.set_fuse_threshold(32 << 20)
+
+
+def test_c5_shape_two_spin_subrange_parity(engine):
+    cfg = synth.CONFIGS["c5"]
+    n, na, nb, naux, qs = cfg["n"], cfg["n_alpha"], cfg["n_beta"], cfg["naux"], 16
+    scale = synth.default_scale(n, naux)
+    ca = synth.synth_orbitals(SEED + 5, n, na)
+    cb = synth.synth_orbitals(SEED + 6, n, nb)
+    h = synth.synth_core_hamiltonian(SEED + 5, n)
+    da, db = oracle.build_density_spin(ca, na), oracle.build_density_spin(cb, nb)
+    b = synth.synth_tensor(SEED + 5, n, naux, scale, q_begin=100, q_count=qs)
+    engine.synth_tensor(n, naux, SEED + 5, scale, q_begin=100, q_count=qs)
+    j_ref, ka_ref, _ = oracle.jk_df_fast(b, da + db, ca, na, rhf_factor=1.0)
+    _, kb_ref, _ = oracle.jk_df_fast(b, da + db, cb, nb, rhf_factor=1.0)
+    j, ka, kb = engine.build_jk_uhf(da + db, ca, na, cb, nb)
+    assert max(np.max(np.abs(j - j_ref)), np.max(np.abs(ka - ka_ref)), np.max(np.abs(kb - kb_ref))) <= 1e-10
+    fa, fb = engine.build_fock_df_uhf(h, da, db, ca, na, cb, nb)
+    assert np.max(np.abs(fa - (h + j_ref - ka_ref))) <= 1e-10 and np.max(np.abs(fb - (h + j_ref - kb_ref))) <= 1e-10
+    e = oracle.uhf_electronic_energy(h, fa, fb, da, db)
+    assert abs(e - oracle.uhf_electronic_energy(h, h + j_ref - ka_ref, h + j_ref - kb_ref, da, db)) <= 1e-9

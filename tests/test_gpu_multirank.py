@@ -68,3 +68,48 @@ def test_two_gpu_sharded_build(tmp_path, exchange):
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_two_gpus_as_threads_of_one_process():
+    """The dispatcher shape of the reference (one host thread per GPU in ONE process):
+    CUDA IPC handles cannot be opened by the process that exported them, so the exchange maps its
+    peers by raw pointer + peer access instead.  Same checks as the multi-process test."""
+    import threading
+
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    from metalquicha_b200 import B200FockEngine, synth
+    from oracle import df_fock_oracle as oracle
+
+    n, n_occ, naux, world = 150, 33, 101, 2
+    b, h, d, c = synth.synth_problem(5, n, n_occ, naux)
+    ref = oracle.build_fock_df(h, b, d, c, n_occ, k_scale=0.2)
+    uid = B200FockEngine.comm_unique_id()
+    out, errors = {}, []
+
+    def worker(rank):
+        try:
+            eng = B200FockEngine(rank)
+            eng.comm_init(world, rank, uid)
+            q0, qc = synth.shard_range(naux, world, rank)
+            eng.set_tensor_shard(np.asfortranarray(b[:, q0:q0 + qc]), n, naux, q0)
+            f1 = eng.build_fock_df(h, d, c, n_occ, k_scale=0.2)
+            f2 = eng.build_fock_df(h, d, c, n_occ, k_scale=0.2)
+            out[rank] = (f1, f2)
+            eng.comm_destroy()
+            eng.close()
+        except Exception as ex:          # surfaced by the main thread
+            errors.append((rank, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join(timeout=300) for t in threads]
+    assert not errors, errors
+    assert sorted(out) == [0, 1]
+    for rank in range(world):
+        f1, f2 = out[rank]
+        assert np.max(np.abs(f1 - ref)) <= 1e-10 and np.array_equal(f1, f2)
+    assert np.array_equal(out[0][0], out[1][0])          # bit-identical on both GPUs

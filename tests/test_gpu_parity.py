@@ -97,6 +97,50 @@ def test_coeff_leading_dimension_and_extra_columns(engine):
     assert _maxabs(engine.build_fock_df(h, density, np.ascontiguousarray(full), n_occ), ref) <= TOL
 
 
+def test_strided_views_of_h_and_density_are_copied(engine):
+    """Only the coefficient matrix carries a leading dimension through the C ABI; a column-major
+    VIEW of h or D (big[:n, :n]) must not be handed over as if it were contiguous."""
+    n, n_occ, naux = 40, 7, 30
+    b, h, density, coeff = synth.synth_problem(23, n, n_occ, naux)
+    engine.set_tensor(b)
+    ref = oracle.build_fock_df(h, b, density, coeff, n_occ)
+    big_h = np.asfortranarray(np.full((n + 5, n + 3), 7.0)); big_h[:n, :n] = h
+    big_d = np.asfortranarray(np.full((n + 2, n + 9), -3.0)); big_d[:n, :n] = density
+    hv, dv = big_h[:n, :n], big_d[:n, :n]
+    assert not hv.flags.f_contiguous and not dv.flags.f_contiguous
+    assert _maxabs(engine.build_fock_df(hv, dv, coeff, n_occ), ref) <= TOL
+    j, k = engine.build_jk(dv, coeff, n_occ)
+    j_ref, k_ref, _ = oracle.jk_df(b, density, coeff, n_occ)
+    assert _maxabs(j, j_ref) <= TOL and _maxabs(k, k_ref) <= TOL
+    # operands of another size than the resident tensor are refused, not read out of bounds
+    assert engine.tensor_shape() == (n, naux, 0, naux)
+    with pytest.raises(ValueError, match="resident tensor"):
+        engine.build_fock_df(np.zeros((n + 1, n + 1)), np.zeros((n + 1, n + 1)), np.zeros((n + 1, 2)), 2)
+    with pytest.raises(ValueError, match="resident tensor"):
+        engine.build_jk(np.zeros((n - 1, n - 1)), coeff, n_occ)
+
+
+def test_non_finite_density_never_takes_the_fused_route(engine):
+    """A NaN in D whose other elements match 2CC^T must not set the fuse flag (a max() drops
+    NaN): the reference propagates it into J and F."""
+    n, n_occ, naux = 96, 20, 40
+    b, h, density, coeff = synth.synth_problem(29, n, n_occ, naux)
+    engine.set_tensor(b)
+    engine.set_fuse_threshold(0)
+    try:
+        engine.build_fock_df(h, density, coeff, n_occ)
+        assert engine.last_gamma_fused()
+        bad = density.copy(order="F"); bad[3, 5] = np.nan
+        f = engine.build_fock_df(h, bad, coeff, n_occ)
+        assert not engine.last_gamma_fused() and np.isnan(f).any()
+        asym = density.copy(order="F"); asym[7, 2] += 1e-6        # upper != lower: not an orbital product
+        f2 = engine.build_fock_df(h, asym, coeff, n_occ)
+        assert not engine.last_gamma_fused()
+        assert _maxabs(f2, oracle.build_fock_df(h, b, asym, coeff, n_occ)) <= TOL
+    finally:
+        engine.set_fuse_threshold(32 << 20)
+
+
 def test_pseudo_orbital_guess_build(engine):
     """atomic_guess_fock: a non-idempotent guess density through its pseudo-orbitals."""
     n, naux = 60, 80
@@ -260,10 +304,13 @@ def test_coulomb_vector_from_half_transform(engine, n, n_occ, naux):
         j_ref, ka_ref, kb_ref = oracle.jk_df_uhf(b, da + db, coeff, n_occ, cb, nb_)
         assert _maxabs(j, j_ref) <= TOL and _maxabs(ka, ka_ref) <= TOL and _maxabs(kb, kb_ref) <= TOL
     finally:
-        engine.set_fuse_threshold(1 << 30)
-    f_general = engine.build_fock_df(h, density, coeff, n_occ)
-    assert not engine.last_gamma_fused()
-    assert _maxabs(f_general, ref) <= TOL and _maxabs(f_general, f_fused) <= 1e-11
+        engine.set_fuse_threshold(2 ** 62)
+    try:
+        f_general = engine.build_fock_df(h, density, coeff, n_occ)
+        assert not engine.last_gamma_fused()
+        assert _maxabs(f_general, ref) <= TOL and _maxabs(f_general, f_fused) <= 1e-11
+    finally:
+        engine.set_fuse_threshold(32 << 20)
 
 
 def test_device_generator_matches_host_generator(engine):

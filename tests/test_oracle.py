@@ -150,3 +150,25 @@ def test_asymmetric_density_only_its_symmetric_part_matters():
     j1, _, _ = oracle.jk_df(b, d, coeff, o)
     j2, _, _ = oracle.jk_df(b, 0.5 * (d + d.T), coeff, o)
     assert np.max(np.abs(j1 - j2)) <= 1e-12
+
+
+def test_c_blas_restatement_agrees_with_the_numpy_restatement():
+    """oracle/df_fock_blas.c (bench.py's CPU baseline: the reference's loops on a vendor dgemm)
+    vs the loop-for-loop NumPy oracle, closed shell and two-spin, at 1 and at all BLAS threads."""
+    from oracle import df_fock_blas as blas_port
+    n, n_occ, naux = 37, 9, 23
+    b, h, density, coeff = synth.synth_problem(61, n, n_occ, naux)
+    ref = oracle.build_fock_df(h, b, density, coeff, n_occ, k_scale=0.2, j_scale=0.7)
+    for threads in (1, blas_port.host_threads()):
+        with blas_port.blas_threads(threads):
+            got = blas_port.build_fock_df(h, b, density, coeff, n_occ, k_scale=0.2, j_scale=0.7)
+        assert np.max(np.abs(got - ref)) <= 1e-12
+    padded = np.zeros((n + 4, n), order="F"); padded[:n, :n_occ] = coeff       # extra rows/columns are ignored
+    j, k, c = blas_port.jk_df(b, density, np.asfortranarray(padded[:n, :]), n_occ)
+    j_ref, k_ref, c_ref = oracle.jk_df(b, density, coeff, n_occ)
+    assert np.max(np.abs(j - j_ref)) <= 1e-12 and np.max(np.abs(k - k_ref)) <= 1e-12 and np.max(np.abs(c - c_ref)) <= 1e-12
+    cb = synth.synth_orbitals(62, n, n_occ - 2)
+    da, db = oracle.build_density_spin(coeff, n_occ), oracle.build_density_spin(cb, n_occ - 2)
+    fa, fb = blas_port.build_fock_df_uhf(h, b, da, db, coeff, n_occ, cb, n_occ - 2, k_scale=0.5)
+    fa_ref, fb_ref = oracle.build_fock_df_uhf(h, b, da, db, coeff, n_occ, cb, n_occ - 2, k_scale=0.5)
+    assert np.max(np.abs(fa - fa_ref)) <= 1e-12 and np.max(np.abs(fb - fb_ref)) <= 1e-12

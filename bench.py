@@ -38,6 +38,18 @@ import sys
 import threading
 import time
 
+# torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, and OpenBLAS sizes its thread
+# pool from the environment when it is LOADED: the CPU arm must see every host thread, so the
+# variables are put right before NumPy/SciPy come in (the thread count actually used is then set
+# explicitly per measurement and stated in the line).
+if "reference" in sys.argv[1:]:
+    try:
+        _n_host = len(os.sched_getaffinity(0))
+    except AttributeError:
+        _n_host = os.cpu_count() or 1
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_n_host)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -7,15 +7,22 @@ is shipped or measured as the product.  Only ``tests/``,
 of ``bench.py`` may import it.  The product package ``metalquicha_b200`` never
 does (``tests/test_no_oracle_in_product.py`` enforces that).
 
-PARITY UNPINNED.  The reference (JorgeG94/metalquicha) is Fortran; this image
-has no Fortran compiler, no libcint/libfint, no pic-blas, and no basis-set
-data, so the reference cannot be compiled or run here, and none of the
-reference's own tests asserts a J, K, F or c_P element.
-The only golden numbers that pass through this path are end-to-end SCF energies
-that need real three-centre integrals.  The restatement below therefore follows
-the reference *loop for loop* with file:line citations, is cross-checked
-against an independent plain-C restatement (``oracle/df_fock_ref.c``), and has
-to satisfy the reference's own algebraic identities (tests/test_oracle.py).
+PARITY PIN.  The reference (JorgeG94/metalquicha) is Fortran; this image has no Fortran
+compiler, no libcint/libfint, no pic-blas and no basis-set bundle, so the reference cannot
+be compiled or run here, and none of its tests asserts a J, K, F or c_P element (SURVEY.md
+section 8c).  What it DOES hold are total energies -- and two of them come with their basis
+written out inline: H2 and H2O in STO-3G (validation/check_rhf.f90:54-153, 1e-9 Eh against
+PySCF).  With the integrals restated (oracle/gto_integrals.py) the SCF restatement
+(oracle/scf_oracle.py) reproduces both to 3e-11 Eh through ``build_fock_eri`` AND through
+``build_fock_df`` on a tensor that fits the four-index integrals exactly
+(tests/test_reference_golden_energies.py) -- which pins the factor 2 of K, the 1/2 of F, the
+energy expression and the flattening of the fitted path to reference-held numbers.  The CUDA
+engine runs the same SCF to the same energies (tests/test_gpu_golden_scf.py).  The energies
+that need the named basis sets (cc-pVDZ/JKFIT, def2, 6-31G*) stay unasserted
+(tests/golden/reference_energies.json).  Beyond that pin the restatement follows the
+reference *loop for loop* with file:line citations, is cross-checked against two independent
+C restatements (``oracle/df_fock_ref.c``, ``oracle/df_fock_blas.c``), and satisfies the
+reference's own algebraic identities (tests/test_oracle.py).
 
 All arrays are float64.  Matrices use the reference's layout: ``b`` is
 ``(n*n, naux)`` with slab ``b[:, p]`` holding the symmetric ``n x n`` matrix of

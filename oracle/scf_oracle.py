@@ -1,0 +1,171 @@
+"""CPU restatement of the reference's closed-shell SCF loop -- TEST INFRASTRUCTURE ONLY.
+
+Follows ``run_libcint_rhf`` (backends/libcint/mqc_libcint_rhf.f90:321-680) statement for
+statement around a pluggable Fock build, so that the SAME loop can be driven by
+
+  * the oracle's exact-integral ``build_fock`` restatement (pins the loop + the J/K conventions
+    to the reference-held STO-3G energies of validation/check_rhf.f90),
+  * the oracle's ``build_fock_df`` on an exactly-fitting tensor,
+  * the CUDA engine through the C ABI (tests/test_gpu_golden_scf.py), and
+  * the device-resident SCF step of the engine, whose trajectory it checks iteration by iteration.
+
+Pieces and their sources:
+  build_orthogonalizer   src/scf/mqc_scf_common.f90:42-82      X = U s^-1/2 over eigenvalues > 1e-7
+  guess_fock (GWH)       mqc_libcint_rhf.f90:1354-1380, GWH_K = 1.75 (mqc_scf_common.f90:33)
+  diagonalize            mqc_libcint_rhf.f90:1464-1489         F' = X^T F X, dsyev, C = X C'
+  build_density          src/scf/mqc_scf_common.f90:84-96      D = 2 C_occ C_occ^T
+  commutator             mqc_libcint_rhf.f90:1326-1352         e = X^T (F D S - S D F) X
+  DIIS                   src/methods/mqc_diis.f90:94-275       ring of 8, scaled B matrix, pivoted elimination
+  loop / convergence     mqc_libcint_rhf.f90:566-636           iter > 1 and |dE| < e_tol and rms(dD) < d_tol
+  final rebuild          mqc_libcint_rhf.f90:646-649
+"""
+from __future__ import annotations
+
+import numpy as np
+
+LINEAR_DEPENDENCE_TOL = 1.0e-7      # mqc_scf_common.f90:27
+GWH_K = 1.75                        # mqc_scf_common.f90:33
+PIVOT_FLOOR = 1.0e-14               # mqc_diis.f90:35
+
+
+def build_orthogonalizer(overlap):
+    values, vectors = np.linalg.eigh(overlap, UPLO="U")
+    keep = values > LINEAR_DEPENDENCE_TOL
+    if not np.any(keep):
+        raise ValueError("SCF: overlap matrix is singular")
+    return vectors[:, keep] / np.sqrt(values[keep])[None, :]
+
+
+def guess_fock_gwh(overlap, h):
+    n = h.shape[0]
+    hd = np.diag(h)
+    f = 0.5 * GWH_K * overlap * (hd[:, None] + hd[None, :])
+    f[np.arange(n), np.arange(n)] = hd
+    return f
+
+
+def diagonalize(fock, x):
+    f_ortho = x.T @ (fock @ x)
+    eigenvalues, c_prime = np.linalg.eigh(f_ortho, UPLO="U")
+    return x @ c_prime, eigenvalues
+
+
+def build_density_closed_shell(coeff, n_occ):
+    c = coeff[:, :n_occ]
+    return 2.0 * (c @ c.T)
+
+
+def commutator(fock, density, overlap, x):
+    fds = (fock @ density) @ overlap - (overlap @ density) @ fock
+    return x.T @ (fds @ x)
+
+
+def solve_diis(b_matrix):
+    """Pivoted Gaussian elimination of mqc_diis.f90:228-273; returns (coefficients, ok)."""
+    n = b_matrix.shape[0]
+    aug = np.zeros((n, n + 1))
+    aug[:, :n] = b_matrix
+    aug[n - 1, n] = -1.0
+    for i in range(n):
+        pivot_row = i + int(np.argmax(np.abs(aug[i:, i])))
+        if pivot_row != i:
+            aug[[i, pivot_row], :] = aug[[pivot_row, i], :]
+        pivot = aug[i, i]
+        if abs(pivot) < PIVOT_FLOOR:
+            return None, False
+        for j in range(i + 1, n):
+            factor = aug[j, i] / pivot
+            aug[j, i:] = aug[j, i:] - factor * aug[i, i:]
+    coef = np.zeros(n)
+    for i in range(n - 1, -1, -1):
+        coef[i] = (aug[i, n] - np.dot(aug[i, i + 1:n], coef[i + 1:n])) / aug[i, i]
+    return coef, True
+
+
+class Diis:
+    """``diis_state_t``: a ring of Fock/error vectors, oldest first when extrapolating."""
+
+    def __init__(self, max_vectors: int):
+        self.max_vectors = max(1, max_vectors)
+        self.focks, self.errors = [], []
+
+    def push(self, fock, error):
+        self.focks.append(np.array(fock, copy=True))
+        self.errors.append(np.array(error, copy=True))
+        if len(self.focks) > self.max_vectors:
+            self.focks.pop(0)
+            self.errors.pop(0)
+
+    def count(self):
+        return len(self.focks)
+
+    def coefficients(self):
+        n = len(self.focks)
+        if n < 2:
+            return None, False
+        b = -np.ones((n + 1, n + 1))
+        b[n, n] = 0.0
+        for i in range(n):
+            for j in range(n):
+                b[i, j] = float(np.sum(self.errors[i] * self.errors[j]))
+        scale = float(np.max(np.abs(b[:n, :n])))
+        if scale > 0.0:
+            b[:n, :n] /= scale
+        coef, ok = solve_diis(b)
+        return (coef[:n] if ok else None), ok
+
+    def extrapolate(self, fock):
+        coef, ok = self.coefficients()
+        if not ok:
+            return fock, False
+        out = np.zeros_like(fock)
+        for c, f in zip(coef, self.focks):
+            out = out + c * f
+        return out, True
+
+
+def run_rhf(h, s, n_electrons, fock_builder, e_nuc=0.0, max_iter=100, energy_tol=1e-10, density_tol=1e-8,
+            diis_vectors=8, guess="gwh", record=None):
+    """``run_libcint_rhf`` around ``fock_builder(h, density, coeff, n_occ) -> (fock, e_elec)``.
+    Returns a dict with energy, electronic, iterations, converged, orbitals, density."""
+    n_occ = n_electrons // 2
+    x = build_orthogonalizer(s)
+    fock = guess_fock_gwh(s, h) if guess == "gwh" else np.array(h, copy=True)
+    coeff, eigenvalues = diagonalize(fock, x)
+    density = build_density_closed_shell(coeff, n_occ)
+    diis = Diis(diis_vectors)
+    e_old, converged, iterations = 0.0, False, 0
+    for it in range(1, max_iter + 1):
+        density_old = density
+        fock, e_elec = fock_builder(h, density, coeff, n_occ)
+        err = commutator(fock, density, s, x)
+        if diis_vectors > 0:
+            diis.push(fock, err)
+            fock, _ = diis.extrapolate(fock)
+        coeff, eigenvalues = diagonalize(fock, x)
+        density = build_density_closed_shell(coeff, n_occ)
+        de = abs(e_elec - e_old)
+        drms = float(np.sqrt(np.sum((density - density_old) ** 2) / density.size))
+        if record is not None:
+            record.append({"iter": it, "e_elec": e_elec, "de": de, "drms": drms, "diis": diis.count()})
+        e_old, iterations = e_elec, it
+        if it > 1 and de < energy_tol and drms < density_tol:
+            converged = True
+            break
+    _, electronic = fock_builder(h, density, coeff, n_occ)           # final rebuild, :646-649
+    return {"energy": electronic + e_nuc, "electronic": electronic, "nuclear_repulsion": e_nuc,
+            "iterations": iterations, "converged": converged, "orbitals": coeff,
+            "orbital_energies": eigenvalues, "density": density, "n_occupied": n_occ}
+
+
+def exact_fit_tensor(eri, tol=1e-13):
+    """A fitted tensor b(n*n, naux) that reproduces the four-index integrals exactly:
+    (ab|cd) = sum_P b(ab,P) b(cd,P), from the eigendecomposition of the (n^2 x n^2) positive
+    semi-definite ERI matrix (modes below ``tol`` of the largest dropped).  With it the DF build
+    IS the exact build, so a DF-SCF on it must land on the reference's exact-integral energy."""
+    n = eri.shape[0]
+    m = eri.reshape(n * n, n * n, order="F")          # row index mu + n*nu, the reference's flattening
+    m = 0.5 * (m + m.T)
+    w, v = np.linalg.eigh(m)
+    keep = w > tol * w[-1]
+    return np.asfortranarray(v[:, keep] * np.sqrt(w[keep])[None, :])

@@ -131,18 +131,29 @@ int mqcb200_build_fock_uhf(void *handle, int slot, const double *h,
                            const double *coeff_a, int lda, int n_alpha,
                            const double *coeff_b, int ldb, int n_beta,
                            double k_scale, double *fock_a, double *fock_b);
-/* G = J[density] + ka*K[Ca] + kb*K[Cb] with K[C] = sum_P (B_P C)(B_P C)^T (no factor 2).
- * The building block of the reference's other two fitted operators on the same tensor
- * (SURVEY 8f row 3), which the host mirror assembles from it:
- *   response_operator_df (backends/libcint/mqc_libcint_cphf.F90:499-566):
- *       (B X)(B C)^T + h.c. = 1/2 [K[X+C] - K[X-C]]   ->  ka = -kf/4, kb = +kf/4
- *   fitted_potential_general (mqc_libcint_cphf.F90:568-616): D = V+ w+ V+^T - V- |w-| V-^T
- *       K = K[V+ sqrt(w+)] - K[V- sqrt|w-|]           ->  ka = -kf/2, kb = +kf/2
- * A channel with n == 0 is skipped. */
+/* G = J[density] + ka*K[Ca] + kb*K[Cb] with K[C] = sum_P (B_P C)(B_P C)^T (no factor 2):
+ * a Coulomb term plus two weighted symmetric exchange terms in one call (round 1 assembled the
+ * operators below from it; they now have their own direct kernels).  A channel with n == 0 is
+ * skipped. */
 int mqcb200_build_g_two_factor(void *handle, int slot, const double *density,
                                const double *coeff_a, int lda, int n_a,
                                const double *coeff_b, int ldb, int n_b,
                                double ka, double kb, double *g);
+
+/* mqcb200_response_operator == response_operator_df(b, x, c_occ, dtilde, g, k_scale)
+ * (backends/libcint/mqc_libcint_cphf.F90:499-566) with b resident:
+ *   g = J[dtilde] - (k_scale/2) * sum_P [(B_P X)(B_P C)^T + (B_P C)(B_P X)^T]
+ * computed in that direct rank-2 form -- ONE half-transform of the stacked [X | C] and a
+ * SYR2K-form accumulation -- so a small trial vector X keeps full relative accuracy (no
+ * difference of squares).  x and c_occ are n x n_occ with leading dimensions ldx, ldc.
+ * mqcb200_fitted_potential_general == fitted_potential_general(b, dens, g, k_scale)
+ * (mqc_libcint_cphf.F90:568-616):  g = J[D] - (k_scale/2) * sum_P B_P D B_P  for the symmetric,
+ * otherwise arbitrary D the reference requires; same kernels with X = D, C = 1 (n^3 naux). */
+int mqcb200_response_operator(void *handle, int slot, const double *x, int ldx,
+                              const double *c_occ, int ldc, int n_occ,
+                              const double *dtilde, double k_scale, double *g);
+int mqcb200_fitted_potential_general(void *handle, int slot, const double *dens,
+                                     double k_scale, double *g);
 
 /* E = 1/2 sum D (H + F)  (electronic_energy, mqc_libcint_rhf.f90:1691-1697),
  * evaluated on the device from the operands of the last mqcb200_build_fock. */

@@ -49,6 +49,9 @@ SIGNATURES = {
                                        c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     "mqcb200_build_g_two_factor": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                                            c_void_p, c_int, c_int, c_double, c_double, c_void_p]),
+    "mqcb200_response_operator": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
+                                          c_double, c_void_p]),
+    "mqcb200_fitted_potential_general": (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p]),
     "mqcb200_last_energy": (c_int, [c_void_p, POINTER(c_double)]),
     "mqcb200_build_fock_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                           c_double, c_double, c_void_p, c_int]),

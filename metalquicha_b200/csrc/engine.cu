@@ -156,6 +156,7 @@ struct Engine {
   DevBuf d_w, d_ctf, d_gamma_partial, d_gamma, d_jpart, d_x, d_kpart;
   DevBuf d_gpart_a, d_gpart_b;   // Coulomb-vector partials written by the half-transform
   DevBuf d_cep;                  // coefficients in accumulator order for that epilogue
+  DevBuf d_stack;                // [X | C] of a rank-2 exchange, each half on a 16-column boundary
   DevBuf d_jk;       // [J | K | K_beta] contiguous so one all-reduce covers them
   DevBuf d_scalar, d_stage, d_escratch;
   DevBuf d_in;                   // [H | D | C_a | C_b] of a host-operand build, contiguous
@@ -621,6 +622,7 @@ struct BuildArgs {
   const double *coeff_a = nullptr, *coeff_b = nullptr;
   int lda = 0, ldb = 0, n_a = 0, n_b = 0;
   bool two_spin = false;          // K per spin with factor 1 instead of one K with factor 2
+  bool rank2 = false;             // K = sum_P (B_P Ca)(B_P Cb)^T + (B_P Cb)(B_P Ca)^T  (n_a == n_b columns), factor 1
   bool want_j = true, want_k = true;
   // outputs (host pointers unless device_operands)
   double *j = nullptr, *k_a = nullptr, *k_b = nullptr, *fock_a = nullptr, *fock_b = nullptr;
@@ -632,9 +634,9 @@ struct BuildArgs {
 };
 
 static void run_k(Engine *e, const TensorSlot &sl, const double *d_coeff, int ldc, int n_occ, double *d_kpart_out,
-                  double *d_gamma_part, KPlan &plan, cudaEvent_t ev_last_half = nullptr) {
+                  double *d_gamma_part, KPlan &plan, cudaEvent_t ev_last_half = nullptr, int rank2_occ = 0) {
   const int n = sl.n;
-  plan = plan_k(n, n_occ, sl.q_count, e->workspace_limit, e->sm_count);
+  plan = plan_k(n, n_occ, sl.q_count, e->workspace_limit, e->sm_count, rank2_occ);
   e->d_ctf.ensure((size_t)num_tiles(n) * plan.nib * 128 * sizeof(double));
   e->d_x.ensure(plan.x_elems_per_q * (size_t)plan.q_chunk * sizeof(double));
   double *d_cep = nullptr;
@@ -667,6 +669,8 @@ static void build(Engine *e, const BuildArgs &a) {
   if (a.n_a < 0 || a.n_b < 0) throw Failure("mqcb200: negative occupied count");
   if (a.want_k && a.n_a > 0 && (!a.coeff_a || a.lda < sl.n)) throw Failure("mqcb200: bad coefficient matrix / leading dimension");
   if (a.want_k && a.two_spin && a.n_b > 0 && (!a.coeff_b || a.ldb < sl.n)) throw Failure("mqcb200: bad beta coefficient matrix / leading dimension");
+  if (a.rank2 && a.want_k && (a.n_a != a.n_b || a.n_a <= 0 || !a.coeff_b || a.ldb < sl.n || a.two_spin))
+    throw Failure("mqcb200: the rank-2 exchange needs two factors with the same, positive number of columns");
   e->bind();
   e->launches = 0;
   const int n = sl.n;
@@ -705,7 +709,7 @@ static void build(Engine *e, const BuildArgs &a) {
       // all operands go into one device block; small sets are first gathered in pinned
       // memory so that the whole upload is ONE DMA (a fragment's 72x72 matrices would
       // otherwise pay the driver's per-copy overhead three times)
-      const bool up_ca = a.want_k && a.n_a > 0, up_cb = a.want_k && a.two_spin && a.n_b > 0;
+      const bool up_ca = a.want_k && a.n_a > 0, up_cb = a.want_k && (a.two_spin || a.rank2) && a.n_b > 0;
       const size_t o_h = 0, o_d = o_h + (a.h ? nn : 0), o_ca = o_d + (a.density ? nn : 0);
       const size_t o_cb = o_ca + (up_ca ? (size_t)n * a.n_a : 0), in_elems = o_cb + (up_cb ? (size_t)n * a.n_b : 0);
       e->d_in.ensure(std::max<size_t>(16, in_elems * sizeof(double)));
@@ -755,13 +759,13 @@ static void build(Engine *e, const BuildArgs &a) {
   double *d_j = use_p2p ? static_cast<double *>(e->p2p.in) : e->d_jk.d(), *d_ka = d_j + nn, *d_kb = d_j + 2 * nn;
 
   const bool have = sl.q_count > 0;
-  const double kfac = a.two_spin ? 1.0 : 2.0;
+  const double kfac = (a.two_spin || a.rank2) ? 1.0 : 2.0;
   JPlan jp = plan_j(n, sl.q_count);
   int n_jslices = jp.n_slices;          // partial-buffer shapes handed to finalize below
   int n_ksplits = 0, n_ksplits_diag = -1, ktile = 64;
   bool ka_finalized = false;
   const int max_occ = std::max(do_ka ? a.n_a : 0, do_kb ? a.n_b : 0);
-  const bool frag = have && (do_j || do_ka || do_kb) && fragment_path_enabled() &&
+  const bool frag = have && (do_j || do_ka || do_kb) && fragment_path_enabled() && !a.rank2 &&
                     fragment_path_applies(n, std::max(max_occ, 1));
 
   if (frag) {
@@ -809,7 +813,7 @@ static void build(Engine *e, const BuildArgs &a) {
   // (D = f C C^T: every SCF iteration).  Decided on the device by a consistency check fused
   // into the density packing, so an arbitrary density (guess, response, user-supplied)
   // silently takes the general pass over B instead.
-  const bool fuse = do_j && do_ka && have && fuse_gamma_enabled() &&
+  const bool fuse = do_j && do_ka && have && fuse_gamma_enabled() && !a.rank2 &&
                     (size_t)sl.L * (size_t)sl.q_count * sizeof(double) >= e->fuse_threshold &&
                     (!a.two_spin || do_kb || a.n_b == 0);
   int *d_flag = nullptr;
@@ -823,11 +827,20 @@ static void build(Engine *e, const BuildArgs &a) {
   if (overlap) CUDA_CHECK(cudaEventRecord(e->ev_fork, e->stream));
   // ---- K (alpha / closed shell); K (beta) reuses the scratch after alpha has been finalized
   if (do_ka && have) {
-    KPlan probe = plan_k(n, a.n_a, sl.q_count, e->workspace_limit, e->sm_count);
+    KPlan probe = plan_k(n, a.n_a, sl.q_count, e->workspace_limit, e->sm_count, a.rank2 ? a.n_a : 0);
     e->d_kpart.ensure(probe.kpart_elems * sizeof(double));
     if (fuse) e->d_gpart_a.ensure((size_t)probe.gamma_stride * sl.q_count * sizeof(double));
-    run_k(e, sl, d_ca, lda, a.n_a, e->d_kpart.d(), fuse ? e->d_gpart_a.d() : nullptr, kp,
-          (overlap && fuse && !do_kb) ? e->ev_k1_done : nullptr);
+    if (a.rank2) {
+      // one half-transform of the stacked [X | C], then the SYR2K-form accumulation
+      const int o16 = (a.n_a + 15) / 16 * 16;
+      e->d_stack.ensure((size_t)n * 2 * o16 * sizeof(double));
+      launch_stack_factors(d_ca, lda, d_cb, ldb, n, a.n_a, e->d_stack.d(), e->stream);
+      e->launches += 1;
+      run_k(e, sl, e->d_stack.d(), n, 2 * o16, e->d_kpart.d(), nullptr, kp, nullptr, a.n_a);
+    } else {
+      run_k(e, sl, d_ca, lda, a.n_a, e->d_kpart.d(), fuse ? e->d_gpart_a.d() : nullptr, kp,
+            (overlap && fuse && !do_kb) ? e->ev_k1_done : nullptr);
+    }
   }
   if (do_kb) {
     if (have) {
@@ -1147,7 +1160,7 @@ int mqcb200_destroy(void *handle) {
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto &sl : e->slots) sl.packed.release();
   DevBuf *bufs[] = {&e->d_w, &e->d_ctf, &e->d_gamma_partial,
-                    &e->d_gamma, &e->d_jpart, &e->d_x, &e->d_kpart, &e->d_gpart_a, &e->d_gpart_b, &e->d_cep, &e->d_jk, &e->d_in, &e->d_out,
+                    &e->d_gamma, &e->d_jpart, &e->d_x, &e->d_kpart, &e->d_gpart_a, &e->d_gpart_b, &e->d_cep, &e->d_stack, &e->d_jk, &e->d_in, &e->d_out,
                     &e->d_scalar, &e->d_stage, &e->d_escratch};
   for (DevBuf *b : bufs) b->release();
   e->h_in.release();
@@ -1392,6 +1405,41 @@ int mqcb200_build_g_two_factor(void *handle, int slot, const double *density, co
   a.coeff_a = coeff_a; a.lda = lda; a.n_a = n_a; a.coeff_b = coeff_b; a.ldb = ldb; a.n_b = n_b;
   a.combine = true; a.ka_coef = ka; a.kb_coef = kb; a.fock_a = g;
   a.want_k = (ka != 0.0 && n_a > 0) || (kb != 0.0 && n_b > 0);
+  build(e, a);
+  API_END
+}
+
+int mqcb200_response_operator(void *handle, int slot, const double *x, int ldx, const double *c_occ, int ldc,
+                              int n_occ, const double *dtilde, double k_scale, double *g) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!dtilde || !g) throw Failure("mqcb200: null matrix argument to response_operator");
+  BuildArgs a;
+  a.slot = slot; a.density = dtilde; a.rank2 = true;
+  a.coeff_a = x; a.lda = ldx; a.n_a = n_occ; a.coeff_b = c_occ; a.ldb = ldc; a.n_b = n_occ;
+  a.combine = true; a.ka_coef = -0.5 * k_scale; a.fock_a = g;        // g = coul - 0.5*kf*exch  (cphf.F90:565)
+  a.want_k = k_scale != 0.0 && n_occ > 0;
+  if (!a.want_k) a.rank2 = false;
+  build(e, a);
+  API_END
+}
+
+int mqcb200_fitted_potential_general(void *handle, int slot, const double *dens, double k_scale, double *g) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!dens || !g) throw Failure("mqcb200: null matrix argument to fitted_potential_general");
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS || !e->slots[slot].set) throw Failure("mqcb200: no fitted tensor has been set on this slot (call mqcb200_set_tensor first)");
+  const int n = e->slots[slot].n;
+  // sum_P B_P D B_P = 1/2 [(B_P D)(B_P 1)^T + (B_P 1)(B_P D)^T] for the symmetric D the reference
+  // requires (cphf.F90:570): the rank-2 kernels with X = D, C = 1 -- no eigendecomposition, no cancellation
+  std::vector<double> eye((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) eye[(size_t)i * n + i] = 1.0;
+  BuildArgs a;
+  a.slot = slot; a.density = dens; a.rank2 = true;
+  a.coeff_a = dens; a.lda = n; a.n_a = n; a.coeff_b = eye.data(); a.ldb = n; a.n_b = n;
+  a.combine = true; a.ka_coef = -0.25 * k_scale; a.fock_a = g;       // g = coul - 0.5*kf*exch  (cphf.F90:615)
+  a.want_k = k_scale != 0.0;
+  if (!a.want_k) a.rank2 = false;
   build(e, a);
   API_END
 }

@@ -18,9 +18,12 @@
 // stored tile (max, min) and is read transposed out of shared memory when
 // tr_s < kc (the packed tensor holds each off-diagonal tile once).
 //
-// Accumulation: SYRK over 128x128 lower-triangular tiles of K with the (Q, i)
-// contraction index split across CTAs; partial tiles are written (or added to, on
-// later Q-chunks) in a fixed order -- no floating-point atomics.
+// Accumulation: SYRK over 64x64 lower-triangular tiles of K (three CTAs per SM) with the
+// (Q, i) contraction index split across CTAs; partial tiles are written (or added to, on
+// later Q-chunks) in a fixed order -- no floating-point atomics.  The same kernel runs the
+// rank-2 (SYR2K) form  sum_P (B_P X)(B_P C)^T + (B_P C)(B_P X)^T  of the response operator
+// (reference mqc_libcint_cphf.F90:554-563): the half-transform is fed the stacked [X | C], and a
+// pipeline stage pairs the X-chunk of one panel with the C-chunk of the other, then the reverse.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -324,7 +327,8 @@ __device__ __forceinline__ void syrk_diag_warp(const double *stage_base, uint64_
 template <int TILE>
 __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads, SyrkCfg<TILE>::kMinBlocks)
 k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count, int n_ktiles, int n_splits,
-                    int n_splits_diag, int n_panels, double *__restrict__ kpart, int accumulate, int ks_last) {
+                    int n_splits_diag, int n_panels, double *__restrict__ kpart, int accumulate, int ks_last,
+                    int pair_off, int npairs) {
   using Cfg = SyrkCfg<TILE>;
   constexpr int PB = Cfg::kPanelBlocks;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -355,11 +359,17 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
       tile = mp * (mp + 1) / 2 + np;
     }
   }
-  const bool diag = mp == np;
-  const int my_splits = diag ? n_splits_diag : n_splits;
+  // rank-2 mode (pair_off > 0): chunk k of the X half is paired with chunk k + pair_off of the C half,
+  // once as (rows of panel mp: X, rows of panel np: C) and once reversed; every tile -- the
+  // diagonal ones too -- then takes the two-panel path, and a step list per auxiliary function is
+  // 2*npairs long instead of nkc.
+  const bool rank2 = pair_off > 0;
+  const bool diag = mp == np && !rank2;
+  const int my_splits = (mp == np) ? n_splits_diag : n_splits;
   const int qa = (int)((long long)split * q_count / my_splits);
   const int qb = (int)((long long)(split + 1) * q_count / my_splits);
-  const int n_steps = (qb - qa) * nkc;
+  const int per_q = rank2 ? 2 * npairs : nkc;
+  const int n_steps = (qb - qa) * per_q;
   const int valid_a = nmb - PB * mp < PB ? nmb - PB * mp : PB;   // 8-row blocks present in each panel
   const int valid_b = nmb - PB * np < PB ? nmb - PB * np : PB;
 
@@ -387,10 +397,13 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
         const uint32_t ph = (step / Cfg::kStages) & 1;
         mbar_wait(&empty_bar[st], ph ^ 1);
         double *a_s = stage_base + (size_t)st * Cfg::kStageElems;
-        const size_t blk = ((size_t)(qa + step / nkc) * nkc + (step % nkc)) * nmb;
+        const int r = step % per_q;
+        const size_t qrow = (size_t)(qa + step / per_q) * nkc;
+        const int ka = rank2 ? ((r & 1) ? (r >> 1) + pair_off : (r >> 1)) : r;
+        const int kb = rank2 ? ((r & 1) ? (r >> 1) : (r >> 1) + pair_off) : r;
         mbar_arrive_expect_tx(&full_bar[st], bytes_a + bytes_b);
-        tma_load_1d(a_s, x + (blk + PB * mp) * 128, bytes_a, &full_bar[st]);
-        if (!diag) tma_load_1d(a_s + Cfg::kPanelElems, x + (blk + PB * np) * 128, bytes_b, &full_bar[st]);
+        tma_load_1d(a_s, x + ((qrow + ka) * nmb + PB * mp) * 128, bytes_a, &full_bar[st]);
+        if (!diag) tma_load_1d(a_s + Cfg::kPanelElems, x + ((qrow + kb) * nmb + PB * np) * 128, bytes_b, &full_bar[st]);
       }
     }
     return;
@@ -431,12 +444,13 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
     load_frags(fa[0], fb[0], 0, 0);
   }
   int kc_idx = 0;                                   // position of this step inside its auxiliary function
+  const int last_from = rank2 ? per_q - 2 : per_q - 1;    // rank-2: both orders of the last pair
   for (int step = 0; step < n_steps; ++step) {
     const int st = step % Cfg::kStages;
     // the last 16-wide chunk of the padded occupied range may hold fewer than four valid
     // 4-wide k-subs (n_occ = 241: one): the rest is zero padding, skip its DMMAs
-    const int ks_lim = (kc_idx == nkc - 1) ? ks_last : 4;
-    kc_idx = (kc_idx + 1 == nkc) ? 0 : kc_idx + 1;
+    const int ks_lim = (kc_idx >= last_from) ? ks_last : 4;
+    kc_idx = (kc_idx + 1 == per_q) ? 0 : kc_idx + 1;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       if (ks < 3) {
@@ -484,9 +498,14 @@ static int ktile_override() {
   return v;
 }
 
-KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm_count) {
+KPlan plan_k(int n, int n_occ_in, int q_count, size_t workspace_limit_bytes, int sm_count, int rank2_occ) {
   KPlan p;
   const int nt = num_tiles(n);
+  // rank-2 form: the half-transform sees the stacked [X | C], each half padded to whole 16-wide chunks
+  const int o16_r2 = rank2_occ > 0 ? (rank2_occ + 15) / 16 * 16 : 0;
+  const int n_occ = rank2_occ > 0 ? 2 * o16_r2 : n_occ_in;
+  p.pair_off = o16_r2 / 16;
+  p.npairs = o16_r2 / 16;
   const int op16 = ((n_occ > 0 ? n_occ : 1) + 15) / 16 * 16;
   p.n_ntiles = (op16 + 127) / 128;
   int bn = (op16 + p.n_ntiles - 1) / p.n_ntiles;
@@ -498,7 +517,9 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
   {
     const int valid_last = (n_occ > 0 ? n_occ : 1) - 16 * (p.nkc - 1);   // may be <= 0 when N tiles pad a whole chunk
     p.ks_last = valid_last >= 16 ? 4 : (valid_last <= 0 ? 0 : (valid_last + 3) / 4);
+    if (rank2_occ > 0) p.ks_last = (rank2_occ - 16 * (p.npairs - 1) + 3) / 4;   // of the last pair of chunks
   }
+  const int steps_per_q = rank2_occ > 0 ? 2 * p.npairs : p.nkc;
   // K tile edge: 64 trims the diagonal/padding waste of the SYRK; 128 halves the operand
   // traffic per flop and wins once n is large enough that the waste is small.
   p.ktile = ktile_override() ? ktile_override() : 64;
@@ -521,7 +542,7 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
   const size_t tile_bytes = (size_t)p.ktile * p.ktile * sizeof(double);
   const int n_diag = p.n_panels, n_off = p.n_ktiles - p.n_panels;
   auto diag_splits = [&](int s) {           // 64-wide diagonal tiles cost 9/16 of a full tile
-    if (p.ktile != 64) return s;
+    if (p.ktile != 64 || rank2_occ > 0) return s;
     int sd = (9 * s + 8) / 16;
     return sd < 1 ? 1 : sd;
   };
@@ -530,8 +551,8 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
     const int sd = diag_splits(s);
     const long long units = (long long)s * n_off + (long long)sd * n_diag;
     const long long waves = (units + slots - 1) / slots;
-    const double steps_off = (double)((p.q_chunk + s - 1) / s) * p.nkc;
-    const double steps_diag = (double)((p.q_chunk + sd - 1) / sd) * p.nkc * (p.ktile == 64 ? 9.0 / 16.0 : 1.0);
+    const double steps_off = (double)((p.q_chunk + s - 1) / s) * steps_per_q;
+    const double steps_diag = (double)((p.q_chunk + sd - 1) / sd) * steps_per_q * ((p.ktile == 64 && rank2_occ == 0) ? 9.0 / 16.0 : 1.0);
     const double steps = n_off > 0 ? (steps_off > steps_diag ? steps_off : steps_diag) : steps_diag;
     // + the fixed-order sum over the splits in finalize_jk_kernel (~3/4 of a step per split)
     double cost = (double)waves * (steps + 12.0) + 0.75 * (double)s;
@@ -589,11 +610,11 @@ void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, doub
   if (plan.ktile == 128)
     k_accumulate_kernel<128><<<units, SyrkCfg<128>::kThreads, SyrkCfg<128>::kSmemBytes, s>>>(
         d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, plan.n_splits_diag, plan.n_panels, d_kpart, accumulate,
-        plan.ks_last);
+        plan.ks_last, plan.pair_off, plan.npairs);
   else
     k_accumulate_kernel<64><<<units, SyrkCfg<64>::kThreads, SyrkCfg<64>::kSmemBytes, s>>>(
         d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, plan.n_splits_diag, plan.n_panels, d_kpart, accumulate,
-        plan.ks_last);
+        plan.ks_last, plan.pair_off, plan.npairs);
 }
 
 template <int NB>

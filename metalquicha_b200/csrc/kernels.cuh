@@ -114,10 +114,17 @@ struct KPlan {
   int q_chunk;     // auxiliary functions per half-transform launch
   int sm_count;    // persistent grid size of the half-transform
   int gamma_stride;  // Coulomb-vector partials per auxiliary function written by the half-transform
+  int pair_off;      // rank-2 form: chunk k of the X half pairs with chunk k + pair_off of the C half (0 = SYRK)
+  int npairs;        // rank-2 form: 16-wide chunks per half
   size_t x_elems_per_q;     // doubles of X per auxiliary function
   size_t kpart_elems;       // n_splits * n_ktiles * ktile*ktile
 };
-KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm_count);
+// rank2_occ > 0: plan the rank-2 (SYR2K) form for two n x rank2_occ factors; the half-transform then
+// takes the stacked operand of launch_stack_factors (2*ceil16(rank2_occ) columns), n_occ is ignored.
+KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm_count, int rank2_occ = 0);
+// S (n x 2*o16, ld n) = [X | 0 | C | 0]: each n x n_occ factor starts on a 16-column boundary.
+void launch_stack_factors(const double *d_x, int ldx, const double *d_c, int ldc, int n, int n_occ, double *d_s,
+                          cudaStream_t s);
 // d_gamma_part (nullable, needs d_cep): [q_count][plan.gamma_stride] partials of sum_{mu,i} X_Q[mu,i] C[mu,i].
 void launch_k_half_transform(const double *d_packed, long long L, int n, int q_count,
                              const double *d_ctf, const double *d_cep, const KPlan &plan, double *d_x,

@@ -339,6 +339,28 @@ void launch_density_prep(const double *d_density, int n, double *d_w, const doub
                                                                     tol_rel, d_scratch, d_flag);
 }
 
+__global__ void __launch_bounds__(256) stack_factors_kernel(const double *__restrict__ x, int ldx,
+                                                            const double *__restrict__ c, int ldc, int n, int n_occ,
+                                                            int o16, double *__restrict__ s) {
+  const size_t total = (size_t)n * 2 * o16;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int mu = (int)(e % n), col = (int)(e / n);
+    const int i = col < o16 ? col : col - o16;
+    double v = 0.0;
+    if (i < n_occ) v = col < o16 ? x[(size_t)mu + (size_t)ldx * i] : c[(size_t)mu + (size_t)ldc * i];
+    s[e] = v;
+  }
+}
+
+void launch_stack_factors(const double *d_x, int ldx, const double *d_c, int ldc, int n, int n_occ, double *d_s,
+                          cudaStream_t s) {
+  const int o16 = (n_occ + 15) / 16 * 16;
+  const size_t total = (size_t)n * 2 * o16;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  stack_factors_kernel<<<blocks, 256, 0, s>>>(d_x, ldx, d_c, ldc, n, n_occ, o16, d_s);
+}
+
 void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib, double *d_ctf, double *d_cep,
                        cudaStream_t s) {
   const int nt = num_tiles(n);

@@ -276,31 +276,34 @@ class B200FockEngine:
     def response_operator_df(self, x, c_occ, dtilde, k_scale=None, slot: int = SLOT_FULL_RANGE) -> np.ndarray:
         """``response_operator_df(b, x, c_occ, dtilde, g, k_scale)`` with ``b`` resident
         (backends/libcint/mqc_libcint_cphf.F90:499-566): ``g = J[dtilde] - kf/2 * sum_P
-        [(B_P X)(B_P C)^T + h.c.]``.  The rank-2 exchange is the difference of two
-        symmetric builds, ``1/2 (K[X+C] - K[X-C])``, so it runs on the same kernels."""
-        x = np.asarray(x, dtype=np.float64)
-        c_occ = np.asarray(c_occ, dtype=np.float64)
-        if x.shape != c_occ.shape:
+        [(B_P X)(B_P C)^T + h.c.]``, evaluated in that direct rank-2 form on the device (one
+        half-transform of the stacked ``[X | C]``, SYR2K-form accumulation)."""
+        n = self.n[slot]
+        x, ldx = self._coeff(x, n, np.asarray(x).shape[1])
+        n_occ = x.shape[1]
+        c_occ, ldc = self._coeff(c_occ, n, n_occ)
+        if c_occ.shape[1] != n_occ:
             raise ValueError("x and c_occ must both be (n_ao, n_occ)")
-        kf = 1.0 if k_scale is None else k_scale
-        n_occ = c_occ.shape[1]
-        plus = np.asfortranarray(x + c_occ)
-        minus = np.asfortranarray(x - c_occ)
-        return self._g_two_factor(dtilde, plus, n_occ, minus, n_occ, -0.25 * kf, 0.25 * kf, slot)
+        dtilde = _f64_colmajor(dtilde, "dtilde")
+        if dtilde.shape != (n, n):
+            raise ValueError(f"the resident tensor has n = {n}, dtilde is {dtilde.shape}")
+        g = np.empty((n, n), dtype=np.float64, order="F")
+        _check(self._lib.mqcb200_response_operator(self._h, slot, _ptr(x), ldx, _ptr(c_occ), ldc, int(n_occ),
+                                                   _ptr(dtilde), c_double(1.0 if k_scale is None else k_scale), _ptr(g)))
+        return g
 
     def fitted_potential_general(self, dens, k_scale=None, slot: int = SLOT_FULL_RANGE) -> np.ndarray:
         """``fitted_potential_general(b, dens, g, k_scale)`` (mqc_libcint_cphf.F90:568-616):
-        ``g = J[D] - kf/2 * sum_P B_P D B_P`` for a symmetric, possibly indefinite ``D``.
-        ``D`` is split by its eigendecomposition into a positive and a negative part
-        (host dsyev, as ``density_pseudo_orbitals`` does for a guess density), each of
-        which has orbitals; the exchange is then ``K[V+ sqrt(w+)] - K[V- sqrt|w-|]``."""
-        dens = np.asarray(dens, dtype=np.float64)
-        kf = 1.0 if k_scale is None else k_scale
-        values, vectors = np.linalg.eigh(0.5 * (dens + dens.T), UPLO="U")
-        pos, neg = values > OCCUPATION_FLOOR, values < -OCCUPATION_FLOOR
-        cp = np.asfortranarray(vectors[:, pos] * np.sqrt(values[pos])[None, :])
-        cn = np.asfortranarray(vectors[:, neg] * np.sqrt(-values[neg])[None, :])
-        return self._g_two_factor(dens, cp, cp.shape[1], cn, cn.shape[1], -0.5 * kf, 0.5 * kf, slot)
+        ``g = J[D] - kf/2 * sum_P B_P D B_P`` for a symmetric, otherwise arbitrary ``D``, on the
+        device through the rank-2 kernels (``X = D``, ``C = 1``): no eigendecomposition."""
+        n = self.n[slot]
+        dens = _f64_colmajor(dens, "dens")
+        if dens.shape != (n, n):
+            raise ValueError(f"the resident tensor has n = {n}, dens is {dens.shape}")
+        g = np.empty((n, n), dtype=np.float64, order="F")
+        _check(self._lib.mqcb200_fitted_potential_general(self._h, slot, _ptr(dens),
+                                                          c_double(1.0 if k_scale is None else k_scale), _ptr(g)))
+        return g
 
     def last_energy(self) -> float:
         """``electronic_energy(h, fock, density)`` of the last ``build_fock_df`` (rhf.f90:1691-1697)."""

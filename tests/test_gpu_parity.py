@@ -243,7 +243,7 @@ def test_device_whitening_matches_reference_gemm(engine, n, naux, n_null):
 
 def test_response_operator_and_general_density_potential(engine):
     """The reference's other two fitted operators on the same resident tensor
-    (mqc_libcint_cphf.F90:499-566 and :568-616), SURVEY 8f row 3."""
+    (mqc_libcint_cphf.F90:499-566 and :568-616), SURVEY 8f row 3 -- direct rank-2 kernels."""
     n, n_occ, naux = 58, 9, 70
     b, _, _, coeff_all = synth.synth_problem(41, n, n, naux)           # all n orbitals
     c_occ = np.asfortranarray(coeff_all[:, :n_occ])
@@ -252,20 +252,45 @@ def test_response_operator_and_general_density_potential(engine):
     x = np.asfortranarray(c_vir @ rng.standard_normal((n - n_occ, n_occ)))   # X = C_vir U
     dtilde = np.asfortranarray(x @ c_occ.T + c_occ @ x.T)                    # symmetric, indefinite
     engine.set_tensor(b)
-    for ks in (None, 0.25):
+    for ks in (None, 0.25, 0.0):
         g = engine.response_operator_df(x, c_occ, dtilde, k_scale=ks)
         g_ref = oracle.response_operator_df(b, x, c_occ, dtilde, k_scale=ks)
         assert _maxabs(g, g_ref) <= TOL * max(1.0, float(np.max(np.abs(g_ref))))
+        assert np.array_equal(g, g.T)
     # the rank-2 form and the general form agree on the same response density
     g_gen = engine.fitted_potential_general(dtilde)
-    assert _maxabs(g_gen, oracle.fitted_potential_general(b, dtilde)) <= 1e-9
-    assert _maxabs(g_gen, engine.response_operator_df(x, c_occ, dtilde)) <= 1e-9
+    assert _maxabs(g_gen, oracle.fitted_potential_general(b, dtilde)) <= TOL
+    assert _maxabs(g_gen, engine.response_operator_df(x, c_occ, dtilde)) <= TOL
     # an unstructured symmetric density that integrates to zero (MP2-relaxed-like)
     a = rng.standard_normal((n, n)); d = a + a.T; d -= np.trace(d) / n * np.eye(n)
     d = np.asfortranarray(d)
     g = engine.fitted_potential_general(d, k_scale=0.5)
     g_ref = oracle.fitted_potential_general(b, d, k_scale=0.5)
-    assert _maxabs(g, g_ref) <= 1e-9 * max(1.0, float(np.max(np.abs(g_ref))))
+    assert _maxabs(g, g_ref) <= TOL * max(1.0, float(np.max(np.abs(g_ref))))
+
+
+@pytest.mark.parametrize("n,n_occ,naux", [(58, 9, 70), (130, 33, 40), (97, 16, 30), (200, 81, 12), (72, 15, 64), (150, 129, 9)])
+def test_response_operator_keeps_relative_accuracy_for_a_small_trial_vector(engine, n, n_occ, naux):
+    """Near CPHF convergence |X| ~ 1e-8 |C|.  The direct rank-2 form keeps ~16 digits of g there;
+    a difference of squares K[X+C] - K[X-C] keeps eight.  Tolerance is
+    RELATIVE to |g|.  Shapes: ragged n, n_occ on and off the 16-wide chunk boundary, two N tiles
+    of the stacked half-transform (2*ceil16(n_occ) > 128), fragment-sized n (general path forced)."""
+    b, _, _, coeff_all = synth.synth_problem(500 + n, n, n, naux)
+    c_occ = np.asfortranarray(coeff_all[:, :n_occ])
+    rng = np.random.default_rng(n)
+    x = np.asfortranarray(1.0e-8 * (coeff_all[:, n_occ:] @ rng.standard_normal((n - n_occ, n_occ))))
+    dtilde = np.asfortranarray(x @ c_occ.T + c_occ @ x.T)
+    engine.set_tensor(b)
+    g = engine.response_operator_df(x, c_occ, dtilde, k_scale=1.0)
+    g_ref = oracle.response_operator_df(b, x, c_occ, dtilde, k_scale=1.0)
+    scale = float(np.max(np.abs(g_ref)))
+    assert 1e-10 < scale < 1e-5
+    assert _maxabs(g, g_ref) <= 1e-10 * scale
+    assert np.array_equal(g, engine.response_operator_df(x, c_occ, dtilde, k_scale=1.0))      # bit-reproducible
+    # coefficient matrices with a leading dimension
+    pad = np.zeros((n + 3, 2 * n_occ), order="F")
+    pad[:n, :n_occ], pad[:n, n_occ:] = x, c_occ
+    assert np.array_equal(g, engine.response_operator_df(pad[:n, :n_occ], pad[:n, n_occ:], dtilde, k_scale=1.0))
 
 
 def test_singular_metric_is_refused():

@@ -155,6 +155,33 @@ int mqcb200_response_operator(void *handle, int slot, const double *x, int ldx,
 int mqcb200_fitted_potential_general(void *handle, int slot, const double *dens,
                                      double k_scale, double *g);
 
+/* ---- device-resident SCF of a fragment ----------------------
+ * mqcb200_scf_fragment == run_libcint_rhf(mol, nelec, max_iter, energy_tol, density_tol, ...,
+ * aux=aux, diis_vectors, guess) (mqc_libcint_rhf.f90:321-680) minus the integral generation: the
+ * caller passes the core Hamiltonian and the overlap (n x n, host) and the fitted tensor is the
+ * one resident on `slot`.  Everything between two Fock builds -- commutator X^T(FDS-SDF)X
+ * (:1326-1352), DIIS (src/methods/mqc_diis.f90), F' = X^T F X + eigendecomposition + C = X C'
+ * (:1464-1489), D = 2 C_occ C_occ^T (src/scf/mqc_scf_common.f90:84-96), the convergence test
+ * (:626-636) -- runs on the GPU; per iteration only a few scalars cross PCIe (cf.
+ * backends/cuest/backend/mqc_cuest_scf.f90:444-553).  Fragment-sized problems only (n <= 80,
+ * n_occ <= 64); anything larger is refused, not run on the host.
+ *   guess: 0 = core Hamiltonian, 1 = generalised Wolfsberg-Helmholz (the reference's default);
+ *   diis_vectors: 0..8 (reference default 8), 0 = plain iteration;
+ *   outputs: electronic energy of the FINAL rebuild (:646-649), iterations, converged flag,
+ *   n_mo (orbitals surviving the 1e-7 overlap threshold, mqc_scf_common.f90:27), and -- each
+ *   may be NULL -- coeff (n x n_mo), orbital_energies (n_mo), density (n x n),
+ *   e_history (max_iter: electronic energy of every iteration's build).
+ * Errors carry the reference's messages ("SCF: overlap matrix is singular", ...). */
+int mqcb200_scf_fragment(void *handle, int slot, const double *hcore, const double *overlap,
+                         int n_electrons, int guess, int max_iter,
+                         double energy_tol, double density_tol, int diis_vectors, double k_scale,
+                         double *e_electronic, int *iterations, int *converged, int *n_mo,
+                         double *coeff, double *orbital_energies, double *density,
+                         double *e_history);
+/* Iterations queued on the GPU between two looks at the convergence flag (default 1; queued
+ * iterations after convergence are no-ops on the device). */
+int mqcb200_set_scf_check_every(void *handle, int iterations);
+
 /* E = 1/2 sum D (H + F)  (electronic_energy, mqc_libcint_rhf.f90:1691-1697),
  * evaluated on the device from the operands of the last mqcb200_build_fock. */
 int mqcb200_last_energy(void *handle, double *e_elec);

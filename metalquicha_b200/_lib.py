@@ -52,6 +52,10 @@ SIGNATURES = {
     "mqcb200_response_operator": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
                                           c_double, c_void_p]),
     "mqcb200_fitted_potential_general": (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p]),
+    "mqcb200_scf_fragment": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_int,
+                                     c_double, _dp, POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mqcb200_set_scf_check_every": (c_int, [c_void_p, c_int]),
     "mqcb200_last_energy": (c_int, [c_void_p, POINTER(c_double)]),
     "mqcb200_build_fock_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                           c_double, c_double, c_void_p, c_int]),

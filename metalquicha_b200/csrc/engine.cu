@@ -157,6 +157,9 @@ struct Engine {
   DevBuf d_gpart_a, d_gpart_b;   // Coulomb-vector partials written by the half-transform
   DevBuf d_cep;                  // coefficients in accumulator order for that epilogue
   DevBuf d_stack;                // [X | C] of a rank-2 exchange, each half on a 16-column boundary
+  DevBuf d_scf;                  // device-resident SCF of a fragment: H, S, X, F, D, C, eps, work, DIIS history, scalars
+  PinnedBuf h_scf;               // its per-iteration scalars on the host side
+  int scf_check_every = 1;       // iterations queued between two looks at the convergence flag
   DevBuf d_jk;       // [J | K | K_beta] contiguous so one all-reduce covers them
   DevBuf d_scalar, d_stage, d_escratch;
   DevBuf d_in;                   // [H | D | C_a | C_b] of a host-operand build, contiguous
@@ -1059,6 +1062,139 @@ static void build(Engine *e, const BuildArgs &a) {
   }
 }
 
+// ------------------------------- device-resident SCF of a fragment -------------------------
+// run_libcint_rhf (mqc_libcint_rhf.f90:321-680) minus the integrals: H, S and the resident fitted
+// tensor in, the converged closed-shell SCF out, with every matrix staying on the GPU between
+// iterations.  Per iteration the host queues six kernels (pack D, pack C, one-pass J/K,
+// finalize+assemble F, energy, SCF step) and reads back a handful of scalars.
+struct ScfArgs {
+  int slot = 0;
+  const double *h = nullptr, *s = nullptr;
+  int n_electrons = 0, guess = 1, max_iter = 100, diis_vectors = 8;
+  double energy_tol = 1e-10, density_tol = 1e-8, k_scale = 1.0;
+  double *e_electronic = nullptr;
+  int *iterations = nullptr, *converged = nullptr, *n_mo = nullptr;
+  double *coeff = nullptr, *eps = nullptr, *density = nullptr, *e_history = nullptr;
+};
+
+static void fragment_fock_device(Engine *e, const TensorSlot &sl, const double *d_h, const double *d_density,
+                                 const double *d_coeff, int n_occ, double k_scale, double *d_j, double *d_k,
+                                 double *d_fock, double *d_energy) {
+  const int n = sl.n;
+  const bool wk = k_scale != 0.0 && n_occ > 0;
+  FragPlan fp = plan_fragment(n, std::max(n_occ, 1), sl.q_count, e->sm_count);
+  e->d_w.ensure((size_t)sl.L * sizeof(double));
+  e->d_jpart.ensure(fp.jpart_elems * sizeof(double));
+  launch_pack_density(d_density, n, e->d_w.d(), nullptr, e->stream);
+  if (wk) {
+    e->d_ctf.ensure((size_t)fp.nt * fp.nib * 128 * sizeof(double));
+    e->d_kpart.ensure(fp.kpart_elems * sizeof(double));
+    launch_pack_coeff(d_coeff, n, n, n_occ, fp.nib, e->d_ctf.d(), nullptr, e->stream);
+  }
+  launch_fragment_jk(sl.packed.d(), sl.q_count, e->d_w.d(), e->d_ctf.d(), fp, true, wk, e->d_jpart.d(), e->d_kpart.d(),
+                     e->stream);
+  launch_finalize_jk(e->d_jpart.d(), fp.grid, wk ? e->d_kpart.d() : nullptr, fp.grid, 64, n, 2.0, d_j, wk ? d_k : nullptr,
+                     e->stream, d_h, 1.0, 0.5 * k_scale, d_fock, -1);
+  launch_energy(d_density, d_h, d_fock, n, e->d_escratch.d(), d_energy, e->stream);
+  e->launches += wk ? 5 : 4;
+}
+
+static void scf_fragment(Engine *e, const ScfArgs &a) {
+  if (a.slot < 0 || a.slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  TensorSlot &sl = e->slots[a.slot];
+  if (!sl.set) throw Failure("mqcb200: no fitted tensor has been set on this slot (call mqcb200_set_tensor first)");
+  if (!a.h || !a.s || !a.e_electronic || !a.iterations || !a.converged)
+    throw Failure("mqcb200: null argument to scf_fragment");
+  if (e->comm && e->n_ranks > 1) throw Failure("mqcb200: the device-resident SCF runs whole fragments on one GPU, not a sharded tensor");
+  if (sl.q_count != sl.naux_total) throw Failure("mqcb200: the device-resident SCF needs the whole tensor on this GPU");
+  const int n = sl.n;
+  if (a.n_electrons < 0 || (a.n_electrons & 1)) throw Failure("mqcb200: closed-shell SCF needs an even, non-negative electron count");
+  const int n_occ = a.n_electrons / 2;
+  if (!scf_path_applies(n) || !fragment_path_applies(n, std::max(n_occ, 1)))
+    throw Failure("mqcb200: the device-resident SCF step covers fragment-sized problems (n <= 80, n_occ <= 64)");
+  if (a.diis_vectors < 0 || a.diis_vectors > 8) throw Failure("mqcb200: diis_vectors must lie in 0..8");
+  if (a.max_iter < 1) throw Failure("mqcb200: max_iter must be positive");
+  e->bind();
+  e->launches = 0;
+  const size_t nn = (size_t)n * n;
+  const int dmax = a.diis_vectors;
+  // layout of the device block (doubles)
+  size_t off = 0;
+  auto take = [&](size_t count) { const size_t o = off; off += (count + 1) & ~(size_t)1; return o; };
+  const size_t o_h = take(nn), o_s = take(nn), o_x = take(nn), o_f = take(nn), o_d = take(nn), o_c = take(nn);
+  const size_t o_j = take(nn), o_k = take(nn), o_eps = take(n), o_work = take(4 * nn);
+  const size_t o_df = take((size_t)std::max(dmax, 1) * nn), o_de = take((size_t)std::max(dmax, 1) * nn), o_db = take(64);
+  const size_t o_scal = take(8), o_state = take(4 /* ints, in 4 doubles */), o_nmo = take(2);
+  e->d_scf.ensure(off * sizeof(double));
+  e->h_scf.ensure(16 * sizeof(double));
+  double *base = e->d_scf.d();
+  int *d_state = reinterpret_cast<int *>(base + o_state), *d_nmo = reinterpret_cast<int *>(base + o_nmo);
+  // H and S up (one staged DMA when they fit the small-operand buffer), everything else cleared
+  const size_t hs_span = (o_s - o_h) + nn;               // S starts on an even offset: one pad double for odd n*n
+  e->h_in.ensure((hs_span + 1) * sizeof(double));
+  std::memset(e->h_in.ptr, 0, hs_span * sizeof(double));
+  std::memcpy(e->h_in.d(), a.h, nn * sizeof(double));
+  std::memcpy(e->h_in.d() + (o_s - o_h), a.s, nn * sizeof(double));
+  CUDA_CHECK(cudaMemcpyAsync(base + o_h, e->h_in.ptr, hs_span * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_CHECK(cudaMemsetAsync(base + o_x, 0, (off - o_x) * sizeof(double), e->stream));
+  launch_scf_orthogonalizer(base + o_s, n, base + o_x, d_nmo, e->stream);
+  e->launches += 1;
+  int n_mo = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&n_mo, d_nmo, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  if (n_mo <= 0) throw Failure("SCF: overlap matrix is singular");                           // mqc_scf_common.f90:69
+  if (n_occ > n_mo)
+    throw Failure("RHF: more occupied orbitals than the basis supports after near-null modes were dropped (" +
+                  std::to_string(n_occ) + " occupied, " + std::to_string(n_mo) + " of " + std::to_string(n) +
+                  " orbitals kept)");                                                          // rhf.f90:510-513
+
+  ScfStepLaunch st{};
+  st.n = n; st.n_mo = n_mo; st.n_occ = n_occ; st.diis_max = dmax; st.guess = a.guess;
+  st.h = base + o_h; st.s = base + o_s; st.x = base + o_x; st.fock = base + o_f; st.density = base + o_d;
+  st.coeff = base + o_c; st.eps = base + o_eps; st.work = base + o_work; st.diis_f = base + o_df; st.diis_e = base + o_de;
+  st.diis_b = base + o_db; st.state = d_state; st.scalars = base + o_scal;
+  st.energy_tol = a.energy_tol; st.density_tol = a.density_tol;
+  st.mode = 0;
+  launch_scf_step(st, e->stream);                      // guess Fock -> C, D
+  e->launches += 1;
+  st.mode = 1;
+
+  double *hs = e->h_scf.d();                            // [0..7] scalars, [8..9] state as 4 ints
+  int iterations = 0, converged = 0;
+  const int every = std::max(1, e->scf_check_every);
+  while (iterations < a.max_iter && !converged) {
+    const int batch = std::min(every, a.max_iter - iterations);
+    for (int b = 0; b < batch; ++b) {
+      fragment_fock_device(e, sl, st.h, st.density, st.coeff, n_occ, a.k_scale, base + o_j, base + o_k, st.fock, st.scalars);
+      launch_scf_step(st, e->stream);
+      e->launches += 1;
+      if (a.e_history && batch > 1) {
+        // queued iterations: their energies are fetched one by one, in stream order
+        CUDA_CHECK(cudaMemcpyAsync(a.e_history + iterations + b, st.scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(hs, st.scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(hs + 8, d_state, 4 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    const int *hstate = reinterpret_cast<const int *>(hs + 8);
+    if (a.e_history && batch == 1) a.e_history[iterations] = hs[1];
+    iterations = hstate[2];
+    converged = hstate[3];
+  }
+  // the energy that goes out belongs to the density that satisfied the test: one more full build (rhf.f90:646-649)
+  fragment_fock_device(e, sl, st.h, st.density, st.coeff, n_occ, a.k_scale, base + o_j, base + o_k, st.fock, st.scalars);
+  CUDA_CHECK(cudaMemcpyAsync(hs, st.scalars, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (a.coeff) CUDA_CHECK(cudaMemcpyAsync(a.coeff, st.coeff, (size_t)n * n_mo * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (a.eps) CUDA_CHECK(cudaMemcpyAsync(a.eps, st.eps, (size_t)n_mo * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (a.density) CUDA_CHECK(cudaMemcpyAsync(a.density, st.density, nn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  *a.e_electronic = hs[0];
+  *a.iterations = iterations;
+  *a.converged = converged;
+  if (a.n_mo) *a.n_mo = n_mo;
+}
+
 // ------------------------------- fragment FIFO -------------------------------------------
 struct Fifo {
   uint32_t magic = 0x4D51F1F0u;
@@ -1160,11 +1296,12 @@ int mqcb200_destroy(void *handle) {
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto &sl : e->slots) sl.packed.release();
   DevBuf *bufs[] = {&e->d_w, &e->d_ctf, &e->d_gamma_partial,
-                    &e->d_gamma, &e->d_jpart, &e->d_x, &e->d_kpart, &e->d_gpart_a, &e->d_gpart_b, &e->d_cep, &e->d_stack, &e->d_jk, &e->d_in, &e->d_out,
+                    &e->d_gamma, &e->d_jpart, &e->d_x, &e->d_kpart, &e->d_gpart_a, &e->d_gpart_b, &e->d_cep, &e->d_stack, &e->d_scf, &e->d_jk, &e->d_in, &e->d_out,
                     &e->d_scalar, &e->d_stage, &e->d_escratch};
   for (DevBuf *b : bufs) b->release();
   e->h_in.release();
   e->h_out.release();
+  e->h_scf.release();
   for (int i = 0; i < 2; ++i) {
     e->h_stage[i].release();
     e->d_stage_lower[i].release();
@@ -1461,6 +1598,28 @@ int mqcb200_build_fock_uhf_device(void *handle, int slot, const double *d_h, con
   a.want_k = k_scale != 0.0;
   build(e, a);
   API_END
+}
+
+int mqcb200_scf_fragment(void *handle, int slot, const double *hcore, const double *overlap, int n_electrons,
+                         int guess, int max_iter, double energy_tol, double density_tol, int diis_vectors,
+                         double k_scale, double *e_electronic, int *iterations, int *converged, int *n_mo,
+                         double *coeff, double *orbital_energies, double *density, double *e_history) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  ScfArgs a;
+  a.slot = slot; a.h = hcore; a.s = overlap; a.n_electrons = n_electrons; a.guess = guess; a.max_iter = max_iter;
+  a.energy_tol = energy_tol; a.density_tol = density_tol; a.diis_vectors = diis_vectors; a.k_scale = k_scale;
+  a.e_electronic = e_electronic; a.iterations = iterations; a.converged = converged; a.n_mo = n_mo;
+  a.coeff = coeff; a.eps = orbital_energies; a.density = density; a.e_history = e_history;
+  scf_fragment(e, a);
+  API_END
+}
+
+int mqcb200_set_scf_check_every(void *handle, int iterations) {
+  GET_ENGINE(handle)
+  if (iterations < 1) { g_last_error = "mqcb200: check_every must be positive"; return MQCB200_FAIL; }
+  e->scf_check_every = iterations;
+  return MQCB200_OK;
 }
 
 int mqcb200_last_energy(void *handle, double *e_elec) {

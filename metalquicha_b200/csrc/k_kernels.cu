@@ -626,6 +626,7 @@ static void configure_half() {
 void configure_kernels() {
   configure_fragment_kernels();
   configure_whiten_kernels();
+  configure_scf_kernels();
   configure_half<1>(); configure_half<2>(); configure_half<3>(); configure_half<4>();
   configure_half<5>(); configure_half<6>(); configure_half<7>(); configure_half<8>();
   cudaFuncSetAttribute(k_accumulate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg<128>::kSmemBytes);

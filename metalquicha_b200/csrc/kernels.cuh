@@ -98,6 +98,21 @@ void launch_fragment_jk(const double *d_packed, int q_count, const double *d_w, 
                         const FragPlan &p, bool want_j, bool want_k, double *d_jpart, double *d_kpart,
                         cudaStream_t s);
 
+// ---- device-resident SCF step for fragment-sized problems (scf_kernels.cu) ---------------
+struct ScfStepLaunch {
+  int n, n_mo, n_occ, diis_max, mode /*0 guess, 1 iteration*/, guess /*0 core, 1 GWH*/;
+  const double *h, *s, *x;
+  double *fock, *density, *coeff, *eps, *work, *diis_f, *diis_e, *diis_b;
+  int *state;        // [0] n_stored [1] newest [2] iterations [3] converged
+  double *scalars;   // [0] e_elec (in) [1] e_old [2] |dE| [3] rms(dD) [4] extrapolated
+  double energy_tol, density_tol;
+};
+bool scf_path_applies(int n);                       // n <= 80
+void configure_scf_kernels();
+// x (n x n_mo) = U s^-1/2 over the eigenvalues of S above 1e-7; *d_n_mo = surviving orbitals.
+void launch_scf_orthogonalizer(const double *d_s, int n, double *d_x, int *d_n_mo, cudaStream_t s);
+void launch_scf_step(const ScfStepLaunch &a, cudaStream_t s);
+
 // ---- K: half-transform + symmetric accumulation on the FP64 tensor pipe -----
 struct KPlan {
   int nb;          // n8-blocks per warp in the half-transform (BN = 16*nb)

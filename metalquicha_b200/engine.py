@@ -305,6 +305,36 @@ class B200FockEngine:
                                                           c_double(1.0 if k_scale is None else k_scale), _ptr(g)))
         return g
 
+    def run_scf_fragment(self, h, s, n_electrons: int, max_iter: int = 100, energy_tol: float = 1e-10,
+                         density_tol: float = 1e-8, diis_vectors: int = 8, guess: str = "gwh", k_scale=None,
+                         e_nuc: float = 0.0, slot: int = SLOT_FULL_RANGE, check_every: int = 1) -> dict:
+        """``run_libcint_rhf`` (mqc_libcint_rhf.f90:321-680) on the resident tensor with the SCF
+        step on the GPU (fragment-sized problems, n <= 80).  Returns the fields of the reference's
+        ``rhf_result_t`` (:117-141): energy, electronic, nuclear_repulsion, iterations, converged,
+        n_occupied, orbitals, orbital_energies, density -- plus ``e_history``."""
+        h = np.asfortranarray(_f64_colmajor(h, "h"))
+        s = np.asfortranarray(_f64_colmajor(s, "s"))
+        n = h.shape[0]
+        if h.shape != (n, n) or s.shape != (n, n):
+            raise ValueError("h and s must both be n x n")
+        self._check_operand(n, slot)
+        _check(self._lib.mqcb200_set_scf_check_every(self._h, int(check_every)))
+        e_el, it, conv, n_mo = c_double(0.0), c_int(0), c_int(0), c_int(0)
+        coeff = np.zeros((n, n), order="F")
+        eps = np.zeros(n)
+        density = np.empty((n, n), order="F")
+        hist = np.zeros(max_iter)
+        _check(self._lib.mqcb200_scf_fragment(
+            self._h, slot, _ptr(h), _ptr(s), int(n_electrons), {"core": 0, "gwh": 1}[guess], int(max_iter),
+            c_double(energy_tol), c_double(density_tol), int(diis_vectors),
+            c_double(1.0 if k_scale is None else k_scale), byref(e_el), byref(it), byref(conv), byref(n_mo),
+            _ptr(coeff), _ptr(eps), _ptr(density), _ptr(hist)))
+        m = n_mo.value
+        return {"energy": e_el.value + e_nuc, "electronic": e_el.value, "nuclear_repulsion": e_nuc,
+                "iterations": it.value, "converged": bool(conv.value), "n_occupied": n_electrons // 2,
+                "orbitals": np.asfortranarray(coeff.reshape(-1, order="F")[:n * m].reshape((n, m), order="F")),
+                "orbital_energies": eps[:m].copy(), "density": density, "e_history": hist[:it.value].copy()}
+
     def last_energy(self) -> float:
         """``electronic_energy(h, fock, density)`` of the last ``build_fock_df`` (rhf.f90:1691-1697)."""
         e = c_double(0.0)

@@ -1124,7 +1124,7 @@ static void scf_fragment(Engine *e, const ScfArgs &a) {
   const size_t o_h = take(nn), o_s = take(nn), o_x = take(nn), o_f = take(nn), o_d = take(nn), o_c = take(nn);
   const size_t o_j = take(nn), o_k = take(nn), o_eps = take(n), o_work = take(4 * nn);
   const size_t o_df = take((size_t)std::max(dmax, 1) * nn), o_de = take((size_t)std::max(dmax, 1) * nn), o_db = take(64);
-  const size_t o_scal = take(8), o_state = take(4 /* ints, in 4 doubles */), o_nmo = take(2);
+  const size_t o_scal = take(24), o_state = take(4 /* ints, in 4 doubles */), o_nmo = take(2);
   e->d_scf.ensure(off * sizeof(double));
   e->h_scf.ensure(16 * sizeof(double));
   double *base = e->d_scf.d();
@@ -1178,6 +1178,12 @@ static void scf_fragment(Engine *e, const ScfArgs &a) {
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     const int *hstate = reinterpret_cast<const int *>(hs + 8);
     if (a.e_history && batch == 1) a.e_history[iterations] = hs[1];
+    if (getenv("MQCB200_SCF_TRACE")) {
+      double tr[24];
+      CUDA_CHECK(cudaMemcpy(tr, st.scalars, sizeof(tr), cudaMemcpyDeviceToHost));
+      std::fprintf(stderr, "scf step: sweeps %.0f  clocks: commutator+diis %.0f  F' gemms %.0f  jacobi %.0f  back+density %.0f\n",
+                   tr[5], tr[8], tr[9], tr[10], tr[11]);
+    }
     iterations = hstate[2];
     converged = hstate[3];
   }

@@ -18,6 +18,11 @@
 // n/2 disjoint rotations per round); eigenvalues are sorted ascending afterwards, so the occupied
 // space -- the only thing the density depends on -- is the one dsyev gives.  All reductions are in
 // fixed order: a fragment's SCF is bit-reproducible.
+//
+// Measured (B200, n = 72): a Jacobi round costs ~2700 clocks, two thirds of it the shared-memory
+// traffic of rotating A and V (every round reads and writes both matrices once: 250 KB at 128 B/clk
+// of ONE SM), so an iteration's step is ~0.4 ms once the warm start has cut the sweeps to 2-4;
+// the whole iteration (build + step) is ~0.84 ms against ~1.0 ms for the host-driven loop.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -30,27 +35,76 @@ constexpr double SCF_LINDEP_TOL = 1.0e-7;  // LINEAR_DEPENDENCE_TOL, mqc_scf_com
 constexpr double SCF_GWH_K = 1.75;         // mqc_scf_common.f90:33
 constexpr double SCF_PIVOT_FLOOR = 1.0e-14;   // mqc_diis.f90:35
 
-// C(M x N, ldc) = alpha * op(A) * op(B); op(A) is M x K.  Column-major; ta/tb = transpose flags.
-// Block-cooperative, 2x2 register tiles; operands may have been written by this block (plain loads).
+// C(M x N, ldc) = alpha * op(A) * op(B); op(A) is M x K, all dimensions <= 80.  Column-major;
+// ta/tb = transpose flags.  Block-cooperative: op(A) and op(B) are first staged in shared memory
+// (sa[i + LD k], sb[k + LD j]; the global reads are coalesced whichever way the operand lies, the
+// odd leading dimension keeps the transposing writes conflict-free), then every thread owns a
+// strided 4x4 set of outputs -- rows i, i+tm, i+2tm, i+3tm -- so that the lanes of a warp read
+// consecutive words of sa and broadcast words of sb.  Operands may have been written by this
+// block (plain loads).  C may live in global or shared memory, but not in sa/sb.
 __device__ void blk_gemm(int M, int N, int K, double alpha, const double *A, int lda, bool ta, const double *B, int ldb,
-                         bool tb, double *C, int ldc) {
-  const int tm = (M + 1) / 2, tn = (N + 1) / 2;
-  for (int t = threadIdx.x; t < tm * tn; t += blockDim.x) {
-    const int i0 = 2 * (t % tm), j0 = 2 * (t / tm);
-    const bool i1 = i0 + 1 < M, j1 = j0 + 1 < N;
-    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-    for (int k = 0; k < K; ++k) {
-      const double a0 = ta ? A[(size_t)k + (size_t)lda * i0] : A[(size_t)i0 + (size_t)lda * k];
-      const double a1 = i1 ? (ta ? A[(size_t)k + (size_t)lda * (i0 + 1)] : A[(size_t)i0 + 1 + (size_t)lda * k]) : 0.0;
-      const double b0 = tb ? B[(size_t)j0 + (size_t)ldb * k] : B[(size_t)k + (size_t)ldb * j0];
-      const double b1 = j1 ? (tb ? B[(size_t)j0 + 1 + (size_t)ldb * k] : B[(size_t)k + (size_t)ldb * (j0 + 1)]) : 0.0;
-      c00 = fma(a0, b0, c00); c01 = fma(a0, b1, c01);
-      c10 = fma(a1, b0, c10); c11 = fma(a1, b1, c11);
+                         bool tb, double *C, int ldc, double *sa, double *sb) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  // Staging: a warp copies whole columns of the operand as it lies in memory (coalesced), every
+  // lane fetching all of its elements of up to five columns BEFORE the first store -- the loads
+  // would otherwise be serialised behind the stores (the compiler must assume sa aliases A).
+  auto stage = [&](const double *src, int ld, int rows, int cols, double *dst, bool transpose_into) {
+    // element (r, c) of src goes to dst[r + LD c] (or dst[c + LD r] when transposing)
+    for (int c0 = warp; c0 < cols; c0 += 5 * n_warps) {
+      double v[5][3];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int c = c0 + u * n_warps;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const int r = lane + 32 * w;
+          if (c < cols && r < rows) v[u][w] = src[(size_t)r + (size_t)ld * c];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int c = c0 + u * n_warps;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const int r = lane + 32 * w;
+          if (c < cols && r < rows) dst[transpose_into ? c + SCF_LD * r : r + SCF_LD * c] = v[u][w];
+        }
+      }
     }
-    C[(size_t)i0 + (size_t)ldc * j0] = alpha * c00;
-    if (j1) C[(size_t)i0 + (size_t)ldc * (j0 + 1)] = alpha * c01;
-    if (i1) C[(size_t)i0 + 1 + (size_t)ldc * j0] = alpha * c10;
-    if (i1 && j1) C[(size_t)i0 + 1 + (size_t)ldc * (j0 + 1)] = alpha * c11;
+  };
+  // sa[i + LD k] = op(A)(i, k): A is M x K as stored when !ta, K x M when ta
+  if (!ta) stage(A, lda, M, K, sa, false); else stage(A, lda, K, M, sa, true);
+  // sb[k + LD j] = op(B)(k, j): B is K x N as stored when !tb, N x K when tb
+  if (!tb) stage(B, ldb, K, N, sb, false); else stage(B, ldb, N, K, sb, true);
+  __syncthreads();
+  const int tm = (M + 3) / 4, tn = (N + 3) / 4;
+  for (int t = threadIdx.x; t < tm * tn; t += blockDim.x) {
+    const int ti = t % tm, tj = t / tm;
+    int ri[4], cj[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      ri[r] = ti + r * tm < M ? ti + r * tm : M - 1;       // ragged edge: computed and dropped
+      cj[r] = tj + r * tn < N ? tj + r * tn : N - 1;
+    }
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { av[r] = sa[ri[r] + SCF_LD * k]; bv[r] = sb[k + SCF_LD * cj[r]]; }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (ti + r * tm < M && tj + c * tn < N) C[(size_t)(ti + r * tm) + (size_t)ldc * (tj + c * tn)] = alpha * acc[r][c];
   }
   __syncthreads();
 }
@@ -74,9 +128,14 @@ __device__ double blk_sum(double v, double *red /*[SCF_THREADS/32 + 1]*/) {
 // on return a_s's diagonal holds the eigenvalues and v_s the eigenvectors (columns), both
 // UNSORTED.  Cyclic Jacobi, round-robin ordering: round r pairs position i with position
 // m_e-1-i of the sequence [0, 1+((k-1+r) mod (m_e-1))], so the m_e/2 rotations of a round touch
-// disjoint rows/columns and are applied in parallel: columns of A and V, then rows of A.
-__device__ void jacobi_eigh(double *a_s, double *v_s, int m, double *red, int *pq_s /*[2*40]*/, double *cs_s /*[2*40]*/,
-                            int *rotated_s) {
+// disjoint rows/columns and are applied in parallel.  A warp owns up to three rotations of a
+// round: it derives their (c, s) itself (every lane the same arithmetic -- they only read
+// columns p and q, which nobody else writes in this phase), rotates those columns of A and V,
+// and after ONE barrier rotates the rows p and q of A with the (c, s) still in its registers.
+// Returns the number of sweeps.
+constexpr int SCF_JW = 3;      // rotations per warp and round: ceil(40 / 16 warps)
+
+__device__ int jacobi_eigh(double *a_s, double *v_s, int m, double *red, int *rotated_s) {
   const int tid = threadIdx.x, nth = blockDim.x;
   const int m_e = (m + 1) & ~1, half = m_e / 2;
   for (int e = tid; e < m * m; e += nth) {
@@ -86,64 +145,111 @@ __device__ void jacobi_eigh(double *a_s, double *v_s, int m, double *red, int *p
   double fro = 0.0;
   for (int e = tid; e < m * m; e += nth) { const double x = a_s[(e % m) + SCF_LD * (e / m)]; fro = fma(x, x, fro); }
   fro = blk_sum(fro, red);
-  // an off-diagonal element below 1e-17 |A|_F is left alone; a sweep that rotates nothing ends the iteration
-  const double skip = 1.0e-17 * sqrt(fro);
+  // an off-diagonal element below 2e-16 |A|_F is left alone (eigenvectors then carry errors of that size
+  // over the gap); a sweep that rotates nothing ends the iteration
+  const double skip = 2.0e-16 * sqrt(fro);
+  const int warp = tid >> 5, lane = tid & 31, n_warps = nth >> 5;
+  int sweeps = 0;
   for (int sweep = 0; sweep < 40; ++sweep) {
+    ++sweeps;
     if (tid == 0) *rotated_s = 0;
     __syncthreads();
-    for (int r = 0; r < m_e - 1; ++r) {
-      if (tid < half) {
-        const int pa = tid == 0 ? 0 : 1 + (tid - 1 + r) % (m_e - 1);
-        const int pb = 1 + (m_e - 1 - tid - 1 + r) % (m_e - 1);
-        int p = pa < pb ? pa : pb, q = pa < pb ? pb : pa;
-        double c = 1.0, s = 0.0;
-        if (q < m) {
-          const double apq = a_s[p + SCF_LD * q];
-          const double app = a_s[p + SCF_LD * p], aqq = a_s[q + SCF_LD * q];
-          if (fabs(apq) > skip) {
-            const double tau = (aqq - app) / (2.0 * apq);
-            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + t * t);
-            s = t * c;
-            *rotated_s = 1;
-          }
-        } else {
-          q = p;                                           // the padding index of an odd m: no rotation
-        }
-        pq_s[2 * tid] = p; pq_s[2 * tid + 1] = q;
-        cs_s[2 * tid] = c; cs_s[2 * tid + 1] = s;
-      }
-      __syncthreads();
-      // columns: (A[:,p], A[:,q]) <- (c A[:,p] - s A[:,q], s A[:,p] + c A[:,q]); same for V
-      for (int e = tid; e < half * m * 2; e += nth) {
-        const int which = e / (half * m);                  // 0: A, 1: V
-        const int f = e - which * half * m;
-        const int k = f / m, i = f - k * m;
-        const int p = pq_s[2 * k], q = pq_s[2 * k + 1];
-        if (p == q) continue;
-        const double c = cs_s[2 * k], s = cs_s[2 * k + 1];
-        double *mat = which ? v_s : a_s;
-        const double xp = mat[i + SCF_LD * p], xq = mat[i + SCF_LD * q];
-        mat[i + SCF_LD * p] = c * xp - s * xq;
-        mat[i + SCF_LD * q] = s * xp + c * xq;
-      }
-      __syncthreads();
-      // rows of A
-      for (int e = tid; e < half * m; e += nth) {
-        const int k = e / m, j = e - k * m;
-        const int p = pq_s[2 * k], q = pq_s[2 * k + 1];
-        if (p == q) continue;
-        const double c = cs_s[2 * k], s = cs_s[2 * k + 1];
-        const double xp = a_s[p + SCF_LD * j], xq = a_s[q + SCF_LD * j];
-        a_s[p + SCF_LD * j] = c * xp - s * xq;
-        a_s[q + SCF_LD * j] = s * xp + c * xq;
-      }
-      __syncthreads();
+    int any = 0;
+    int slot[SCF_JW];                                     // position of this warp's pairs in the round-robin sequence
+#pragma unroll
+    for (int u = 0; u < SCF_JW; ++u) slot[u] = warp + n_warps * u;
+    // sequence position -> index: pos 0 is index 0, pos k >= 1 is 1 + (k - 1 + r) mod (m_e - 1); kept incrementally
+    int ia[SCF_JW], ib[SCF_JW];
+#pragma unroll
+    for (int u = 0; u < SCF_JW; ++u) {
+      ia[u] = slot[u] == 0 ? 0 : 1 + (slot[u] - 1) % (m_e - 1);
+      ib[u] = 1 + (m_e - 2 - slot[u] + (m_e - 1)) % (m_e - 1);
     }
+    for (int r = 0; r < m_e - 1; ++r) {
+      int pp[SCF_JW], qq[SCF_JW];
+      double cc[SCF_JW], ss[SCF_JW];
+#pragma unroll
+      for (int u = 0; u < SCF_JW; ++u) {
+        const int p = ia[u] < ib[u] ? ia[u] : ib[u], q = ia[u] < ib[u] ? ib[u] : ia[u];
+        pp[u] = p; qq[u] = q; cc[u] = 1.0; ss[u] = 0.0;
+        if (slot[u] < half && q < m) {
+          const double apq = a_s[p + SCF_LD * q];
+          if (fabs(apq) > skip) {
+            // t = sgn(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 apq), written with one
+            // square root and one division; c = (1 + t^2)^-1/2
+            const double d = a_s[q + SCF_LD * q] - a_s[p + SCF_LD * p];
+            const double num = d >= 0.0 ? 2.0 * apq : -2.0 * apq;
+            const double t = num / (fabs(d) + sqrt(fma(d, d, 4.0 * apq * apq)));
+            const double c = rsqrt(fma(t, t, 1.0));
+            cc[u] = c; ss[u] = t * c;
+            any = 1;
+          }
+        }
+      }
+      __syncwarp();                                        // every lane has read a_pp, a_qq, a_pq before any lane rotates
+      // columns: (A[:,p], A[:,q]) <- (c A[:,p] - s A[:,q], s A[:,p] + c A[:,q]); same for V
+#pragma unroll
+      for (int u = 0; u < SCF_JW; ++u) {
+        if (ss[u] == 0.0) continue;
+        const int p = pp[u], q = qq[u];
+        const double c = cc[u], s = ss[u];
+        double xp[3], xq[3], vp[3], vq[3];
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const int i = lane + 32 * w;
+          if (i < m) {
+            xp[w] = a_s[i + SCF_LD * p]; xq[w] = a_s[i + SCF_LD * q];
+            vp[w] = v_s[i + SCF_LD * p]; vq[w] = v_s[i + SCF_LD * q];
+          }
+        }
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const int i = lane + 32 * w;
+          if (i < m) {
+            a_s[i + SCF_LD * p] = c * xp[w] - s * xq[w];
+            a_s[i + SCF_LD * q] = s * xp[w] + c * xq[w];
+            v_s[i + SCF_LD * p] = c * vp[w] - s * vq[w];
+            v_s[i + SCF_LD * q] = s * vp[w] + c * vq[w];
+          }
+        }
+      }
+      __syncthreads();
+      // rows of A (stride SCF_LD is odd: the lanes hit distinct banks)
+#pragma unroll
+      for (int u = 0; u < SCF_JW; ++u) {
+        if (ss[u] == 0.0) continue;
+        const int p = pp[u], q = qq[u];
+        const double c = cc[u], s = ss[u];
+        double xp[3], xq[3];
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const int j = lane + 32 * w;
+          if (j < m) { xp[w] = a_s[p + SCF_LD * j]; xq[w] = a_s[q + SCF_LD * j]; }
+        }
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const int j = lane + 32 * w;
+          if (j < m) {
+            a_s[p + SCF_LD * j] = c * xp[w] - s * xq[w];
+            a_s[q + SCF_LD * j] = s * xp[w] + c * xq[w];
+          }
+        }
+      }
+      __syncthreads();
+      // next round: every position but 0 moves on by one
+#pragma unroll
+      for (int u = 0; u < SCF_JW; ++u) {
+        if (slot[u] != 0) ia[u] = ia[u] == m_e - 1 ? 1 : ia[u] + 1;
+        ib[u] = ib[u] == m_e - 1 ? 1 : ib[u] + 1;
+      }
+    }
+    if (any && lane == 0) *rotated_s = 1;
+    __syncthreads();
     const int rotated = *rotated_s;
     __syncthreads();                                       // everyone has read it before the next sweep resets it
     if (rotated == 0) break;
   }
+  return sweeps;
 }
 
 // Ascending order of the m diagonal entries of a_s: order_s[k] = index of the k-th smallest
@@ -164,10 +270,10 @@ __device__ void sort_eigenvalues(const double *a_s, int m, int *order_s) {
 struct ScfShared {
   double a[SCF_MAX_N * SCF_LD];
   double v[SCF_MAX_N * SCF_LD];
+  double ga[SCF_MAX_N * SCF_LD];       // operand staging of blk_gemm
+  double gb[SCF_MAX_N * SCF_LD];
   double red[SCF_THREADS / 32 + 2];
-  double cs[2 * (SCF_MAX_N / 2)];
   double coef[16];
-  int pq[2 * (SCF_MAX_N / 2)];
   int order[SCF_MAX_N];
   int flag;
   int rotated;
@@ -181,7 +287,7 @@ __global__ void __launch_bounds__(SCF_THREADS, 1) scf_orthogonalizer_kernel(cons
   ScfShared &sh = *reinterpret_cast<ScfShared *>(smem_raw);
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) sh.a[(e % n) + SCF_LD * (e / n)] = s[e];
   __syncthreads();
-  jacobi_eigh(sh.a, sh.v, n, sh.red, sh.pq, sh.cs, &sh.rotated);
+  jacobi_eigh(sh.a, sh.v, n, sh.red, &sh.rotated);
   sort_eigenvalues(sh.a, n, sh.order);
   if (threadIdx.x == 0) {
     int dropped = 0;
@@ -222,6 +328,10 @@ __global__ void __launch_bounds__(SCF_THREADS, 1) scf_step_kernel(ScfStepArgs p)
   if (p.mode == 1 && p.state[3] != 0) return;            // already converged: later queued iterations are no-ops
   double *w0 = p.work, *w1 = w0 + nn, *w2 = w1 + nn, *w3 = w2 + nn;
   const double *f_use = p.fock;
+  long long t_mark = clock64();
+  auto lap = [&](int slot) {               // development instrumentation: clocks per stage, scalars[8 + slot]
+    if (tid == 0) { const long long now = clock64(); p.scalars[8 + slot] = (double)(now - t_mark); t_mark = now; }
+  };
 
   if (p.mode == 0) {
     // ---- starting Fock: core (F = H) or generalised Wolfsberg-Helmholz (rhf.f90:1354-1380)
@@ -234,11 +344,11 @@ __global__ void __launch_bounds__(SCF_THREADS, 1) scf_step_kernel(ScfStepArgs p)
     __syncthreads();
   } else {
     // ---- commutator e = X^T (F D S - S D F) X; S D F = (F D S)^T for the symmetric F, D, S
-    blk_gemm(n, n, n, 1.0, p.fock, n, false, p.density, n, false, w0, n);        // F D
-    blk_gemm(n, n, n, 1.0, w0, n, false, p.s, n, false, w1, n);                  // F D S
+    blk_gemm(n, n, n, 1.0, p.fock, n, false, p.density, n, false, w0, n, sh.ga, sh.gb);        // F D
+    blk_gemm(n, n, n, 1.0, w0, n, false, p.s, n, false, w1, n, sh.ga, sh.gb);                  // F D S
     for (int e = tid; e < nn; e += nth) { const int i = e % n, j = e / n; w0[e] = w1[e] - w1[(size_t)j + (size_t)n * i]; }
     __syncthreads();
-    blk_gemm(n, m, n, 1.0, w0, n, false, p.x, n, false, w2, n);                  // (..) X
+    blk_gemm(n, m, n, 1.0, w0, n, false, p.x, n, false, w2, n, sh.ga, sh.gb);                  // (..) X
     // ---- DIIS push (mqc_diis.f90:94-119): the ring slot after the newest; overlaps of the new entry
     int n_stored = p.state[0], newest = p.state[1];
     const int dmax = p.diis_max;
@@ -246,15 +356,27 @@ __global__ void __launch_bounds__(SCF_THREADS, 1) scf_step_kernel(ScfStepArgs p)
       newest = newest % dmax + 1;
       if (n_stored < dmax) n_stored += 1;
       const int slot = newest - 1;
-      blk_gemm(m, m, n, 1.0, p.x, n, true, w2, n, false, p.diis_e + (size_t)slot * mm, m);   // X^T (..)
+      blk_gemm(m, m, n, 1.0, p.x, n, true, w2, n, false, p.diis_e + (size_t)slot * mm, m, sh.ga, sh.gb);   // X^T (..)
       for (int e = tid; e < nn; e += nth) p.diis_f[(size_t)slot * nn + e] = p.fock[e];
       __syncthreads();
-      for (int age = 1; age <= n_stored; ++age) {
-        const int other = ((newest - n_stored + age - 1) % dmax + dmax) % dmax;          // diis_slot_of_age - 1
-        double part = 0.0;
-        for (int e = tid; e < mm; e += nth) part = fma(p.diis_e[(size_t)slot * mm + e], p.diis_e[(size_t)other * mm + e], part);
-        const double dot = blk_sum(part, sh.red);
-        if (tid == 0) { p.diis_b[slot * dmax + other] = dot; p.diis_b[other * dmax + slot] = dot; }
+      {
+        // overlaps of the new error vector with every stored one, all in one pass over the new vector
+        double part[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) part[g] = 0.0;
+        for (int e = tid; e < mm; e += nth) {
+          const double en = p.diis_e[(size_t)slot * mm + e];
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g < n_stored) part[g] = fma(en, p.diis_e[(size_t)(((newest - n_stored + g) % dmax + dmax) % dmax) * mm + e], part[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (g >= n_stored) break;                                                          // uniform
+          const int other = ((newest - n_stored + g) % dmax + dmax) % dmax;                  // diis_slot_of_age(g+1) - 1
+          const double dot = blk_sum(part[g], sh.red);
+          if (tid == 0) { p.diis_b[slot * dmax + other] = dot; p.diis_b[other * dmax + slot] = dot; }
+        }
       }
       __syncthreads();
       // ---- coefficients (mqc_diis.f90:146-273): ages oldest -> newest, error block scaled to O(1)
@@ -318,22 +440,39 @@ __global__ void __launch_bounds__(SCF_THREADS, 1) scf_step_kernel(ScfStepArgs p)
     }
   }
 
-  // ---- diagonalize (rhf.f90:1464-1489): F' = X^T F X, eigenvectors, C = X C'
-  blk_gemm(n, m, n, 1.0, f_use, n, false, p.x, n, false, w0, n);                 // F X
-  blk_gemm(m, m, n, 1.0, p.x, n, true, w0, n, false, sh.a, SCF_LD);              // X^T F X, into shared memory
-  jacobi_eigh(sh.a, sh.v, m, sh.red, sh.pq, sh.cs, &sh.rotated);
+  lap(0);
+  // ---- diagonalize (rhf.f90:1464-1489): F' = Y^T F Y, eigenvectors V, C = Y V.  The reference takes
+  // Y = X every time; any S-orthonormal basis of the same space gives the same C up to the
+  // eigensolver's rounding, so an iteration takes Y = the PREVIOUS orbitals: F' is then nearly
+  // diagonal and the Jacobi iteration needs two or three sweeps instead of nine.  (The guess step
+  // has no previous orbitals and takes Y = X.)
+  const double *y = p.mode == 0 ? p.x : p.coeff;
+  blk_gemm(n, m, n, 1.0, f_use, n, false, y, n, false, w0, n, sh.ga, sh.gb);                   // F Y
+  blk_gemm(m, m, n, 1.0, y, n, true, w0, n, false, sh.a, SCF_LD, sh.ga, sh.gb);                // Y^T F Y, into shared memory
+  for (int e = tid; e < mm; e += nth) {                                          // exactly symmetric input
+    const int i = e % m, j = e / m;
+    if (i > j) { const double v = 0.5 * (sh.a[i + SCF_LD * j] + sh.a[j + SCF_LD * i]); sh.a[i + SCF_LD * j] = v; sh.a[j + SCF_LD * i] = v; }
+  }
+  __syncthreads();
+  lap(1);
+  const int sweeps = jacobi_eigh(sh.a, sh.v, m, sh.red, &sh.rotated);
+  lap(2);
+  if (tid == 0) p.scalars[5] = (double)sweeps;
   sort_eigenvalues(sh.a, m, sh.order);
   for (int k = tid; k < m; k += nth) p.eps[k] = sh.a[sh.order[k] + SCF_LD * sh.order[k]];
-  // C' with sorted columns, into w1 (m x m), then C = X C'
+  // V with sorted columns, into w1 (m x m), then C = Y V (via w3: Y may be p.coeff itself)
   for (int e = tid; e < mm; e += nth) { const int i = e % m, k = e / m; w1[e] = sh.v[i + SCF_LD * sh.order[k]]; }
   __syncthreads();
-  blk_gemm(n, m, m, 1.0, p.x, n, false, w1, m, false, p.coeff, n);
+  blk_gemm(n, m, m, 1.0, y, n, false, w1, m, false, w0, n, sh.ga, sh.gb);
+  for (int e = tid; e < n * m; e += nth) p.coeff[e] = w0[e];
+  __syncthreads();
   // ---- density D = 2 C_occ C_occ^T and rms(dD)
-  blk_gemm(n, n, p.n_occ, 2.0, p.coeff, n, false, p.coeff, n, true, w2, n);
+  blk_gemm(n, n, p.n_occ, 2.0, p.coeff, n, false, p.coeff, n, true, w2, n, sh.ga, sh.gb);
   double part = 0.0;
   for (int e = tid; e < nn; e += nth) { const double d = w2[e] - p.density[e]; part = fma(d, d, part); }
   const double ss = blk_sum(part, sh.red);
   for (int e = tid; e < nn; e += nth) p.density[e] = w2[e];
+  lap(3);
   if (tid == 0 && p.mode == 1) {
     const double e_elec = p.scalars[0];
     const double de = fabs(e_elec - p.scalars[1]);

@@ -182,6 +182,27 @@ int mqcb200_scf_fragment(void *handle, int slot, const double *hcore, const doub
  * iterations after convergence are no-ops on the device). */
 int mqcb200_set_scf_check_every(void *handle, int iterations);
 
+/* ---- DF two-electron gradient: the two densities ---------------
+ * The contraction half of df_two_electron_gradient + add_exchange_channel
+ * (backends/libcint/mqc_libcint_gradient.f90:1545-1812): everything between the energy-side
+ * integrals and the derivative integrals, i.e.
+ *     rho = J^-1 g,  f^P = (J^-1 e)^P with e^P_ij = C^T (mu nu|P) C,
+ *     gamma(:, :, P) = rho_P D - sum_spin w_s C f^{s,P} C^T           (nao, nao, naux)
+ *     omega          = -1/2 rho rho^T + sum_spin (w_s/2) sum_ij f^{s,P}_ij f^{s,Q}_ij   (naux, naux)
+ * with w = 2*exx_fraction for the single closed-shell channel and exx_fraction for each of the
+ * two unrestricted ones (unrestricted != 0; a channel with n == 0 is skipped), exx_fraction == 0
+ * skipping the exchange assembly, with_coulomb == 0 dropping both Coulomb shapes.  Formed from the
+ * tensor RESIDENT on `slot` (the whitened B = (mu nu|P) . J^-1/2) and `half` = J^-1/2 (naux x naux,
+ * the matrix metric_inverse_sqrt returned when the tensor was built), so neither (mu nu|P) nor the
+ * metric is regenerated.  The derivative integrals (three_centre_deriv, two_centre_deriv) and the
+ * final per-atom sums (:1738-1770) stay with the caller.  gamma and omega are host arrays. */
+int mqcb200_df_gradient_densities(void *handle, int slot, const double *half,
+                                  const double *total_density,
+                                  const double *orbitals, int lda, int n_occupied,
+                                  const double *orbitals_beta, int ldb, int n_occupied_beta,
+                                  int unrestricted, double exx_fraction, int with_coulomb,
+                                  double *gamma, double *omega);
+
 /* E = 1/2 sum D (H + F)  (electronic_energy, mqc_libcint_rhf.f90:1691-1697),
  * evaluated on the device from the operands of the last mqcb200_build_fock. */
 int mqcb200_last_energy(void *handle, double *e_elec);

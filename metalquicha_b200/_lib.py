@@ -56,6 +56,8 @@ SIGNATURES = {
                                      c_double, _dp, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "mqcb200_set_scf_check_every": (c_int, [c_void_p, c_int]),
+    "mqcb200_df_gradient_densities": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                              c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p]),
     "mqcb200_last_energy": (c_int, [c_void_p, POINTER(c_double)]),
     "mqcb200_build_fock_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                           c_double, c_double, c_void_p, c_int]),

@@ -1201,6 +1201,142 @@ static void scf_fragment(Engine *e, const ScfArgs &a) {
   if (a.n_mo) *a.n_mo = n_mo;
 }
 
+// ------------------------------- DF gradient densities -------------------------------------
+// The two densities every term of the density-fitted two-electron gradient is contracted with
+// (df_two_electron_gradient + add_exchange_channel, backends/libcint/mqc_libcint_gradient.f90:
+// 1545-1812), formed on the device from the RESIDENT whitened tensor B = (mu nu|P) . J^(-1/2) and
+// the caller's J^(-1/2) (`half`) -- the reference re-generates (mu nu|P) and the metric for this:
+//
+//   rho    = J^-1 g = half . gamma,          gamma_R = sum B_R . D              (:1672-1676)
+//   e~^R   = C^T B_R C ,   f^P = sum_R half(P,R) e~^R   (= J^-1 e, :1781-1795)
+//   Gamma^P = rho_P D - sum_spin w_s C f^{s,P} C^T                               (:1678-1681, :1797-1804)
+//   Omega   = -1/2 rho rho^T + sum_spin (w_s / 2) sum_ij f^{s,P}_ij f^{s,Q}_ij   (:1696-1700, :1806-1812)
+//
+// w = 2 kf for the single closed-shell channel, kf for each unrestricted one (:1706-1716); kf = 0
+// skips the whole exchange assembly (:1702-1705); with_coulomb = false drops BOTH Coulomb shapes
+// (:1677, :1696-1700).  The derivative integrals stay on the host (libcint).
+struct GradArgs {
+  int slot = 0;
+  const double *half = nullptr, *density = nullptr, *ca = nullptr, *cb = nullptr;
+  int lda = 0, ldb = 0, n_a = 0, n_b = 0;
+  bool unrestricted = false, with_coulomb = true;
+  double kf = 1.0;
+  double *gamma = nullptr, *omega = nullptr;
+};
+
+static void df_gradient_densities(Engine *e, const GradArgs &a) {
+  if (a.slot < 0 || a.slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  TensorSlot &sl = e->slots[a.slot];
+  if (!sl.set) throw Failure("mqcb200: no fitted tensor has been set on this slot (call mqcb200_set_tensor first)");
+  if (sl.q_count != sl.naux_total || (e->comm && e->n_ranks > 1))
+    throw Failure("mqcb200: the gradient densities need the whole tensor on this GPU");
+  if (!a.half || !a.density || !a.gamma || !a.omega) throw Failure("mqcb200: null argument to df_gradient_densities");
+  if (a.n_a < 0 || a.n_b < 0 || (a.n_a > 0 && (!a.ca || a.lda < sl.n)) || (a.unrestricted && a.n_b > 0 && (!a.cb || a.ldb < sl.n)))
+    throw Failure("mqcb200: bad orbital matrix / leading dimension");
+  e->bind();
+  e->launches = 0;
+  const int n = sl.n, Q = sl.naux_total;
+  const size_t nn = (size_t)n * n;
+  cudaStream_t st = e->stream;
+  struct Channel { const double *c_host; int ld, o; double w; DevBuf c, et, f; };
+  Channel ch[2];
+  int n_ch = 0;
+  if (a.kf != 0.0) {
+    if (a.unrestricted) {
+      if (a.n_a > 0) { ch[n_ch].c_host = a.ca; ch[n_ch].ld = a.lda; ch[n_ch].o = a.n_a; ch[n_ch].w = a.kf; ++n_ch; }
+      if (a.n_b > 0) { ch[n_ch].c_host = a.cb; ch[n_ch].ld = a.ldb; ch[n_ch].o = a.n_b; ch[n_ch].w = a.kf; ++n_ch; }
+    } else if (a.n_a > 0) {
+      ch[n_ch].c_host = a.ca; ch[n_ch].ld = a.lda; ch[n_ch].o = a.n_a; ch[n_ch].w = 2.0 * a.kf; ++n_ch;
+    }
+  }
+  int o_max = 1;
+  for (int k = 0; k < n_ch; ++k) o_max = std::max(o_max, ch[k].o);
+  // auxiliary functions per pass: unpacked slabs, half-transformed slabs and the Gamma block share ~1 GiB
+  size_t chunk = std::max<size_t>(1, ((size_t)384 << 20) / (nn * sizeof(double)));
+  chunk = std::min<size_t>(chunk, (size_t)Q);
+  DevBuf d_half, d_dens, d_rho, d_omega, d_u, d_x, d_z;
+  auto release_all = [&]() {
+    for (DevBuf *b : {&d_half, &d_dens, &d_rho, &d_omega, &d_u, &d_x, &d_z}) b->release();
+    for (int k = 0; k < 2; ++k) { ch[k].c.release(); ch[k].et.release(); ch[k].f.release(); }
+  };
+  try {
+    d_half.ensure((size_t)Q * Q * sizeof(double));
+    d_dens.ensure(nn * sizeof(double));
+    d_rho.ensure((size_t)Q * sizeof(double));
+    d_omega.ensure((size_t)Q * Q * sizeof(double));
+    d_u.ensure(chunk * nn * sizeof(double));
+    d_x.ensure(chunk * (size_t)n * o_max * sizeof(double));
+    d_z.ensure(chunk * nn * sizeof(double));
+    CUDA_CHECK(cudaMemcpyAsync(d_half.ptr, a.half, (size_t)Q * Q * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(d_dens.ptr, a.density, nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < n_ch; ++k) {
+      const int o = ch[k].o;
+      ch[k].c.ensure((size_t)n * o * sizeof(double));
+      ch[k].et.ensure((size_t)o * o * Q * sizeof(double));
+      ch[k].f.ensure((size_t)o * o * Q * sizeof(double));
+      CUDA_CHECK(cudaMemcpy2DAsync(ch[k].c.ptr, (size_t)n * sizeof(double), ch[k].c_host, (size_t)ch[k].ld * sizeof(double),
+                                   (size_t)n * sizeof(double), o, cudaMemcpyHostToDevice, st));
+    }
+    // ---- rho = half . gamma, gamma_R = sum B_R . D  (the Coulomb kernels' first pass)
+    if (a.with_coulomb) {
+      JPlan jp = plan_j(n, Q);
+      e->d_w.ensure((size_t)sl.L * sizeof(double));
+      e->d_gamma_partial.ensure(jp.gamma_partial_elems * sizeof(double));
+      e->d_gamma.ensure((size_t)Q * sizeof(double));
+      launch_pack_density(d_dens.d(), n, e->d_w.d(), nullptr, st);
+      launch_j_gamma(sl.packed.d(), sl.L, Q, e->d_w.d(), jp, e->d_gamma_partial.d(), e->d_gamma.d(), nullptr, st);
+      launch_dgemm_batched(Q, 1, Q, 1.0, d_half.d(), Q, 0, false, e->d_gamma.d(), Q, 0, false, 0.0, d_rho.d(), Q, 0, 1, st);
+      launch_dgemm_batched(Q, Q, 1, -0.5, d_rho.d(), Q, 0, false, d_rho.d(), Q, 0, true, 0.0, d_omega.d(), Q, 0, 1, st);
+      e->launches += 5;
+    } else {
+      CUDA_CHECK(cudaMemsetAsync(d_rho.ptr, 0, (size_t)Q * sizeof(double), st));
+      CUDA_CHECK(cudaMemsetAsync(d_omega.ptr, 0, (size_t)Q * Q * sizeof(double), st));
+    }
+    // ---- per channel: e~^R = C^T B_R C for every R, f = e~ . half, Omega += (w/2) f^T f
+    for (int k = 0; k < n_ch; ++k) {
+      const int o = ch[k].o;
+      for (size_t r0 = 0; r0 < (size_t)Q; r0 += chunk) {
+        const int rc = (int)std::min(chunk, (size_t)Q - r0);
+        launch_unpack_tensor(sl.packed.d() + r0 * (size_t)sl.L, n, rc, d_u.d(), st);
+        launch_dgemm_batched(n, o, n, 1.0, d_u.d(), n, (long long)nn, false, ch[k].c.d(), n, 0, false, 0.0, d_x.d(), n,
+                             (long long)n * o, rc, st);                                     // X_R = B_R C
+        launch_dgemm_batched(o, o, n, 1.0, ch[k].c.d(), n, 0, true, d_x.d(), n, (long long)n * o, false, 0.0,
+                             ch[k].et.d() + r0 * (size_t)o * o, o, (long long)o * o, rc, st);   // e~^R = C^T X_R
+        e->launches += 3;
+      }
+      launch_dgemm_batched(o * o, Q, Q, 1.0, ch[k].et.d(), (long long)o * o, 0, false, d_half.d(), Q, 0, false, 0.0,
+                           ch[k].f.d(), (long long)o * o, 0, 1, st);                          // f = e~ . half
+      launch_dgemm_batched(Q, Q, o * o, 0.5 * ch[k].w, ch[k].f.d(), (long long)o * o, 0, true, ch[k].f.d(),
+                           (long long)o * o, 0, false, 1.0, d_omega.d(), Q, 0, 1, st);        // Omega += (w/2) f^T f
+      e->launches += 2;
+    }
+    // ---- Gamma, a block of auxiliary functions at a time, straight to the caller's array
+    for (size_t p0 = 0; p0 < (size_t)Q; p0 += chunk) {
+      const int pc = (int)std::min(chunk, (size_t)Q - p0);
+      launch_gradient_gamma(d_rho.d() + p0, d_dens.d(), nullptr, 0.0, n, pc, false, d_u.d(), st);   // rho_P D
+      e->launches += 1;
+      for (int k = 0; k < n_ch; ++k) {
+        const int o = ch[k].o;
+        launch_dgemm_batched(n, o, o, 1.0, ch[k].c.d(), n, 0, false, ch[k].f.d() + p0 * (size_t)o * o, o, (long long)o * o,
+                             false, 0.0, d_x.d(), n, (long long)n * o, pc, st);               // C f^P
+        launch_dgemm_batched(n, n, o, 1.0, d_x.d(), n, (long long)n * o, false, ch[k].c.d(), n, 0, true, 0.0, d_z.d(), n,
+                             (long long)nn, pc, st);                                          // Z^P = (C f^P) C^T
+        launch_gradient_gamma(nullptr, nullptr, d_z.d(), ch[k].w, n, pc, true, d_u.d(), st);  // Gamma^P -= w Z^P
+        e->launches += 3;
+      }
+      CUDA_CHECK(cudaMemcpyAsync(a.gamma + p0 * nn, d_u.ptr, (size_t)pc * nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(a.omega, d_omega.ptr, (size_t)Q * Q * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  } catch (...) {
+    release_all();
+    throw;
+  }
+  release_all();
+}
+
 // ------------------------------- fragment FIFO -------------------------------------------
 struct Fifo {
   uint32_t magic = 0x4D51F1F0u;
@@ -1618,6 +1754,20 @@ int mqcb200_scf_fragment(void *handle, int slot, const double *hcore, const doub
   a.e_electronic = e_electronic; a.iterations = iterations; a.converged = converged; a.n_mo = n_mo;
   a.coeff = coeff; a.eps = orbital_energies; a.density = density; a.e_history = e_history;
   scf_fragment(e, a);
+  API_END
+}
+
+int mqcb200_df_gradient_densities(void *handle, int slot, const double *half, const double *total_density,
+                                  const double *orbitals, int lda, int n_occupied, const double *orbitals_beta,
+                                  int ldb, int n_occupied_beta, int unrestricted, double exx_fraction,
+                                  int with_coulomb, double *gamma, double *omega) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  GradArgs a;
+  a.slot = slot; a.half = half; a.density = total_density; a.ca = orbitals; a.lda = lda; a.n_a = n_occupied;
+  a.cb = orbitals_beta; a.ldb = ldb; a.n_b = n_occupied_beta; a.unrestricted = unrestricted != 0;
+  a.kf = exx_fraction; a.with_coulomb = with_coulomb != 0; a.gamma = gamma; a.omega = omega;
+  df_gradient_densities(e, a);
   API_END
 }
 

@@ -98,6 +98,17 @@ void launch_fragment_jk(const double *d_packed, int q_count, const double *d_w, 
                         const FragPlan &p, bool want_j, bool want_k, double *d_jpart, double *d_kpart,
                         cudaStream_t s);
 
+// ---- general strided-batched FP64 GEMM on DMMA + helpers of the gradient densities (gemm_kernels.cu)
+// C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b]; column-major, op(A) is M x K, op(B) is K x N.
+void launch_dgemm_batched(int M, int N, int K, double alpha, const double *a, long long lda, long long stride_a, bool ta,
+                          const double *b, long long ldb, long long stride_b, bool tb, double beta, double *c,
+                          long long ldc, long long stride_c, int batch, cudaStream_t s);
+// Packed slabs -> full symmetric n x n slabs (column-major), q_count of them.
+void launch_unpack_tensor(const double *d_packed, int n, int q_count, double *d_full, cudaStream_t s);
+// gamma(:,:,p) (+)= rho[p] * D - w * z(:,:,p) for p_count auxiliary functions (rho, D, z may be null == 0).
+void launch_gradient_gamma(const double *d_rho, const double *d_density, const double *d_z, double w, int n, int p_count,
+                           bool accumulate, double *d_gamma, cudaStream_t s);
+
 // ---- device-resident SCF step for fragment-sized problems (scf_kernels.cu) ---------------
 struct ScfStepLaunch {
   int n, n_mo, n_occ, diis_max, mode /*0 guess, 1 iteration*/, guess /*0 core, 1 GWH*/;

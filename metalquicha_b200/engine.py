@@ -335,6 +335,30 @@ class B200FockEngine:
                 "orbitals": np.asfortranarray(coeff.reshape(-1, order="F")[:n * m].reshape((n, m), order="F")),
                 "orbital_energies": eps[:m].copy(), "density": density, "e_history": hist[:it.value].copy()}
 
+    def df_gradient_densities(self, half, total_density, orbitals, n_occupied: int, orbitals_beta=None,
+                              n_occupied_beta: int = 0, exx_fraction=None, with_coulomb: bool = True,
+                              slot: int = SLOT_FULL_RANGE):
+        """The contraction half of ``df_two_electron_gradient`` (mqc_libcint_gradient.f90:1545-1812)
+        on the resident whitened tensor: returns ``(gamma(nao, nao, naux), omega(naux, naux))``.
+        ``half`` is the ``metric_inverse_sqrt`` the tensor was whitened with; ``orbitals_beta``
+        present means the unrestricted form (channel weight ``exx_fraction`` each instead of twice it)."""
+        n = self.n[slot]
+        naux = self.naux[slot][0]
+        half = np.asfortranarray(_f64_colmajor(half, "half"))
+        dens = np.asfortranarray(_f64_colmajor(total_density, "total_density"))
+        if half.shape != (naux, naux) or dens.shape != (n, n):
+            raise ValueError("half must be naux x naux and total_density nao x nao")
+        ca, lda = self._coeff(orbitals, n, n_occupied)
+        unrestricted = orbitals_beta is not None
+        cb, ldb = self._coeff(orbitals_beta, n, n_occupied_beta) if unrestricted and n_occupied_beta > 0 else (None, n)
+        gamma = np.empty((n, n, naux), dtype=np.float64, order="F")
+        omega = np.empty((naux, naux), dtype=np.float64, order="F")
+        _check(self._lib.mqcb200_df_gradient_densities(
+            self._h, slot, _ptr(half), _ptr(dens), _ptr(ca), lda, int(n_occupied), _ptr(cb), ldb, int(n_occupied_beta),
+            1 if unrestricted else 0, c_double(1.0 if exx_fraction is None else exx_fraction), 1 if with_coulomb else 0,
+            _ptr(gamma), _ptr(omega)))
+        return gamma, omega
+
     def last_energy(self) -> float:
         """``electronic_energy(h, fock, density)`` of the last ``build_fock_df`` (rhf.f90:1691-1697)."""
         e = c_double(0.0)

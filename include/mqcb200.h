@@ -81,11 +81,42 @@ int mqcb200_set_overlap(void *handle, int on);
 int mqcb200_set_tensor(void *handle, int slot, int n, int naux, const double *b);
 int mqcb200_set_tensor_shard(void *handle, int slot, int n, int naux_total,
                              int q_begin, int q_count, const double *b_shard);
-/* b = three . metric^(-1/2) on the device (build_df_tensor's last two stages,
- * mqc_libcint_integrals.F90:981-987, :992-1038): `half` is the caller's
- * metric^(-1/2) (naux x naux, symmetric). */
+/* b = three . metric^(-1/2) on the device (build_df_tensor's last stage,
+ * mqc_libcint_integrals.F90:985-986): `half` is metric^(-1/2) (naux x naux, symmetric).  The GEMM
+ * runs nu-slab by nu-slab straight into the packed resident layout: no second device copy. */
 int mqcb200_set_tensor_from_3c(void *handle, int slot, int n, int naux,
                                const double *three, const double *half);
+/* metric_inverse_sqrt(metric, half, error) (mqc_libcint_integrals.F90:992-1038) on the device:
+ * half = U s^(-1/2) U^T over the eigenvalues above null_threshold (the reference's 1e-10), the rest
+ * zeroed; *n_kept = surviving modes (may be NULL).  The eigendecomposition is a one-sided Jacobi
+ * iteration on the GPU (the reference calls LAPACK dsyev).  Fails with the reference's message
+ * "density fitting: the auxiliary metric is singular" when no mode survives. */
+int mqcb200_metric_inverse_sqrt(void *handle, int naux, const double *metric,
+                                double null_threshold, double *half, int *n_kept);
+/* The last two stages of build_df_tensor in one call: metric^(-1/2) on the device, then
+ * b = three . half slab by slab into `slot`.  half_out (naux x naux, host; may be NULL) receives
+ * metric^(-1/2) -- the gradient (mqcb200_df_gradient_densities) needs it again. */
+int mqcb200_build_df_tensor(void *handle, int slot, int n, int naux, const double *three,
+                            const double *metric, double null_threshold, double *half_out);
+/* The same GEMM fed by the caller slab by slab, so that three(nao*nao, naux) -- 115 GB for the
+ * 200-atom case -- never has to exist: the integral code produces (mu nu|P) for a block of nu
+ * (all mu, all P) and hands it over.
+ *   begin: allocates the packed slab [q_begin, q_begin+q_count) of `slot` and takes half (host).
+ *   push : three_cols points at element (mu=0, nu=nu_begin, P=0); consecutive auxiliary functions
+ *          are ld_aux doubles apart (nao*nao inside a full three, nao*nu_count for a compact
+ *          block).  nu_begin is a multiple of 16 and nu_count too, unless the block ends at nao.
+ *          Every nu must be pushed exactly once (in any order, by any rank).  Blocking.
+ *   end  : the tensor becomes usable.
+ * With a communicator active (whole-molecule builds sharded by auxiliary index) the three calls are
+ * collective in the sense that every rank makes them, but each rank pushes only ITS share of the
+ * nu blocks: a rank whitens its blocks for ALL auxiliary rows and the GEMM's epilogue stores every
+ * row directly into the packed tensor of the rank that owns it, over NVLink peer memory -- the
+ * all-to-all from mu-nu slabs to Q slabs costs no separate pass. */
+int mqcb200_whiten_begin(void *handle, int slot, int n, int naux_total, int q_begin, int q_count,
+                         const double *half);
+int mqcb200_whiten_push(void *handle, int slot, int nu_begin, int nu_count,
+                        const double *three_cols, long long ld_aux);
+int mqcb200_whiten_end(void *handle, int slot);
 /* Synthetic tensor generated on the device from a counter-based generator that
  * metalquicha_b200/synth.py reproduces bit-for-bit on the host (benchmarks at
  * sizes whose full-square host tensor does not fit in RAM). */
@@ -260,9 +291,11 @@ int mqcb200_last_gamma_fused(void *handle, int *fused);
 /* Stream time (ms, host gathers included) and PCIe bytes of the last mqcb200_set_tensor[_shard]:
  * only the lower triangles cross the bus, double-buffered ("timed separately"). */
 int mqcb200_last_set_tensor(void *handle, double *ms, double *h2d_bytes);
-/* Device time (ms) of the whitening GEMM of the last mqcb200_set_tensor_from_3c and its
- * flop count 2*naux^2*L ("timed separately", not part of builds/sec). */
+/* Device time (ms) of the whitening GEMM kernels of the last whitening (from_3c, build_df_tensor or
+ * begin/push/end on this rank) and their flop count 2*rows*naux*L ("timed separately", not part
+ * of builds/sec); device time and Jacobi sweeps of the last metric^(-1/2). */
 int mqcb200_last_whiten(void *handle, double *ms, double *flops);
+int mqcb200_last_metric(void *handle, double *ms, int *sweeps);
 
 #ifdef __cplusplus
 }

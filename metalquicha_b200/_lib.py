@@ -37,6 +37,12 @@ SIGNATURES = {
     "mqcb200_set_tensor": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "mqcb200_set_tensor_shard": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mqcb200_set_tensor_from_3c": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mqcb200_metric_inverse_sqrt": (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p, POINTER(c_int)]),
+    "mqcb200_build_df_tensor": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_void_p]),
+    "mqcb200_whiten_begin": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mqcb200_whiten_push": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_longlong]),
+    "mqcb200_whiten_end": (c_int, [c_void_p, c_int]),
+    "mqcb200_last_metric": (c_int, [c_void_p, _dp, POINTER(c_int)]),
     "mqcb200_synth_tensor": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint64, c_double]),
     "mqcb200_clear_tensor": (c_int, [c_void_p, c_int]),
     "mqcb200_tensor_bytes": (c_int, [c_void_p, c_int, POINTER(c_size_t)]),

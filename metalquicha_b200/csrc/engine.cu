@@ -169,6 +169,19 @@ struct Engine {
   DevBuf d_stage_lower[2];
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
   double whiten_ms = 0.0, whiten_flops = 0.0;
+  // slab-streamed whitening in progress (mqcb200_whiten_begin .. _end)
+  struct Whiten {
+    bool active = false;
+    int slot = 0, n = 0, naux = 0, m_rows = 0;
+    DevBuf d_af, d_slab, d_tp;
+    WhitenDst dst{};
+    void *mapped[WHITEN_MAX_RANKS] = {};
+    bool multi = false;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    double gemm_ms = 0.0, flops = 0.0;
+  } wh;
+  double metric_ms = 0.0;
+  int metric_sweeps = 0;
   double set_tensor_ms = 0.0, set_tensor_h2d_bytes = 0.0;   // last host -> packed upload (stream time incl. host gathers)
   bool last_fuse_attempted = false;
   int last_n = 0;    // shape of the operands of the last build_fock (for last_energy)
@@ -1337,6 +1350,218 @@ static void df_gradient_densities(Engine *e, const GradArgs &a) {
   release_all();
 }
 
+// ------------------------------- building the tensor on the device -------------------------
+// metric^(-1/2) = U s^(-1/2) U^T over the modes above `threshold` (metric_inverse_sqrt,
+// mqc_libcint_integrals.F90:992-1038) with the eigendecomposition on the GPU: one-sided Jacobi on the
+// columns of the symmetric metric (launch_hestenes_round), a sweep that rotates nothing ends it.
+// d_half_out (naux x naux, device) receives the result.
+static int metric_inverse_sqrt_device(Engine *e, int naux, const double *metric_host, double threshold, double *d_half_out) {
+  if (naux <= 0 || !metric_host) throw Failure("mqcb200: bad metric");
+  const size_t qq = (size_t)naux * naux;
+  DevBuf d_g, d_v, d_s, d_misc;
+  int kept = 0;
+  try {
+    d_g.ensure(qq * sizeof(double));
+    d_v.ensure(qq * sizeof(double));
+    d_s.ensure(qq * sizeof(double));
+    d_misc.ensure((size_t)naux * sizeof(double) + 64);
+    int *d_flag = reinterpret_cast<int *>(static_cast<char *>(d_misc.ptr) + (size_t)naux * sizeof(double));
+    int *d_kept = d_flag + 1;
+    cudaEvent_t t0, t1;
+    CUDA_CHECK(cudaEventCreate(&t0));
+    CUDA_CHECK(cudaEventCreate(&t1));
+    CUDA_CHECK(cudaMemcpyAsync(d_g.ptr, metric_host, qq * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(cudaEventRecord(t0, e->stream));
+    launch_set_identity(d_v.d(), naux, e->stream);
+    const int n_e = (naux + 1) & ~1;
+    int sweeps = 0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+      ++sweeps;
+      CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), e->stream));
+      for (int r = 0; r < n_e - 1; ++r) launch_hestenes_round(d_g.d(), d_v.d(), naux, r, d_flag, e->stream);
+      int rotated = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&rotated, d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      CUDA_CHECK(cudaGetLastError());
+      if (!rotated) break;
+    }
+    CUDA_CHECK(cudaMemsetAsync(d_kept, 0, sizeof(int), e->stream));
+    launch_metric_scale(d_g.d(), d_v.d(), naux, threshold, d_s.d(), static_cast<double *>(d_misc.ptr), d_kept, e->stream);
+    // half = scaled . U^T   (integrals.F90:1036)
+    launch_dgemm_batched(naux, naux, naux, 1.0, d_s.d(), naux, 0, false, d_v.d(), naux, 0, true, 0.0, d_half_out, naux, 0, 1,
+                         e->stream);
+    CUDA_CHECK(cudaEventRecord(t1, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&kept, d_kept, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    e->metric_ms = ms;
+    e->metric_sweeps = sweeps;
+  } catch (...) {
+    d_g.release(); d_v.release(); d_s.release(); d_misc.release();
+    throw;
+  }
+  d_g.release(); d_v.release(); d_s.release(); d_misc.release();
+  if (kept == 0) throw Failure("density fitting: the auxiliary metric is singular");      // integrals.F90:1015-1019
+  return kept;
+}
+
+static void whiten_abort(Engine *e) {
+  Engine::Whiten &w = e->wh;
+  if (w.multi) {
+    for (int k = 0; k < e->n_ranks; ++k)
+      if (k != e->rank && w.mapped[k] && !e->p2p.same_process[k]) cudaIpcCloseMemHandle(w.mapped[k]);
+  }
+  for (auto &m : w.mapped) m = nullptr;
+  w.d_af.release(); w.d_slab.release(); w.d_tp.release();
+  if (w.t0) cudaEventDestroy(w.t0);
+  if (w.t1) cudaEventDestroy(w.t1);
+  w.t0 = w.t1 = nullptr;
+  w.active = false;
+  w.multi = false;
+}
+
+// `half` is on the HOST unless half_on_device.  Collective when a communicator is active: every rank
+// calls it with its own [q_begin, q_begin + q_count).
+static void whiten_begin(Engine *e, int slot, int n, int naux_total, int q_begin, int q_count, const double *half,
+                         bool half_on_device) {
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  if (!half) throw Failure("mqcb200: null metric factor");
+  if (e->wh.active) throw Failure("mqcb200: a whitening is already in progress on this handle");
+  e->bind();
+  Engine::Whiten &w = e->wh;
+  TensorSlot &sl = e->slots[slot];
+  slot_prepare(e, sl, n, naux_total, q_begin, q_count);
+  const bool multi = e->comm && e->n_ranks > 1;
+  w.slot = slot; w.n = n; w.naux = naux_total; w.multi = multi;
+  w.m_rows = multi ? naux_total : q_count;              // a lone rank forms only the rows it keeps
+  w.gemm_ms = 0.0; w.flops = 0.0;
+  try {
+    CUDA_CHECK(cudaEventCreate(&w.t0));
+    CUDA_CHECK(cudaEventCreate(&w.t1));
+    w.d_af.ensure(std::max<size_t>(16, whiten_half_elems(w.m_rows, naux_total) * sizeof(double)));
+    DevBuf d_half;
+    const double *dh = half;
+    if (!half_on_device) {
+      d_half.ensure((size_t)naux_total * naux_total * sizeof(double));
+      CUDA_CHECK(cudaMemcpyAsync(d_half.ptr, half, (size_t)naux_total * naux_total * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+      dh = d_half.d();
+    }
+    if (w.m_rows > 0) launch_pack_half(dh, naux_total, multi ? 0 : q_begin, w.m_rows, w.d_af.d(), e->stream);
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    d_half.release();
+    w.dst = WhitenDst{};
+    w.dst.ld = sl.L;
+    w.dst.col_off = 0;
+    if (!multi) {
+      w.dst.n_ranks = 1;
+      w.dst.base[0] = sl.packed.d();
+      w.dst.q_begin[0] = 0;
+      w.dst.q_begin[1] = q_count;
+    } else {
+      if (e->n_ranks > WHITEN_MAX_RANKS) throw Failure("mqcb200: too many ranks for the peer-memory whitening");
+      // everyone learns everyone's slab boundaries and packed-tensor address
+      DevBuf sb, rb;
+      std::vector<int> all(2 * e->n_ranks, 0);
+      int mine[2] = {q_begin, q_count};
+      sb.ensure(sizeof(mine));
+      rb.ensure(sizeof(mine) * e->n_ranks);
+      CUDA_CHECK(cudaMemcpyAsync(sb.ptr, mine, sizeof(mine), cudaMemcpyHostToDevice, e->stream));
+      NCCL_CHECK(g_nccl.AllGather(sb.ptr, rb.ptr, sizeof(mine), kNcclChar, e->comm, e->stream));
+      CUDA_CHECK(cudaMemcpyAsync(all.data(), rb.ptr, sizeof(mine) * e->n_ranks, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      sb.release();
+      rb.release();
+      int expect = 0;
+      for (int k = 0; k < e->n_ranks; ++k) {
+        if (all[2 * k] != expect) throw Failure("mqcb200: the ranks' auxiliary slabs must be contiguous and in rank order");
+        w.dst.q_begin[k] = all[2 * k];
+        expect += all[2 * k + 1];
+      }
+      if (expect != naux_total) throw Failure("mqcb200: the ranks' auxiliary slabs do not cover the auxiliary range");
+      w.dst.q_begin[e->n_ranks] = naux_total;
+      w.dst.n_ranks = e->n_ranks;
+      const bool ok = p2p_exchange(e, sl.packed.ptr, w.mapped);
+      if (!ranks_agree(e, ok)) {
+        if (!ok) for (auto &m : w.mapped) m = nullptr;
+        throw Failure("mqcb200: a rank could not map its peers' packed tensors (peer access is required for the sharded whitening)");
+      }
+      for (int k = 0; k < e->n_ranks; ++k) w.dst.base[k] = static_cast<double *>(w.mapped[k]);
+    }
+    w.active = true;
+  } catch (...) {
+    whiten_abort(e);
+    throw;
+  }
+}
+
+// One nu-slab of (mu nu|P): `three_cols` points at (mu = 0, nu = nu_begin, P = 0) of the host tensor, the
+// auxiliary functions ld_aux doubles apart (n*n inside the full three(n*n, naux); n*nu_count for a compact slab).
+static void whiten_push(Engine *e, int slot, int nu_begin, int nu_count, const double *three_cols, long long ld_aux) {
+  Engine::Whiten &w = e->wh;
+  if (!w.active || w.slot != slot) throw Failure("mqcb200: no whitening in progress on this slot (call mqcb200_whiten_begin)");
+  const int n = w.n;
+  if (!three_cols || nu_begin < 0 || nu_count <= 0 || nu_begin + nu_count > n || (nu_begin % TILE) != 0 ||
+      ((nu_begin + nu_count) % TILE != 0 && nu_begin + nu_count != n) || ld_aux < (long long)n * nu_count)
+    throw Failure("mqcb200: a slab must cover whole 16-wide column tiles [nu_begin, nu_begin + nu_count) of the orbital index");
+  e->bind();
+  TensorSlot &sl = e->slots[slot];
+  const int nt = num_tiles(n);
+  const int tc0 = nu_begin / TILE, tc1 = (nu_begin + nu_count + TILE - 1) / TILE;
+  const long long tile0 = tile_index(tc0, tc0, nt);
+  const long long tile1 = tc1 >= nt ? num_lower_tiles(nt) : tile_index(tc1, tc1, nt);
+  const long long l_slab = (tile1 - tile0) * TILE_ELEMS;
+  const size_t slab_elems = (size_t)n * nu_count;
+  w.d_slab.ensure(slab_elems * w.naux * sizeof(double));
+  w.d_tp.ensure((size_t)l_slab * w.naux * sizeof(double));
+  CUDA_CHECK(cudaMemcpy2DAsync(w.d_slab.ptr, slab_elems * sizeof(double), three_cols, (size_t)ld_aux * sizeof(double),
+                               slab_elems * sizeof(double), (size_t)w.naux, cudaMemcpyHostToDevice, e->stream));
+  launch_pack_slab(w.d_slab.d(), n, w.naux, nu_begin, nu_count, w.d_tp.d(), e->stream);
+  if (w.m_rows > 0) {
+    WhitenDst d = w.dst;
+    d.col_off = tile0 * TILE_ELEMS;
+    CUDA_CHECK(cudaEventRecord(w.t0, e->stream));
+    launch_whiten_slab(w.d_af.d(), w.m_rows, w.naux, w.d_tp.d(), l_slab, l_slab, d, e->stream);
+    CUDA_CHECK(cudaEventRecord(w.t1, e->stream));
+  }
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));          // the caller may reuse its slab buffer; ours is reused too
+  if (w.m_rows > 0) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, w.t0, w.t1);
+    w.gemm_ms += ms;
+    w.flops += 2.0 * (double)w.m_rows * (double)w.naux * (double)l_slab;
+  }
+  (void)sl;
+}
+
+static void whiten_end(Engine *e, int slot) {
+  Engine::Whiten &w = e->wh;
+  if (!w.active || w.slot != slot) throw Failure("mqcb200: no whitening in progress on this slot");
+  e->bind();
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  bool ok = true;
+  if (w.multi) ok = ranks_agree(e, true);                // every rank's stores into my rows have landed
+  e->whiten_ms = w.gemm_ms;
+  e->whiten_flops = w.flops;
+  whiten_abort(e);                                       // releases the scratch and unmaps the peers
+  if (!ok) throw Failure("mqcb200: a rank failed during the sharded whitening");
+  e->slots[slot].set = true;
+}
+
+// Whole host tensor three(n*n, naux) through the slab path (single rank or sharded alike).
+static void whiten_all_from_host(Engine *e, int slot, int n, int naux, const double *three, int nu_lo, int nu_hi) {
+  // slabs of whole tile columns, at most ~512 MiB of staging each
+  const size_t per_col = (size_t)n * naux * sizeof(double) * TILE;
+  int cols_per = (int)std::max<size_t>(1, ((size_t)512 << 20) / std::max<size_t>(per_col, 1));
+  for (int nu0 = nu_lo; nu0 < nu_hi; nu0 += cols_per * TILE) {
+    const int cnt = std::min(cols_per * TILE, nu_hi - nu0);
+    whiten_push(e, slot, nu0, cnt, three + (size_t)nu0 * n, (long long)n * n);
+  }
+}
+
 // ------------------------------- fragment FIFO -------------------------------------------
 struct Fifo {
   uint32_t magic = 0x4D51F1F0u;
@@ -1434,6 +1659,7 @@ int mqcb200_destroy(void *handle) {
   API_BEGIN
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->wh.active) whiten_abort(e);
   if (e->comm) p2p_teardown(e);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto &sl : e->slots) sl.packed.release();
@@ -1518,53 +1744,99 @@ int mqcb200_set_tensor_shard(void *handle, int slot, int n, int naux_total, int 
 int mqcb200_set_tensor_from_3c(void *handle, int slot, int n, int naux, const double *three, const double *half) {
   GET_ENGINE(handle)
   API_BEGIN
-  if (slot < 0 || slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
   if (!three || !half) throw Failure("mqcb200: null three-centre tensor or metric factor");
-  e->bind();
-  // 1. pack (mu nu|P) exactly like a fitted tensor, into a scratch of the same size
-  DevBuf tp;
-  TensorSlot &sl = e->slots[slot];
-  slot_prepare(e, sl, n, naux, 0, naux);
+  if (e->comm && e->n_ranks > 1) throw Failure("mqcb200: with a communicator active use mqcb200_whiten_begin/push/end (every rank streams its slabs)");
+  whiten_begin(e, slot, n, naux, 0, naux, half, false);
   try {
-    tp.ensure((size_t)sl.L * (size_t)naux * sizeof(double));
-    stream_lower_slabs(e, three, n, (size_t)naux, (size_t)n * n, [&](const double *d_lower, size_t q0, size_t qc) {
-      launch_pack_tensor_lower(d_lower, n, (int)qc, tp.d() + q0 * (size_t)sl.L, e->stream);
-    });
-    // 2. metric^(-1/2) to the device, 3. Bp = half . Tp
-    DevBuf d_half, d_af;
-    try {
-      d_half.ensure((size_t)naux * naux * sizeof(double));
-      d_af.ensure(whiten_half_elems(naux) * sizeof(double));
-      CUDA_CHECK(cudaMemcpyAsync(d_half.ptr, half, (size_t)naux * naux * sizeof(double), cudaMemcpyHostToDevice,
-                                 e->stream));
-      cudaEvent_t w0, w1;
-      CUDA_CHECK(cudaEventCreate(&w0));
-      CUDA_CHECK(cudaEventCreate(&w1));
-      CUDA_CHECK(cudaEventRecord(w0, e->stream));
-      launch_whiten(d_half.d(), naux, tp.d(), n, d_af.d(), sl.packed.d(), e->stream);
-      CUDA_CHECK(cudaEventRecord(w1, e->stream));
-      CUDA_CHECK(cudaGetLastError());
-      CUDA_CHECK(cudaStreamSynchronize(e->stream));
-      float wms = 0.f;
-      cudaEventElapsedTime(&wms, w0, w1);
-      cudaEventDestroy(w0);
-      cudaEventDestroy(w1);
-      e->whiten_ms = wms;
-      e->whiten_flops = 2.0 * (double)naux * (double)naux * (double)sl.L;
-    } catch (...) {
-      d_half.release();
-      d_af.release();
-      throw;
-    }
-    d_half.release();
-    d_af.release();
+    whiten_all_from_host(e, slot, n, naux, three, 0, n);
   } catch (...) {
-    tp.release();
+    whiten_abort(e);
     throw;
   }
-  tp.release();
-  sl.set = true;
+  whiten_end(e, slot);
   API_END
+}
+
+int mqcb200_whiten_begin(void *handle, int slot, int n, int naux_total, int q_begin, int q_count, const double *half) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  whiten_begin(e, slot, n, naux_total, q_begin, q_count, half, false);
+  API_END
+}
+
+int mqcb200_whiten_push(void *handle, int slot, int nu_begin, int nu_count, const double *three_cols, long long ld_aux) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  try {
+    whiten_push(e, slot, nu_begin, nu_count, three_cols, ld_aux);
+  } catch (...) {
+    if (e->wh.active && !e->wh.multi) whiten_abort(e);
+    throw;
+  }
+  API_END
+}
+
+int mqcb200_whiten_end(void *handle, int slot) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  whiten_end(e, slot);
+  API_END
+}
+
+int mqcb200_metric_inverse_sqrt(void *handle, int naux, const double *metric, double null_threshold, double *half,
+                                int *n_kept) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!half) throw Failure("mqcb200: null output for the metric factor");
+  e->bind();
+  DevBuf d_half;
+  try {
+    d_half.ensure((size_t)naux * naux * sizeof(double));
+    const int kept = metric_inverse_sqrt_device(e, naux, metric, null_threshold, d_half.d());
+    CUDA_CHECK(cudaMemcpyAsync(half, d_half.ptr, (size_t)naux * naux * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (n_kept) *n_kept = kept;
+  } catch (...) {
+    d_half.release();
+    throw;
+  }
+  d_half.release();
+  API_END
+}
+
+int mqcb200_build_df_tensor(void *handle, int slot, int n, int naux, const double *three, const double *metric,
+                            double null_threshold, double *half_out) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  if (!three || !metric) throw Failure("mqcb200: null three-centre tensor or metric");
+  if (e->comm && e->n_ranks > 1) throw Failure("mqcb200: with a communicator active use mqcb200_metric_inverse_sqrt + mqcb200_whiten_begin/push/end");
+  e->bind();
+  DevBuf d_half;
+  try {
+    d_half.ensure((size_t)naux * naux * sizeof(double));
+    metric_inverse_sqrt_device(e, naux, metric, null_threshold, d_half.d());
+    if (half_out) CUDA_CHECK(cudaMemcpyAsync(half_out, d_half.ptr, (size_t)naux * naux * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    whiten_begin(e, slot, n, naux, 0, naux, d_half.d(), true);
+    try {
+      whiten_all_from_host(e, slot, n, naux, three, 0, n);
+    } catch (...) {
+      whiten_abort(e);
+      throw;
+    }
+    whiten_end(e, slot);
+  } catch (...) {
+    d_half.release();
+    throw;
+  }
+  d_half.release();
+  API_END
+}
+
+int mqcb200_last_metric(void *handle, double *ms, int *sweeps) {
+  GET_ENGINE(handle)
+  if (ms) *ms = e->metric_ms;
+  if (sweeps) *sweeps = e->metric_sweeps;
+  return MQCB200_OK;
 }
 
 int mqcb200_synth_tensor(void *handle, int slot, int n, int naux_total, int q_begin, int q_count, uint64_t seed,

@@ -41,10 +41,25 @@ void launch_combine_g(const double *d_j, const double *d_ka, const double *d_kb,
 void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n,
                    double *d_scratch, double *d_out, cudaStream_t s);
 
-// ---- whitening: Bp = half . Tp on the packed tensor (build_df_tensor's GEMM) ----
-size_t whiten_half_elems(int naux);   // doubles of the fragment-ordered copy of `half`
-void launch_whiten(const double *d_half, int naux, const double *d_tp, int n, double *d_af, double *d_bp,
-                   cudaStream_t s);
+// ---- whitening: Bp = half . Tp on the packed tensor (build_df_tensor's GEMM), slab by slab ----
+constexpr int WHITEN_MAX_RANKS = 8;
+struct WhitenDst {                      // where the rows of the whitened slab go: rank r owns rows [q_begin[r], q_begin[r+1])
+  double *base[WHITEN_MAX_RANKS];       // packed tensor of every rank (own entry included), device-addressable
+  int q_begin[WHITEN_MAX_RANKS + 1];
+  int n_ranks;
+  long long ld;                         // packed row length L
+  long long col_off;                    // first packed column of the slab
+};
+size_t whiten_half_elems(int m_rows, int naux);   // doubles of the fragment-ordered copy of m_rows rows of `half`
+void launch_pack_half(const double *d_half, int naux, int row0, int m_rows, double *d_af, cudaStream_t s);
+void launch_pack_slab(const double *d_slab, int n, int naux, int nu_begin, int nu_count, double *d_tp, cudaStream_t s);
+void launch_whiten_slab(const double *d_af, int m_rows, int naux, const double *d_tp, long long ld_tp, long long n_cols,
+                        const WhitenDst &dst, cudaStream_t s);
+// metric^(-1/2) pieces: one round of one-sided Jacobi on the columns of g (and v); identity; scaling by lambda^-1/2
+void launch_hestenes_round(double *d_g, double *d_v, int n, int round, int *d_rotated, cudaStream_t s);
+void launch_set_identity(double *d_v, int n, cudaStream_t s);
+void launch_metric_scale(const double *d_g, const double *d_v, int n, double threshold, double *d_scaled, double *d_lambda,
+                         int *d_n_kept, cudaStream_t s);
 
 // ---- cross-GPU sum of [J|K] over NVLink peer memory (sharded builds) ----------
 constexpr int XGPU_MAX_RANKS = 8;

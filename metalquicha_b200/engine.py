@@ -167,11 +167,66 @@ class B200FockEngine:
         self.n[slot] = n
         self.naux[slot] = (naux, 0, naux)
 
-    def build_df_tensor(self, three, metric, n: int, slot: int = SLOT_FULL_RANGE) -> None:
-        """Last two stages of ``build_df_tensor`` (integrals.F90:981-987): ``half =
-        metric^(-1/2)`` on the host as in the reference, ``b = three . half`` on the device,
-        written straight into the packed resident layout."""
-        self.set_tensor_from_3c(three, metric_inverse_sqrt(metric), n, slot=slot)
+    def build_df_tensor(self, three, metric, n: int, slot: int = SLOT_FULL_RANGE) -> np.ndarray:
+        """Last two stages of ``build_df_tensor`` (integrals.F90:981-987), both on the device:
+        ``half = metric^(-1/2)`` (one-sided Jacobi eigensolver + GEMM), ``b = three . half`` slab by
+        slab straight into the packed resident layout.  Returns ``half`` (the gradient needs it)."""
+        three = np.asfortranarray(_f64_colmajor(three, "three"))
+        metric = np.asfortranarray(_f64_colmajor(metric, "metric"))
+        naux = three.shape[1]
+        if three.shape[0] != n * n or metric.shape != (naux, naux):
+            raise ValueError("three must be (nao*nao, naux) and metric (naux, naux)")
+        half = np.empty((naux, naux), order="F")
+        _check(self._lib.mqcb200_build_df_tensor(self._h, slot, n, naux, _ptr(three), _ptr(metric),
+                                                 c_double(NULL_THRESHOLD), _ptr(half)))
+        self.n[slot] = n
+        self.naux[slot] = (naux, 0, naux)
+        return half
+
+    def metric_inverse_sqrt(self, metric) -> np.ndarray:
+        """``metric_inverse_sqrt`` (mqc_libcint_integrals.F90:992-1038) on the device; modes at or
+        below 1e-10 are zeroed, a metric with no surviving mode raises the reference's message."""
+        metric = np.asfortranarray(_f64_colmajor(metric, "metric"))
+        naux = metric.shape[0]
+        if metric.shape != (naux, naux):
+            raise ValueError("the metric is square")
+        half = np.empty((naux, naux), order="F")
+        kept = c_int(0)
+        _check(self._lib.mqcb200_metric_inverse_sqrt(self._h, naux, _ptr(metric), c_double(NULL_THRESHOLD), _ptr(half),
+                                                     byref(kept)))
+        self.last_metric_kept = kept.value
+        return half
+
+    def whiten_begin(self, n: int, naux_total: int, half, q_begin: int = 0, q_count: int | None = None,
+                     slot: int = SLOT_FULL_RANGE) -> None:
+        """Start a slab-streamed ``b = three . half`` into this rank's auxiliary slab (see mqcb200.h)."""
+        half = np.asfortranarray(_f64_colmajor(half, "half"))
+        if q_count is None:
+            q_count = naux_total - q_begin
+        _check(self._lib.mqcb200_whiten_begin(self._h, slot, n, naux_total, q_begin, q_count, _ptr(half)))
+        self._whiten = (slot, n, naux_total, q_begin, q_count)
+
+    def whiten_push(self, nu_begin: int, three_block, slot: int = SLOT_FULL_RANGE) -> None:
+        """``three_block`` is ``(nao*nu_count, naux_total)`` column-major: (mu nu|P) for nu in
+        ``[nu_begin, nu_begin + nu_count)``, all mu, all P."""
+        _, n, naux_total, _, _ = self._whiten
+        blk = np.asfortranarray(_f64_colmajor(three_block, "three_block"))
+        if blk.shape[1] != naux_total or blk.shape[0] % n:
+            raise ValueError("three_block must be (nao*nu_count, naux_total)")
+        _check(self._lib.mqcb200_whiten_push(self._h, slot, int(nu_begin), blk.shape[0] // n, _ptr(blk),
+                                             ctypes.c_longlong(blk.shape[0])))
+
+    def whiten_end(self, slot: int = SLOT_FULL_RANGE) -> None:
+        _check(self._lib.mqcb200_whiten_end(self._h, slot))
+        _, n, naux_total, q_begin, q_count = self._whiten
+        self.n[slot] = n
+        self.naux[slot] = (naux_total, q_begin, q_count)
+
+    def last_metric(self):
+        """``(ms, sweeps)`` of the last device metric^(-1/2)."""
+        ms, sw = c_double(0.0), c_int(0)
+        _check(self._lib.mqcb200_last_metric(self._h, byref(ms), byref(sw)))
+        return ms.value, sw.value
 
     def synth_tensor(self, n: int, naux_total: int, seed: int, scale: float,
                      q_begin: int = 0, q_count: int | None = None,
@@ -472,18 +527,14 @@ class B200FockEngine:
 NULL_THRESHOLD = 1.0e-10     # mqc_libcint_integrals.F90:1002
 
 
-def metric_inverse_sqrt(metric):
-    """J^(-1/2) = U s^(-1/2) U^T over the modes above 1e-10
-    (mqc_libcint_integrals.F90:992-1038).  Host-side like the reference (LAPACK dsyev
-    through pic_syev); eigenvalues at or below the threshold are zeroed, not errored;
-    a metric with no surviving mode raises the reference's message."""
-    metric = np.asarray(metric, dtype=np.float64)
-    values, vectors = np.linalg.eigh(metric, UPLO="U")
-    keep = values > NULL_THRESHOLD
-    if not np.any(keep):
-        raise B200Error(_lib.MQCB200_FAIL, "density fitting: the auxiliary metric is singular")
-    scaled = np.where(keep[None, :], vectors / np.sqrt(np.where(keep, values, 1.0))[None, :], 0.0)
-    return np.asfortranarray(scaled @ vectors.T)
+def metric_inverse_sqrt(metric, engine: "B200FockEngine | None" = None):
+    """J^(-1/2) = U s^(-1/2) U^T over the modes above 1e-10 (mqc_libcint_integrals.F90:992-1038),
+    formed ON THE DEVICE (``B200FockEngine.metric_inverse_sqrt``); without an engine a temporary
+    one is created on GPU 0.  No host eigensolver is involved."""
+    if engine is not None:
+        return engine.metric_inverse_sqrt(metric)
+    with B200FockEngine(0) as tmp:
+        return tmp.metric_inverse_sqrt(metric)
 
 
 def density_pseudo_orbitals(density):

@@ -41,8 +41,25 @@ sb.synth_tensor(n, naux, 77, synth.default_scale(n, naux))
 f3 = sb.build_fock_df(h, d, c, n_occ)
 ref3 = oracle.build_fock_df(h, synth.synth_tensor(77, n, naux), d, c, n_occ)
 err3 = float(np.max(np.abs(f3 - ref3)))
-ok = err <= 1e-10 and errjk <= 1e-10 and err3 <= 1e-10 and same and np.array_equal(f, f2)
-print(f"rank {rank}: err={err:.2e} errjk={errjk:.2e} err3={err3:.2e} same_across_ranks={same} repeat={np.array_equal(f, f2)}", flush=True)
+# sharded whitening: every rank streams ITS nu-blocks of (mu nu|P) for all auxiliary rows; the GEMM's
+# epilogue delivers each row to the rank that owns it over peer memory (all-to-all fused into the stores)
+nw, nauxw = 70, 93
+three, metric = synth.synth_physical_like_tensor(11, nw, nauxw, n_null=1)
+half = oracle.metric_inverse_sqrt(metric)
+bw = np.asfortranarray(three @ half)
+_, hw, dw, cw = synth.synth_problem(11, nw, 12, nauxw, with_tensor=False)
+q0, qc = synth.shard_range(nauxw, world, rank)
+eng.whiten_begin(nw, nauxw, half, q_begin=q0, q_count=qc)
+edges = list(range(0, nw, 16)) + [nw]
+three3 = three.reshape(nw, nw, nauxw, order="F")
+for i, (nu0, nu1) in enumerate(zip(edges[:-1], edges[1:])):
+    if i % world == rank:
+        eng.whiten_push(nu0, np.asfortranarray(three3[:, nu0:nu1, :].reshape(nw * (nu1 - nu0), nauxw, order="F")))
+eng.whiten_end()
+f4 = eng.build_fock_df(hw, dw, cw, 12)
+err4 = float(np.max(np.abs(f4 - oracle.build_fock_df(hw, bw, dw, cw, 12))))
+ok = err <= 1e-10 and errjk <= 1e-10 and err3 <= 1e-10 and err4 <= 1e-10 * max(1.0, float(np.max(np.abs(f4)))) and same and np.array_equal(f, f2)
+print(f"rank {rank}: err={err:.2e} errjk={errjk:.2e} err3={err3:.2e} whiten={err4:.2e} same_across_ranks={same} repeat={np.array_equal(f, f2)}", flush=True)
 eng.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

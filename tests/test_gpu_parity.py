@@ -225,8 +225,10 @@ def test_device_whitening_matches_reference_gemm(engine, n, naux, n_null):
     from metalquicha_b200.engine import metric_inverse_sqrt
     three, metric = synth.synth_physical_like_tensor(3, n, naux, n_null=n_null)
     half_ref = oracle.metric_inverse_sqrt(metric)
-    half = metric_inverse_sqrt(metric)
+    half = metric_inverse_sqrt(metric, engine)          # one-sided Jacobi + GEMM on the device
+    assert engine.last_metric_kept == naux - n_null
     assert _maxabs(half, half_ref) <= 1e-9 * max(1.0, float(np.max(np.abs(half_ref))))
+    assert _maxabs(half, half.T) <= 1e-12 * max(1.0, float(np.max(np.abs(half_ref))))
     b = np.asfortranarray(three @ half)              # the reference's whitening GEMM on these inputs
     n_occ = max(1, n // 5)
     _, h, density, coeff = synth.synth_problem(3, n, n_occ, naux, with_tensor=False)
@@ -237,8 +239,19 @@ def test_device_whitening_matches_reference_gemm(engine, n, naux, n_null):
     scale = max(1.0, float(np.max(np.abs(f_host))))
     assert _maxabs(f_dev, f_host) <= TOL * scale
     assert _maxabs(f_dev, oracle.build_fock_df(h, b, density, coeff, n_occ)) <= TOL * scale
-    engine.build_df_tensor(three, metric, n)          # host eigendecomposition + device GEMM
-    assert _maxabs(engine.build_fock_df(h, density, coeff, n_occ), f_host) <= TOL * scale
+    half2 = engine.build_df_tensor(three, metric, n)  # metric^(-1/2) AND the GEMM on the device, one call
+    assert _maxabs(half2, half_ref) <= 1e-9 * max(1.0, float(np.max(np.abs(half_ref))))
+    assert _maxabs(engine.build_fock_df(h, density, coeff, n_occ), f_host) <= 1e-9 * scale
+    # the same GEMM fed slab by slab by the caller, slabs in any order, full-tensor and compact blocks
+    engine.whiten_begin(n, naux, half)
+    edges = list(range(0, n, 16)) + [n]
+    blocks = list(zip(edges[:-1], edges[1:]))[::-1]
+    three3 = three.reshape(n, n, naux, order="F")               # (mu, nu, P)
+    for nu0, nu1 in blocks:
+        blk = np.asfortranarray(three3[:, nu0:nu1, :].reshape(n * (nu1 - nu0), naux, order="F"))
+        engine.whiten_push(nu0, blk)
+    engine.whiten_end()
+    assert np.array_equal(engine.build_fock_df(h, density, coeff, n_occ), f_dev)
 
 
 def test_response_operator_and_general_density_potential(engine):

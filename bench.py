@@ -606,6 +606,39 @@ def run_setup_timings(ctx, name):
                                  "pinned buffers, DMA + packing kernel of chunk k overlap the gather of chunk k+1"}
     eng.clear_tensor(1)
     del b_host
+    if 8.0 * n * n * naux > 16e9:
+        out["whiten"] = {"skipped": "the host-side stand-in for (mu nu|P) is sized for c2; run --workload c2 for this block"}
+        return out
+    # build_df_tensor's last two stages on the device: metric^(-1/2) (one-sided Jacobi + GEMM), then
+    # b = three . half streamed nu-slab by nu-slab (16 orbital columns per push, every push the same
+    # host block: the arithmetic does not care, the PCIe traffic is the real one)
+    u, _ = np.linalg.qr(rng.standard_normal((naux, naux)))
+    lam = np.exp(rng.uniform(-2.0, 2.0, size=naux))
+    metric = np.asfortranarray((u * lam[None, :]) @ u.T)
+    metric = np.asfortranarray(0.5 * (metric + metric.T))
+    t0 = time.perf_counter()
+    half = eng.metric_inverse_sqrt(metric)
+    wall_metric = time.perf_counter() - t0
+    m_ms, m_sweeps = eng.last_metric()
+    out["metric_inverse_sqrt"] = {"naux": naux, "device_ms": m_ms, "wall_ms": 1e3 * wall_metric, "jacobi_sweeps": m_sweeps,
+                                  "what": "mqcb200_metric_inverse_sqrt: one-sided Jacobi on the GPU + (U s^-1/2) U^T"}
+    block = np.asfortranarray(rng.standard_normal((n * 16, naux)))
+    eng.whiten_begin(n, naux, half, slot=1)
+    t0 = time.perf_counter()
+    nu = 0
+    while nu < n:
+        cnt = min(16, n - nu)
+        eng.whiten_push(nu, block[: n * cnt, :] if cnt < 16 else block, slot=1)
+        nu += cnt
+    eng.whiten_end(slot=1)
+    wall = time.perf_counter() - t0
+    w_ms, w_flops = eng.last_whiten()
+    out["whiten"] = {"gemm_ms": w_ms, "gemm_tflops": w_flops / w_ms * 1e-9 if w_ms > 0 else None,
+                     "flops": w_flops, "wall_ms_with_pcie": 1e3 * wall, "pcie_bytes": 8.0 * n * n * naux,
+                     "reference_flops_2_nao2_naux2": 2.0 * n * n * float(naux) ** 2,
+                     "what": "mqcb200_whiten_begin/push/end: b = three . half slab by slab into the packed layout "
+                             "(only the packed lower-triangular positions are formed: about half the reference's flops)"}
+    eng.clear_tensor(1)
     return out
 
 
@@ -701,6 +734,7 @@ def run_farm(ctx, primary):
     t_dev, builds_dev, _ = timed("d", k)
     for e in engines:
         e.close()
+    scf_block = run_farm_scf(ctx, frags, order, k)
     trimer = synth.CONFIGS["c3"]
     cpu_baseline = None
     if rank == 0 and world == 1 and primary and not args.no_cpu_baseline:
@@ -728,8 +762,102 @@ def run_farm(ctx, primary):
         "gpu_launches": int(launches_all),
         "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
                      "note": "79 MFLOP and 14 MB per trimer build: launch/latency-bound, see DESIGN.md"},
-        "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "cpu_baseline": cpu_baseline, "clocks": clocks, "device_resident_scf": scf_block,
     }
+
+
+def _synthetic_fragment(seed, n, naux, coupling=0.35):
+    """(S, H, b) of a fragment-sized synthetic SCF problem that converges like a closed-shell
+    molecule does: S = 1 + small symmetric, H with a ladder on the diagonal, b = coupling * synth."""
+    from metalquicha_b200 import synth
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((n, n)) * (0.15 / np.sqrt(n))
+    s = np.eye(n) + a + a.T
+    h = synth.synth_core_hamiltonian(seed, n) - 2.0 * np.diag(np.linspace(1.0, 0.0, n))
+    b = coupling * synth.synth_tensor(seed, n, naux)
+    return np.asfortranarray(s), np.asfortranarray(h), np.asfortranarray(b)
+
+
+def run_farm_scf(ctx, frags, order, k):
+    """The same 256-fragment batch with each fragment's WHOLE SCF on the GPU (mqcb200_scf_fragment:
+    tensor from a host bmat, then FARM_BUILDS_PER_FRAGMENT - 1 iterations of build + commutator + DIIS +
+    eigensolver + density on the device, and the final rebuild) -- against the same loop driven from the
+    host (engine Fock build through the C ABI + NumPy/LAPACK SCF step), one worker."""
+    torch, dist, args, world, rank, local_rank = ctx.torch, ctx.dist, ctx.args, ctx.world, ctx.rank, ctx.local_rank
+    from metalquicha_b200 import B200FockEngine, WorkQueue, farm, synth
+    n_workers = max(1, args.scf_workers_per_gpu)
+    iters = FARM_BUILDS_PER_FRAGMENT - 1
+    problems = {}
+    for nm in FARM_BATCH:
+        c = synth.CONFIGS[nm]
+        problems[nm] = (c,) + _synthetic_fragment(900 + c["n"], c["n"], c["naux"])
+    engines = [B200FockEngine(local_rank) for _ in range(n_workers)]
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
+    done = [0] * n_workers
+
+    def do_fragment(eng, widx, idx):
+        c, s_, h_, b_ = problems[frags[idx]]
+        eng.set_tensor(b_, n=c["n"])
+        r = eng.run_scf_fragment(h_, s_, 2 * c["n_occ"], max_iter=iters, energy_tol=0.0, density_tol=0.0)   # never "converges": fixed work
+        done[widx] += r["iterations"] + 1
+        return r["electronic"]
+
+    def run_step(step_id):
+        q = farm.DistributedWorkQueue(order, store, name=f"scf{step_id}", batch=args.farm_pop) if world > 1 else WorkQueue(order)
+        threads = [threading.Thread(target=farm.worker_loop, args=(q, lambda i, w=w: do_fragment(engines[w], w, i)))
+                   for w in range(n_workers)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    run_step("w")
+    done[:] = [0] * n_workers
+    barrier()
+    t0 = time.perf_counter()
+    for s_i in range(k):
+        run_step(f"s{s_i}")
+    torch.cuda.synchronize()
+    t_local = time.perf_counter() - t0
+    barrier()
+    tt = torch.tensor([t_local, float(sum(done))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_all, builds = float(tmax[0]), float(tsum[1])
+    else:
+        t_all, builds = float(tt[0]), float(tt[1])
+    out = {"builds_per_s": builds / t_all, "fragment_scfs_per_s": builds / FARM_BUILDS_PER_FRAGMENT / t_all,
+           "workers_per_gpu": n_workers, "iterations_per_fragment": iters,
+           "what": "every build here is followed ON THE GPU by the SCF step the reference does on the host "
+                   "(commutator, DIIS, eigensolver, density, convergence test); per iteration a few scalars cross PCIe"}
+    # host-driven baseline on rank 0: same fragments, same iteration count, one worker
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import scf_oracle as host_scf          # CPU-side baseline leg (NumPy/LAPACK SCF step)
+        eng = engines[0]
+        c, s_, h_, b_ = problems["c3"]
+
+        def fock_builder(hh, dd, cc, n_occ):
+            f = eng.build_fock_df(np.asfortranarray(hh), np.asfortranarray(dd), np.asfortranarray(cc), n_occ)
+            return f, eng.last_energy()
+        ts = []
+        for _ in range(4):
+            t1 = time.perf_counter()
+            eng.set_tensor(b_, n=c["n"])
+            host_scf.run_rhf(h_, s_, 2 * c["n_occ"], fock_builder, max_iter=iters, energy_tol=0.0, density_tol=0.0)
+            ts.append(time.perf_counter() - t1)
+        t1 = time.perf_counter()
+        eng.set_tensor(b_, n=c["n"])
+        eng.run_scf_fragment(h_, s_, 2 * c["n_occ"], max_iter=iters, energy_tol=0.0, density_tol=0.0)
+        t_dev_one = time.perf_counter() - t1
+        out["one_trimer_scf_ms"] = {"device_resident": 1e3 * t_dev_one, "host_driven": 1e3 * min(ts),
+                                    "note": "host-driven = mqcb200_build_fock per iteration + the NumPy/LAPACK SCF step "
+                                            "(oracle/scf_oracle.py, the restatement of run_libcint_rhf's loop), one thread"}
+    for e in engines:
+        e.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -748,6 +876,7 @@ def main():
     ap.add_argument("--k-scale", type=float, default=None)
     ap.add_argument("--workers-per-gpu", type=int, default=4, help="fragment farm: host workers (engine handles) per GPU")
     ap.add_argument("--farm-pop", type=int, default=4, help="fragment farm: ids taken per round trip to the shared queue")
+    ap.add_argument("--scf-workers-per-gpu", type=int, default=8, help="fragment farm, device-resident SCF mode: workers per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 

@@ -27,6 +27,10 @@ module mqc_b200_iface
    public :: mqcb200_last_energy
    public :: mqcb200_comm_unique_id, mqcb200_comm_init, mqcb200_comm_destroy
    public :: mqcb200_queue_create, mqcb200_queue_pop, mqcb200_queue_is_empty, mqcb200_queue_destroy
+   public :: mqcb200_tensor_shape, mqcb200_response_operator, mqcb200_fitted_potential_general
+   public :: mqcb200_scf_fragment, mqcb200_df_gradient_densities
+   public :: mqcb200_metric_inverse_sqrt, mqcb200_build_df_tensor
+   public :: mqcb200_whiten_begin, mqcb200_whiten_push, mqcb200_whiten_end
    public :: MQCB200_OK, MQCB200_FAIL, MQCB200_BAD_HANDLE
    public :: MQCB200_SLOT_FULL_RANGE, MQCB200_SLOT_ATTENUATED
 
@@ -188,6 +192,104 @@ module mqc_b200_iface
       function mqcb200_queue_destroy(queue) bind(C, name="mqcb200_queue_destroy") result(status)
          import :: c_int, c_ptr
          type(c_ptr), value :: queue
+         integer(c_int) :: status
+      end function
+      function mqcb200_tensor_shape(handle, slot, n, naux_total, q_begin, q_count) &
+         bind(C, name="mqcb200_tensor_shape") result(status)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot
+         integer(c_int), intent(out) :: n, naux_total, q_begin, q_count
+         integer(c_int) :: status
+      end function
+      function mqcb200_response_operator(handle, slot, x, ldx, c_occ, ldc, n_occ, dtilde, k_scale, g) &
+         bind(C, name="mqcb200_response_operator") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot, ldx, ldc, n_occ
+         real(c_double), intent(in) :: x(*), c_occ(*), dtilde(*)
+         real(c_double), value :: k_scale
+         real(c_double), intent(out) :: g(*)
+         integer(c_int) :: status
+      end function
+      function mqcb200_fitted_potential_general(handle, slot, dens, k_scale, g) &
+         bind(C, name="mqcb200_fitted_potential_general") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot
+         real(c_double), intent(in) :: dens(*)
+         real(c_double), value :: k_scale
+         real(c_double), intent(out) :: g(*)
+         integer(c_int) :: status
+      end function
+      function mqcb200_scf_fragment(handle, slot, hcore, overlap, n_electrons, guess, max_iter, energy_tol, &
+                                    density_tol, diis_vectors, k_scale, e_electronic, iterations, converged, &
+                                    n_mo, coeff, orbital_energies, density, e_history) &
+         bind(C, name="mqcb200_scf_fragment") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot, n_electrons, guess, max_iter, diis_vectors
+         real(c_double), intent(in) :: hcore(*), overlap(*)
+         real(c_double), value :: energy_tol, density_tol, k_scale
+         real(c_double), intent(out) :: e_electronic
+         integer(c_int), intent(out) :: iterations, converged, n_mo
+         real(c_double), intent(out) :: coeff(*), orbital_energies(*), density(*), e_history(*)
+         integer(c_int) :: status
+      end function
+      function mqcb200_df_gradient_densities(handle, slot, half, total_density, orbitals, lda, n_occupied, &
+                                             orbitals_beta, ldb, n_occupied_beta, unrestricted, exx_fraction, &
+                                             with_coulomb, gamma, omega) &
+         bind(C, name="mqcb200_df_gradient_densities") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot, lda, n_occupied, ldb, n_occupied_beta, unrestricted, with_coulomb
+         real(c_double), intent(in) :: half(*), total_density(*), orbitals(*), orbitals_beta(*)
+         real(c_double), value :: exx_fraction
+         real(c_double), intent(out) :: gamma(*), omega(*)
+         integer(c_int) :: status
+      end function
+      function mqcb200_metric_inverse_sqrt(handle, naux, metric, null_threshold, half, n_kept) &
+         bind(C, name="mqcb200_metric_inverse_sqrt") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         integer(c_int), value :: naux
+         real(c_double), intent(in) :: metric(*)
+         real(c_double), value :: null_threshold
+         real(c_double), intent(out) :: half(*)
+         integer(c_int), intent(out) :: n_kept
+         integer(c_int) :: status
+      end function
+      function mqcb200_build_df_tensor(handle, slot, n, naux, three, metric, null_threshold, half_out) &
+         bind(C, name="mqcb200_build_df_tensor") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot, n, naux
+         real(c_double), intent(in) :: three(*), metric(*)
+         real(c_double), value :: null_threshold
+         real(c_double), intent(out) :: half_out(*)
+         integer(c_int) :: status
+      end function
+      function mqcb200_whiten_begin(handle, slot, n, naux_total, q_begin, q_count, half) &
+         bind(C, name="mqcb200_whiten_begin") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot, n, naux_total, q_begin, q_count
+         real(c_double), intent(in) :: half(*)
+         integer(c_int) :: status
+      end function
+      function mqcb200_whiten_push(handle, slot, nu_begin, nu_count, three_cols, ld_aux) &
+         bind(C, name="mqcb200_whiten_push") result(status)
+         import :: c_int, c_ptr, c_double, c_int64_t
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot, nu_begin, nu_count
+         real(c_double), intent(in) :: three_cols(*)
+         integer(c_int64_t), value :: ld_aux
+         integer(c_int) :: status
+      end function
+      function mqcb200_whiten_end(handle, slot) bind(C, name="mqcb200_whiten_end") result(status)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot
          integer(c_int) :: status
       end function
    end interface

@@ -60,9 +60,11 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
   uint64_t *empty_bar = full_bar + Cfg::kStages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long total_rows = (long long)q_count * nt;        // flattened (Q, tile-row)
-  const long long n_groups = (total_rows + K_SLOTS - 1) / K_SLOTS;
-  const long long n_work = n_groups * n_ntiles;
+  // 32-bit throughout: q_count * nt fits easily (the launcher checks) and every 64-bit loop variable
+  // costs two of the 168 registers this kernel is launched with
+  const int total_rows = q_count * nt;                          // flattened (Q, tile-row)
+  const int n_groups = (total_rows + K_SLOTS - 1) / K_SLOTS;
+  const int n_work = n_groups * n_ntiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -79,13 +81,13 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
     // ===== TMA producer warp: lanes 0..7 own one slot each, lane 8 owns the C operand =====
     constexpr uint32_t stage_bytes = (uint32_t)(Cfg::kAElems + Cfg::kBElems) * sizeof(double);
     uint32_t it = 0;                                            // ring position, continuous over tiles
-    for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
-      const long long f0 = (work / n_ntiles) * K_SLOTS;
-      const int ib0 = (int)(work % n_ntiles) * (2 * NB);
+    for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+      const int f0 = (work / n_ntiles) * K_SLOTS;
+      const int ib0 = (work % n_ntiles) * (2 * NB);
       // slots past the end of the tensor re-load the last row; their results are not stored
-      long long f = f0 + lane;
+      int f = f0 + lane;
       if (f > total_rows - 1) f = total_rows - 1;
-      const int q = (int)(f / nt), tr = (int)(f % nt);
+      const int q = f / nt, tr = f % nt;
       const double *row = packed + (size_t)q * L;
       for (int kc = 0; kc < nt; ++kc, ++it) {
         const int st = it % Cfg::kStages;
@@ -144,20 +146,20 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
     load_frags(fa[0], fb[0], 0, 0, false, false);
   }
 
-  for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
-    const long long f0 = (work / n_ntiles) * K_SLOTS;
-    const int ib0 = (int)(work % n_ntiles) * (2 * NB);
-    const bool more_work = work + gridDim.x < n_work;
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+    const int f0 = (work / n_ntiles) * K_SLOTS;
+    const int ib0 = (work % n_ntiles) * (2 * NB);
+    const bool more_work = work + (int)gridDim.x < n_work;
     // the two 16-row slots of this warp
     int tr_s[2], q_s[2];
     bool ok_s[2];
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
-      long long f = f0 + 2 * wm + sl;
+      int f = f0 + 2 * wm + sl;
       ok_s[sl] = f < total_rows;
       if (!ok_s[sl]) f = total_rows - 1;
-      q_s[sl] = (int)(f / nt);
-      tr_s[sl] = (int)(f % nt);
+      q_s[sl] = f / nt;
+      tr_s[sl] = f % nt;
     }
 
     double acc[4][NB][2];
@@ -211,7 +213,7 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
     // its 16-row slot against the C fragments and writes one partial per (Q, tile-row,
     // N tile, N half); they are summed in fixed order by gamma_from_x_kernel.
     if (gamma_part != nullptr) {
-      const int ntile = (int)(work % n_ntiles);
+      const int ntile = work % n_ntiles;
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl) {
         double sum = 0.0;

@@ -167,8 +167,8 @@ def _workload_cfg(name):
 
 def _config(name, cfg, world, workers=None):
     if name == "c3":
-        return {"workload": "c3: (H2O)64 MBE-3 def2-SVP fragment farm, 256-fragment batch "
-                            "(1 monomer : 12 dimers : 243 trimers), 12 builds per fragment",
+        return {"workload": f"c3: (H2O)64 MBE-3 def2-SVP fragment farm, {256 * world}-fragment batch per step "
+                            "(1 monomer : 12 dimers : 243 trimers, 256 per GPU), 12 builds per fragment",
                 "n_ao": cfg["n"], "n_occ": cfg["n_occ"], "naux": cfg["naux"],
                 "parallelism": f"fragment FIFO over {world} GPU(s) x {workers} worker(s) per GPU, no collective",
                 "l2": "fragments are L2-resident by nature (7 MB packed); timed as dispatched, no flush",
@@ -658,9 +658,11 @@ def run_farm(ctx, primary):
     torch, dist, args, world, rank, local_rank = ctx.torch, ctx.dist, ctx.args, ctx.world, ctx.rank, ctx.local_rank
     from metalquicha_b200 import B200FockEngine, WorkQueue, farm, synth
 
+    # one batch per step and per GPU: a real MBE-3 run of (H2O)64 has 43 744 fragments, so the
+    # sample grows with the machine instead of starving 8 x 4 workers on 256 fragments
     frags = []
     for nm, count in FARM_BATCH.items():
-        frags += [nm] * count
+        frags += [nm] * (count * world)
     sizes = [synth.CONFIGS[f]["n"] for f in frags]
     order = farm.sort_fragments_largest_first(sizes)
     problems = {}
@@ -756,8 +758,8 @@ def run_farm(ctx, primary):
         "note": "value INCLUDES one mqcb200_set_tensor from a host bmat(n*n, naux) per fragment (lower triangles "
                 "over PCIe + packing); value_tensor_synthesised_on_device is round 1's figure (tensor generated on the GPU)",
         "e2e": {"value": value, "unit": "builds/s", "ms_per_step": 1e3 * t_all / k,
-                "h2d_bytes_per_step": (h2d_build * FARM_BUILDS_PER_FRAGMENT + 8 * tri * trimer["naux"]) * 256,
-                "d2h_bytes_per_step": 8 * trimer["n"] ** 2 * 256 * FARM_BUILDS_PER_FRAGMENT,
+                "h2d_bytes_per_step": (h2d_build * FARM_BUILDS_PER_FRAGMENT + 8 * tri * trimer["naux"]) * 256 * world,
+                "d2h_bytes_per_step": 8 * trimer["n"] ** 2 * 256 * FARM_BUILDS_PER_FRAGMENT * world,
                 "note": "every build goes through mqcb200_build_fock with host buffers"},
         "gpu_launches": int(launches_all),
         "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,

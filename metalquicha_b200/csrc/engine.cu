@@ -148,6 +148,10 @@ struct Engine {
   cudaStream_t j_stream = nullptr;      // the HBM-bound Coulomb kernels, concurrent with the tensor-bound exchange kernels
   cudaEvent_t ev_late_upload = nullptr, ev_fork = nullptr, ev_k1_done = nullptr, ev_j_done = nullptr;
   bool overlap_j = true;
+  // ... optionally with pass 2 as the 64-thread TMA-fed kernel that fits beside k_accumulate's three CTAs per SM.
+  // Measured (profiles/r02_notes.md): the 16 KiB it can keep in flight per SM stream only ~1.1 TB/s, so it
+  // outlasts the accumulation it hides behind (c2 7.95 ms vs 6.72 ms) -- off by default, MQCB200_CORESIDENT_J=1 to try.
+  bool coresident_j = false;
   TensorSlot slots[MQCB200_NUM_SLOTS];
   size_t workspace_limit = (size_t)4 << 30;
   size_t fuse_threshold = (size_t)32 << 20;  // below this a pass over B is cheaper than the extra launch of the fused route
@@ -892,6 +896,9 @@ static void build(Engine *e, const BuildArgs &a) {
       CUDA_CHECK(cudaStreamWaitEvent(js, e->ev_fork, 0));
       if (late_issued) CUDA_CHECK(cudaStreamWaitEvent(js, e->ev_late_upload, 0));
     }
+    // beside the exchange kernels pass 2 runs as the co-resident TMA-fed kernel; alone, as the wide one
+    // (same auxiliary slices, same order of the sums inside a slice: the two kernels give the same bits)
+    const bool j_beside_k = overlap && e->coresident_j;
     e->d_w.ensure((size_t)sl.L * sizeof(double));
     e->d_gamma_partial.ensure(jp.gamma_partial_elems * sizeof(double));
     e->d_gamma.ensure((size_t)sl.q_count * sizeof(double));
@@ -915,7 +922,10 @@ static void build(Engine *e, const BuildArgs &a) {
     }
     e->phase_end(T_J1, js);
     e->phase_begin(T_J2, js);
-    launch_j_accumulate(sl.packed.d(), sl.L, sl.q_count, e->d_gamma.d(), jp, e->d_jpart.d(), js);
+    if (j_beside_k)
+      launch_j_accumulate_tma(sl.packed.d(), sl.L, sl.q_count, e->d_gamma.d(), jp.n_slices, e->sm_count, e->d_jpart.d(), js);
+    else
+      launch_j_accumulate(sl.packed.d(), sl.L, sl.q_count, e->d_gamma.d(), jp, e->d_jpart.d(), js);
     e->phase_end(T_J2, js);
     e->launches += 1;
     if (overlap) {
@@ -1640,6 +1650,7 @@ int mqcb200_create(int device_rank, void **handle) {
     CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_k1_done, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_j_done, cudaEventDisableTiming));
     if (const char *env = getenv("MQCB200_OVERLAP_J")) e->overlap_j = !(env[0] == '0');
+    if (const char *env = getenv("MQCB200_CORESIDENT_J")) e->coresident_j = !(env[0] == '0');
     e->d_scalar.ensure(128);
     CUDA_CHECK(cudaMemsetAsync(e->d_scalar.ptr, 0, 128, e->stream));
     e->d_escratch.ensure(160 * sizeof(double));

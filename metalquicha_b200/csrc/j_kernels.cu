@@ -157,6 +157,118 @@ __global__ void __launch_bounds__(J_THREADS) j_accumulate_kernel(const double *_
   if (live) *reinterpret_cast<double2 *>(jpart + (size_t)slice * L + col) = make_double2(ax, ay);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pass 2 as a CO-RESIDENT streaming kernel: J accumulated beside the exchange accumulation.
+//
+// k_accumulate_kernel<64> holds three CTAs per SM and leaves exactly 4096 registers and ~27 KiB of
+// shared memory unused.  This kernel is shaped to fit in that gap -- 64 threads x 64 registers, a
+// 24 KiB ring -- so that one of its CTAs sits on every SM next to the three DMMA-bound ones and pulls
+// the packed tensor through the otherwise idle HBM interface.  With so few registers the loads
+// cannot be kept in flight by the threads; they are kept in flight by the TMA engine instead: thread 0
+// issues 2 KiB bulk copies (one row segment of 256 packed columns each, four rows per stage, three
+// stages) onto mbarriers, and the two warps fold each landed row into their four accumulators per
+// thread (Jp[col] += gamma_Q * Bp[Q][col]).  Persistent: the ring runs on across work items
+// (column block x auxiliary slice), partials go to jpart[slice][L] like the stand-alone kernel's.
+constexpr int JT_THREADS = 64;
+constexpr int JT_COLS = 256;                 // doubles per row segment: one 2 KiB bulk copy
+constexpr int JT_ROWS = 4;                   // rows per stage
+constexpr int JT_STAGES = 3;
+
+struct JtCursor {                            // position in the flattened (work item, row block) sequence
+  int item, r0, qa, qb;
+  long long col0;
+};
+
+__device__ __forceinline__ void jt_open(JtCursor &c, int item, int n_colblk, int n_slices, int q_count) {
+  c.item = item;
+  const int slice = item / n_colblk;
+  c.col0 = (long long)(item - slice * n_colblk) * JT_COLS;
+  c.qa = (int)((long long)slice * q_count / n_slices);
+  c.qb = (int)((long long)(slice + 1) * q_count / n_slices);
+  c.r0 = c.qa;
+}
+
+__global__ void __launch_bounds__(JT_THREADS, 16)
+j_accumulate_tma_kernel(const double *__restrict__ packed, long long L, int q_count, const double *__restrict__ gamma,
+                        int n_slices, int n_colblk, double *__restrict__ jpart) {
+  __shared__ __align__(128) double tile[JT_STAGES][JT_ROWS][JT_COLS];
+  __shared__ uint64_t full_bar[JT_STAGES], empty_bar[JT_STAGES];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n_items = n_colblk * n_slices;
+  if (tid == 0) {
+    for (int s = 0; s < JT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], JT_THREADS / 32); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if ((int)blockIdx.x >= n_items) return;
+
+  JtCursor prod, cons;
+  jt_open(prod, blockIdx.x, n_colblk, n_slices, q_count);
+  cons = prod;
+  bool prod_live = true;
+  uint32_t it_prod = 0, it_cons = 0;
+  auto produce = [&]() {                      // thread 0 only: one stage = up to JT_ROWS row segments
+    while (prod_live && prod.r0 >= prod.qb) { // (an empty slice has nothing to load)
+      const int next = prod.item + gridDim.x;
+      if (next >= n_items) { prod_live = false; break; }
+      jt_open(prod, next, n_colblk, n_slices, q_count);
+    }
+    if (!prod_live) return;
+    const int st = it_prod % JT_STAGES;
+    mbar_wait(&empty_bar[st], ((it_prod / JT_STAGES) & 1) ^ 1);
+    const int rows = prod.qb - prod.r0 < JT_ROWS ? prod.qb - prod.r0 : JT_ROWS;
+    mbar_arrive_expect_tx(&full_bar[st], (uint32_t)rows * JT_COLS * sizeof(double));
+    for (int r = 0; r < rows; ++r)
+      tma_load_1d(&tile[st][r][0], packed + (size_t)(prod.r0 + r) * L + prod.col0, JT_COLS * sizeof(double), &full_bar[st]);
+    prod.r0 += rows;
+    ++it_prod;
+  };
+  if (tid == 0)
+    for (int s = 0; s < JT_STAGES - 1; ++s) produce();
+
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  while (true) {
+    // skip empty slices on the consumer side too (their partial is zero)
+    while (cons.r0 >= cons.qb) {
+      *reinterpret_cast<double2 *>(jpart + (size_t)(cons.item / n_colblk) * L + cons.col0 + 4 * tid) = make_double2(acc[0], acc[1]);
+      *reinterpret_cast<double2 *>(jpart + (size_t)(cons.item / n_colblk) * L + cons.col0 + 4 * tid + 2) = make_double2(acc[2], acc[3]);
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+      const int next = cons.item + gridDim.x;
+      if (next >= n_items) return;
+      jt_open(cons, next, n_colblk, n_slices, q_count);
+    }
+    if (tid == 0) produce();                  // keep JT_STAGES - 1 stages in flight ahead of this one
+    const int st = it_cons % JT_STAGES;
+    const int rows = cons.qb - cons.r0 < JT_ROWS ? cons.qb - cons.r0 : JT_ROWS;
+    double g[JT_ROWS];
+#pragma unroll
+    for (int r = 0; r < JT_ROWS; ++r) g[r] = r < rows ? gamma[cons.r0 + r] : 0.0;
+    mbar_wait(&full_bar[st], (it_cons / JT_STAGES) & 1);
+#pragma unroll
+    for (int r = 0; r < JT_ROWS; ++r) {
+      if (r < rows) {
+        const double2 v0 = *reinterpret_cast<const double2 *>(&tile[st][r][4 * tid]);
+        const double2 v1 = *reinterpret_cast<const double2 *>(&tile[st][r][4 * tid + 2]);
+        acc[0] = fma(g[r], v0.x, acc[0]);
+        acc[1] = fma(g[r], v0.y, acc[1]);
+        acc[2] = fma(g[r], v1.x, acc[2]);
+        acc[3] = fma(g[r], v1.y, acc[3]);
+      }
+    }
+    release_stage(&empty_bar[st], lane);
+    cons.r0 += rows;
+    ++it_cons;
+  }
+}
+
+void launch_j_accumulate_tma(const double *d_packed, long long L, int q_count, const double *d_gamma, int n_slices,
+                             int sm_count, double *d_jpart, cudaStream_t s) {
+  const int n_colblk = (int)(L / JT_COLS);
+  const long long n_items = (long long)n_colblk * n_slices;
+  const unsigned grid = (unsigned)(n_items < sm_count ? n_items : sm_count);
+  j_accumulate_tma_kernel<<<grid, JT_THREADS, 0, s>>>(d_packed, L, q_count, d_gamma, n_slices, n_colblk, d_jpart);
+}
+
 JPlan plan_j(int n, int q_count) {
   JPlan p;
   const long long L = packed_row_len(n);

@@ -99,6 +99,11 @@ void launch_density_prep(const double *d_density, int n, double *d_w, const doub
                          int *d_flag, cudaStream_t s);
 void launch_j_accumulate(const double *d_packed, long long L, int q_count, const double *d_gamma,
                          const JPlan &plan, double *d_jpart, cudaStream_t s);
+// Pass 2 shaped to sit BESIDE k_accumulate_kernel on every SM (64 threads x 64 registers, 24 KiB ring fed by
+// bulk TMA): used when the Coulomb kernels run on their own stream next to the exchange kernels.
+// Partials: jpart[n_slices][L], the same slices and summation order as launch_j_accumulate (bit-identical).
+void launch_j_accumulate_tma(const double *d_packed, long long L, int q_count, const double *d_gamma, int n_slices,
+                             int sm_count, double *d_jpart, cudaStream_t s);
 
 // ---- fragment-sized problems: J and K in one pass over the tensor ---------------
 struct FragPlan {

@@ -38,9 +38,19 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ uint64_t policy_evict_first();
 __device__ __forceinline__ double2 ld_stream_f64x2(const double *p) {
   double2 v;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// Same with an L2 eviction-priority hint: the Coulomb kernels stream the tensor once and must not
+// push the exchange kernels' half-transformed panels out of L2 when the two run side by side.
+__device__ __forceinline__ double2 ld_stream_f64x2_hint(const double *p, uint64_t policy) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+               : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy));
   return v;
 }
 

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(J_THREADS) j_gamma_kernel(const double *__rest
   double acc[J_ROWS];
 #pragma unroll
   for (int r = 0; r < J_ROWS; ++r) acc[r] = 0.0;
+  const uint64_t pol = policy_evict_first();
 
   long long i = start + 2 * threadIdx.x;
   // two steps per trip: 16 independent 128-bit tensor loads in flight per thread
@@ -48,9 +49,9 @@ __global__ void __launch_bounds__(J_THREADS) j_gamma_kernel(const double *__rest
     const double2 w1 = *reinterpret_cast<const double2 *>(w + i + J_STEP);
     double2 v0[J_ROWS], v1[J_ROWS];
 #pragma unroll
-    for (int r = 0; r < J_ROWS; ++r) v0[r] = ld_stream_f64x2(row[r] + i);
+    for (int r = 0; r < J_ROWS; ++r) v0[r] = ld_stream_f64x2_hint(row[r] + i, pol);
 #pragma unroll
-    for (int r = 0; r < J_ROWS; ++r) v1[r] = ld_stream_f64x2(row[r] + i + J_STEP);
+    for (int r = 0; r < J_ROWS; ++r) v1[r] = ld_stream_f64x2_hint(row[r] + i + J_STEP, pol);
 #pragma unroll
     for (int r = 0; r < J_ROWS; ++r) {
       acc[r] = fma(v0[r].x, w0.x, acc[r]);
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(J_THREADS) j_gamma_kernel(const double *__rest
     const double2 w0 = *reinterpret_cast<const double2 *>(w + i);
     double2 v0[J_ROWS];
 #pragma unroll
-    for (int r = 0; r < J_ROWS; ++r) v0[r] = ld_stream_f64x2(row[r] + i);
+    for (int r = 0; r < J_ROWS; ++r) v0[r] = ld_stream_f64x2_hint(row[r] + i, pol);
 #pragma unroll
     for (int r = 0; r < J_ROWS; ++r) {
       acc[r] = fma(v0[r].x, w0.x, acc[r]);
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(J_THREADS) j_accumulate_kernel(const double *_
   const bool live = col < L;
   const double *base = packed + (live ? col : 0);
   double ax = 0.0, ay = 0.0;
+  const uint64_t pol = policy_evict_first();
 
   for (int qc = qa; qc < qb; qc += J2_QCHUNK) {
     const int cnt = qb - qc < J2_QCHUNK ? qb - qc : J2_QCHUNK;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(J_THREADS) j_accumulate_kernel(const double *_
       for (; t + 8 <= cnt; t += 8) {
         double2 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ld_stream_f64x2(base + (size_t)(qc + t + u) * L);
+        for (int u = 0; u < 8; ++u) v[u] = ld_stream_f64x2_hint(base + (size_t)(qc + t + u) * L, pol);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const double g = g_s[t + u];
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(J_THREADS) j_accumulate_kernel(const double *_
         }
       }
       for (; t < cnt; ++t) {
-        const double2 v = ld_stream_f64x2(base + (size_t)(qc + t) * L);
+        const double2 v = ld_stream_f64x2_hint(base + (size_t)(qc + t) * L, pol);
         const double g = g_s[t];
         ax = fma(g, v.x, ax);
         ay = fma(g, v.y, ay);
@@ -166,13 +168,13 @@ __global__ void __launch_bounds__(J_THREADS) j_accumulate_kernel(const double *_
 // the packed tensor through the otherwise idle HBM interface.  With so few registers the loads
 // cannot be kept in flight by the threads; they are kept in flight by the TMA engine instead: thread 0
 // issues 2 KiB bulk copies (one row segment of 256 packed columns each, four rows per stage, three
-// stages) onto mbarriers, and the two warps fold each landed row into their four accumulators per
+// stages, L2 evict-first) onto mbarriers, and the two warps fold each landed row into their four accumulators per
 // thread (Jp[col] += gamma_Q * Bp[Q][col]).  Persistent: the ring runs on across work items
 // (column block x auxiliary slice), partials go to jpart[slice][L] like the stand-alone kernel's.
 constexpr int JT_THREADS = 64;
 constexpr int JT_COLS = 256;                 // doubles per row segment: one 2 KiB bulk copy
 constexpr int JT_ROWS = 4;                   // rows per stage
-constexpr int JT_STAGES = 3;
+constexpr int JT_STAGES = 3;                 // (12 single-row stages measured worse: per-row barrier traffic, see r02_notes)
 
 struct JtCursor {                            // position in the flattened (work item, row block) sequence
   int item, r0, qa, qb;
@@ -202,6 +204,7 @@ j_accumulate_tma_kernel(const double *__restrict__ packed, long long L, int q_co
   __syncthreads();
   if ((int)blockIdx.x >= n_items) return;
 
+  const uint64_t pol = policy_evict_first();
   JtCursor prod, cons;
   jt_open(prod, blockIdx.x, n_colblk, n_slices, q_count);
   cons = prod;
@@ -219,7 +222,7 @@ j_accumulate_tma_kernel(const double *__restrict__ packed, long long L, int q_co
     const int rows = prod.qb - prod.r0 < JT_ROWS ? prod.qb - prod.r0 : JT_ROWS;
     mbar_arrive_expect_tx(&full_bar[st], (uint32_t)rows * JT_COLS * sizeof(double));
     for (int r = 0; r < rows; ++r)
-      tma_load_1d(&tile[st][r][0], packed + (size_t)(prod.r0 + r) * L + prod.col0, JT_COLS * sizeof(double), &full_bar[st]);
+      tma_load_1d_hint(&tile[st][r][0], packed + (size_t)(prod.r0 + r) * L + prod.col0, JT_COLS * sizeof(double), &full_bar[st], pol);
     prod.r0 += rows;
     ++it_prod;
   };

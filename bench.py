@@ -859,7 +859,89 @@ def run_farm_scf(ctx, frags, order, k):
                                             "(oracle/scf_oracle.py, the restatement of run_libcint_rhf's loop), one thread"}
     for e in engines:
         e.close()
+    out["batched"] = run_farm_scf_batched(ctx, problems, k)
     return out
+
+
+def run_farm_scf_batched(ctx, problems, k):
+    """The same batch once more with the fragments of one kind driven IN LOCK-STEP
+    (mqcb200_scf_fragment_batch): up to 32 fragments per call, their tensors back to back on the slot,
+    every kernel of an iteration launched once with the fragment index on a grid axis.  Two figures:
+    with every fragment's bmat coming from the host inside the timed region, and with the tensors
+    already resident (synthesised on the device) -- the SCF machinery alone."""
+    torch, dist, args, world, rank, local_rank = ctx.torch, ctx.dist, ctx.args, ctx.world, ctx.rank, ctx.local_rank
+    from metalquicha_b200 import B200FockEngine, WorkQueue, farm, synth
+    iters = FARM_BUILDS_PER_FRAGMENT - 1
+    bsz = max(1, args.scf_batch)
+    n_workers = max(1, args.scf_batch_workers_per_gpu)
+    batches = []                                            # (kind, fragments in the batch), largest kind first
+    reps = 4                                                # four 256-fragment samples per GPU and step: a few calls per worker
+    for nm in sorted(FARM_BATCH, key=lambda x: -synth.CONFIGS[x]["n"]):
+        left = FARM_BATCH[nm] * world * reps
+        while left > 0:
+            batches.append((nm, min(bsz, left)))
+            left -= min(bsz, left)
+    host_b = {nm: np.asfortranarray(np.hstack([problems[nm][3]] * min(bsz, FARM_BATCH[nm] * world * reps))) for nm in FARM_BATCH}
+    stacks = {nm: (np.stack([problems[nm][2]] * bsz), np.stack([problems[nm][1]] * bsz)) for nm in FARM_BATCH}
+    engines = [B200FockEngine(local_rank) for _ in range(n_workers)]
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
+    done = [0] * n_workers
+    mode = {"host_tensor": True}
+
+    def do_batch(eng, widx, idx):
+        nm, cnt = batches[idx]
+        c = problems[nm][0]
+        if mode["host_tensor"]:
+            eng.set_tensor(host_b[nm][:, :cnt * c["naux"]], n=c["n"])
+        else:
+            eng.synth_tensor(c["n"], cnt * c["naux"], SEED + idx, 0.35 * synth.default_scale(c["n"], c["naux"]))
+        h_all, s_all = stacks[nm]
+        r = eng.run_scf_fragment_batch(h_all[:cnt], s_all[:cnt], 2 * c["n_occ"], max_iter=iters, energy_tol=0.0,
+                                       density_tol=0.0, want_matrices=False, check_every=iters)
+        done[widx] += int(np.sum(r["iterations"] + 1))
+        return float(r["electronic"][0])
+
+    order = list(range(len(batches)))
+
+    def run_step(step_id):
+        q = farm.DistributedWorkQueue(order, store, name=f"scfb{step_id}", batch=1) if world > 1 else WorkQueue(order)
+        threads = [threading.Thread(target=farm.worker_loop, args=(q, lambda i, w=w: do_batch(engines[w], w, i)))
+                   for w in range(n_workers)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(tag):
+        run_step(tag + "w")
+        done[:] = [0] * n_workers
+        barrier()
+        t0 = time.perf_counter()
+        for s_i in range(k):
+            run_step(f"{tag}{s_i}")
+        torch.cuda.synchronize()
+        t_local = time.perf_counter() - t0
+        barrier()
+        tt = torch.tensor([t_local, float(sum(done))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            return float(tsum[1]) / float(tmax[0])
+        return float(tt[1]) / float(tt[0])
+    rate_host = timed("h")
+    mode["host_tensor"] = False
+    rate_resident = timed("r")
+    for e in engines:
+        e.close()
+    return {"builds_per_s": rate_host, "builds_per_s_tensors_resident": rate_resident,
+            "fragment_scfs_per_s": rate_host / FARM_BUILDS_PER_FRAGMENT, "fragments_per_call": bsz,
+            "workers_per_gpu": n_workers, "batches_per_step": len(batches),
+            "what": "mqcb200_scf_fragment_batch: fragments of one kind in lock-step, six launches per iteration whatever the "
+                    "batch size, one SCF-step CTA per fragment; builds_per_s includes each fragment's bmat coming from the host "
+                    "(7 MB of lower triangles per trimer over PCIe), builds_per_s_tensors_resident does not"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -879,6 +961,8 @@ def main():
     ap.add_argument("--workers-per-gpu", type=int, default=4, help="fragment farm: host workers (engine handles) per GPU")
     ap.add_argument("--farm-pop", type=int, default=4, help="fragment farm: ids taken per round trip to the shared queue")
     ap.add_argument("--scf-workers-per-gpu", type=int, default=8, help="fragment farm, device-resident SCF mode: workers per GPU")
+    ap.add_argument("--scf-batch", type=int, default=128, help="fragment farm, batched device SCF: fragments per call")
+    ap.add_argument("--scf-batch-workers-per-gpu", type=int, default=2, help="fragment farm, batched device SCF: workers per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 

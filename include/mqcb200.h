@@ -209,6 +209,23 @@ int mqcb200_scf_fragment(void *handle, int slot, const double *hcore, const doub
                          double *e_electronic, int *iterations, int *converged, int *n_mo,
                          double *coeff, double *orbital_energies, double *density,
                          double *e_history);
+/* The same for a BATCH of fragments of one kind, driven in lock-step: the slot holds n_fragments
+ * tensors of equal size back to back (set it with naux = n_fragments * naux_per_fragment: fragment f
+ * owns auxiliary slabs [f*naux_per_fragment, (f+1)*naux_per_fragment)), hcore_all / overlap_all are
+ * (n, n, n_fragments), and every kernel of an iteration runs once with the fragment index on a grid
+ * axis -- six launches per iteration whatever the batch size, one SCF-step CTA per fragment.  This is
+ * how an MBE run feeds the GPU: the fragments of one n-mer level share (n, naux, n_occ)
+ * (src/fragmentation/mbe: the work items the reference hands to its workers one at a time).
+ * Outputs are per fragment: e_electronic, iterations, converged (1 yes, 0 not within max_iter,
+ * -1 the overlap threshold left fewer orbitals than occupied), n_mo; coeff_all (n, n, n_fragments),
+ * orbital_energies_all (n, n_fragments) and density_all (n, n, n_fragments) may be NULL. */
+int mqcb200_scf_fragment_batch(void *handle, int slot, int n_fragments,
+                               const double *hcore_all, const double *overlap_all,
+                               int n_electrons, int guess, int max_iter,
+                               double energy_tol, double density_tol, int diis_vectors,
+                               double k_scale, double *e_electronic, int *iterations,
+                               int *converged, int *n_mo, double *coeff_all,
+                               double *orbital_energies_all, double *density_all);
 /* Iterations queued on the GPU between two looks at the convergence flag (default 1; queued
  * iterations after convergence are no-ops on the device). */
 int mqcb200_set_scf_check_every(void *handle, int iterations);

@@ -1224,6 +1224,132 @@ static void scf_fragment(Engine *e, const ScfArgs &a) {
   if (a.n_mo) *a.n_mo = n_mo;
 }
 
+// ------------------------------- a batch of fragment SCFs, in lock-step ----------------------
+// MBE fragments of one kind (all trimers of a water cluster, say) have the same (n, naux, n_occ).
+// `n_frag` of them are driven together: their tensors sit back to back on the slot (fragment f owns
+// auxiliary slabs [f*naux, (f+1)*naux) of a tensor set with naux_total = n_frag*naux), and every
+// kernel of an iteration -- pack D, pack C, one-pass J/K, finalize+assemble, energy, SCF step -- is
+// launched ONCE with the fragment index on a grid axis.  Six launches per iteration whatever the
+// batch size; a fragment that has converged idles through the remaining iterations of its batch.
+struct ScfBatchArgs {
+  int slot = 0, n_frag = 0;
+  const double *h = nullptr, *s = nullptr;            // (n, n, n_frag) each
+  int n_electrons = 0, guess = 1, max_iter = 100, diis_vectors = 8;
+  double energy_tol = 1e-10, density_tol = 1e-8, k_scale = 1.0;
+  double *e_electronic = nullptr;                       // [n_frag]
+  int *iterations = nullptr, *converged = nullptr, *n_mo = nullptr;   // [n_frag]
+  double *coeff = nullptr, *eps = nullptr, *density = nullptr;        // (n, n, n_frag), (n, n_frag), (n, n, n_frag); nullable
+};
+
+static void scf_fragment_batch(Engine *e, const ScfBatchArgs &a) {
+  if (a.slot < 0 || a.slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  TensorSlot &sl = e->slots[a.slot];
+  if (!sl.set) throw Failure("mqcb200: no fitted tensor has been set on this slot (call mqcb200_set_tensor first)");
+  if (!a.h || !a.s || !a.e_electronic || !a.iterations || !a.converged) throw Failure("mqcb200: null argument to scf_fragment_batch");
+  if (e->comm && e->n_ranks > 1) throw Failure("mqcb200: the device-resident SCF runs whole fragments on one GPU, not a sharded tensor");
+  if (a.n_frag < 1 || sl.q_count != sl.naux_total || sl.q_count % a.n_frag != 0)
+    throw Failure("mqcb200: the slot must hold n_fragments tensors of equal size back to back (naux_total = n_fragments * naux)");
+  const int n = sl.n, nf = a.n_frag, naux = sl.q_count / nf;
+  if (a.n_electrons < 0 || (a.n_electrons & 1)) throw Failure("mqcb200: closed-shell SCF needs an even, non-negative electron count");
+  const int n_occ = a.n_electrons / 2;
+  if (!scf_path_applies(n) || !fragment_path_applies(n, std::max(n_occ, 1)))
+    throw Failure("mqcb200: the device-resident SCF step covers fragment-sized problems (n <= 80, n_occ <= 64)");
+  if (a.diis_vectors < 0 || a.diis_vectors > 8) throw Failure("mqcb200: diis_vectors must lie in 0..8");
+  if (a.max_iter < 1) throw Failure("mqcb200: max_iter must be positive");
+  e->bind();
+  e->launches = 0;
+  const size_t nn = (size_t)n * n;
+  const int dmax = a.diis_vectors;
+  size_t off = 0;
+  auto take = [&](size_t count) { const size_t o = off; off += (count + 1) & ~(size_t)1; return o; };
+  const size_t o_h = take(nn), o_s = take(nn), o_x = take(nn), o_f = take(nn), o_d = take(nn), o_c = take(nn);
+  const size_t o_j = take(nn), o_k = take(nn), o_eps = take(n), o_work = take(4 * nn);
+  const size_t o_df = take((size_t)std::max(dmax, 1) * nn), o_de = take((size_t)std::max(dmax, 1) * nn), o_db = take(64);
+  const size_t o_scal = take(24), o_state = take(4), o_nmo = take(2);
+  const size_t blk = off;                                  // doubles per fragment
+  const bool wk = a.k_scale != 0.0 && n_occ > 0;
+  // a few CTAs per fragment are enough once there are many fragments
+  FragPlan fp = plan_fragment(n, std::max(n_occ, 1), naux, std::max(4, 3 * e->sm_count / nf));
+  const size_t ctf_stride = (size_t)fp.nt * fp.nib * 128;
+  DevBuf d_esc;
+  cudaStream_t st = e->stream;
+  std::vector<int> states((size_t)4 * nf, 0), nmos(nf, 0);
+  try {
+    e->d_scf.ensure(blk * nf * sizeof(double));
+    d_esc.ensure((size_t)130 * nf * sizeof(double));
+    e->d_w.ensure((size_t)sl.L * nf * sizeof(double));
+    e->d_jpart.ensure(fp.jpart_elems * nf * sizeof(double));
+    if (wk) {
+      e->d_ctf.ensure(ctf_stride * nf * sizeof(double));
+      e->d_kpart.ensure(fp.kpart_elems * nf * sizeof(double));
+    }
+    double *base = e->d_scf.d();
+    CUDA_CHECK(cudaMemsetAsync(base, 0, blk * nf * sizeof(double), st));
+    CUDA_CHECK(cudaMemsetAsync(d_esc.ptr, 0, (size_t)130 * nf * sizeof(double), st));
+    CUDA_CHECK(cudaMemcpy2DAsync(base + o_h, blk * sizeof(double), a.h, nn * sizeof(double), nn * sizeof(double), nf, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpy2DAsync(base + o_s, blk * sizeof(double), a.s, nn * sizeof(double), nn * sizeof(double), nf, cudaMemcpyHostToDevice, st));
+    int *d_state = reinterpret_cast<int *>(base + o_state), *d_nmo = reinterpret_cast<int *>(base + o_nmo);
+    launch_scf_orthogonalizer(base + o_s, n, base + o_x, d_nmo, st, nf, blk);
+    ScfStepLaunch sp{};
+    sp.batch = nf; sp.block_stride = blk; sp.n_mo_dev = d_nmo;
+    sp.n = n; sp.n_mo = n; sp.n_occ = n_occ; sp.diis_max = dmax; sp.guess = a.guess;
+    sp.h = base + o_h; sp.s = base + o_s; sp.x = base + o_x; sp.fock = base + o_f; sp.density = base + o_d;
+    sp.coeff = base + o_c; sp.eps = base + o_eps; sp.work = base + o_work; sp.diis_f = base + o_df; sp.diis_e = base + o_de;
+    sp.diis_b = base + o_db; sp.state = d_state; sp.scalars = base + o_scal;
+    sp.energy_tol = a.energy_tol; sp.density_tol = a.density_tol;
+    sp.mode = 0;
+    launch_scf_step(sp, st);
+    sp.mode = 1;
+    e->launches += 2;
+    auto fock_build = [&]() {
+      launch_pack_density(base + o_d, n, e->d_w.d(), nullptr, st, nf, blk, (size_t)sl.L);
+      if (wk) launch_pack_coeff(base + o_c, n, n, n_occ, fp.nib, e->d_ctf.d(), nullptr, st, nf, blk, ctf_stride);
+      launch_fragment_jk(sl.packed.d(), naux, e->d_w.d(), e->d_ctf.d(), fp, true, wk, e->d_jpart.d(), e->d_kpart.d(), st, nf);
+      launch_finalize_jk(e->d_jpart.d(), fp.grid, wk ? e->d_kpart.d() : nullptr, fp.grid, 64, n, 2.0, base + o_j,
+                         wk ? base + o_k : nullptr, st, base + o_h, 1.0, 0.5 * a.k_scale, base + o_f, -1, nf, fp.jpart_elems,
+                         fp.kpart_elems, blk);
+      launch_energy(base + o_d, base + o_h, base + o_f, n, d_esc.d(), base + o_scal, st, nf, blk, blk);
+      e->launches += wk ? 5 : 4;
+    };
+    const int every = std::max(1, e->scf_check_every);
+    int done_iters = 0;
+    bool all_done = false;
+    while (done_iters < a.max_iter && !all_done) {
+      const int batch_it = std::min(every, a.max_iter - done_iters);
+      for (int b = 0; b < batch_it; ++b) {
+        fock_build();
+        launch_scf_step(sp, st);
+        e->launches += 1;
+      }
+      done_iters += batch_it;
+      CUDA_CHECK(cudaMemcpy2DAsync(states.data(), 4 * sizeof(int), d_state, blk * sizeof(double), 4 * sizeof(int), nf,
+                                   cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      all_done = true;
+      for (int f = 0; f < nf; ++f) all_done = all_done && states[4 * f + 3] != 0;
+    }
+    fock_build();                                          // the final rebuild (rhf.f90:646-649), every fragment
+    CUDA_CHECK(cudaMemcpy2DAsync(a.e_electronic, sizeof(double), base + o_scal, blk * sizeof(double), sizeof(double), nf,
+                                 cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpy2DAsync(nmos.data(), sizeof(int), d_nmo, blk * sizeof(double), sizeof(int), nf, cudaMemcpyDeviceToHost, st));
+    if (a.coeff) CUDA_CHECK(cudaMemcpy2DAsync(a.coeff, nn * sizeof(double), base + o_c, blk * sizeof(double), nn * sizeof(double), nf, cudaMemcpyDeviceToHost, st));
+    if (a.eps) CUDA_CHECK(cudaMemcpy2DAsync(a.eps, (size_t)n * sizeof(double), base + o_eps, blk * sizeof(double), (size_t)n * sizeof(double), nf, cudaMemcpyDeviceToHost, st));
+    if (a.density) CUDA_CHECK(cudaMemcpy2DAsync(a.density, nn * sizeof(double), base + o_d, blk * sizeof(double), nn * sizeof(double), nf, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  } catch (...) {
+    d_esc.release();
+    throw;
+  }
+  d_esc.release();
+  for (int f = 0; f < nf; ++f) {
+    a.iterations[f] = states[4 * f + 2];
+    a.converged[f] = states[4 * f + 3];                    // 1 converged, 0 not within max_iter, -1 basis collapsed below n_occ
+    if (nmos[f] <= 0 || n_occ > nmos[f]) a.converged[f] = -1;
+    if (a.n_mo) a.n_mo[f] = nmos[f];
+  }
+}
+
 // ------------------------------- DF gradient densities -------------------------------------
 // The two densities every term of the density-fitted two-electron gradient is contracted with
 // (df_two_electron_gradient + add_exchange_channel, backends/libcint/mqc_libcint_gradient.f90:
@@ -2051,6 +2177,21 @@ int mqcb200_df_gradient_densities(void *handle, int slot, const double *half, co
   a.cb = orbitals_beta; a.ldb = ldb; a.n_b = n_occupied_beta; a.unrestricted = unrestricted != 0;
   a.kf = exx_fraction; a.with_coulomb = with_coulomb != 0; a.gamma = gamma; a.omega = omega;
   df_gradient_densities(e, a);
+  API_END
+}
+
+int mqcb200_scf_fragment_batch(void *handle, int slot, int n_fragments, const double *hcore_all, const double *overlap_all,
+                               int n_electrons, int guess, int max_iter, double energy_tol, double density_tol,
+                               int diis_vectors, double k_scale, double *e_electronic, int *iterations, int *converged,
+                               int *n_mo, double *coeff_all, double *orbital_energies_all, double *density_all) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  ScfBatchArgs a;
+  a.slot = slot; a.n_frag = n_fragments; a.h = hcore_all; a.s = overlap_all; a.n_electrons = n_electrons; a.guess = guess;
+  a.max_iter = max_iter; a.energy_tol = energy_tol; a.density_tol = density_tol; a.diis_vectors = diis_vectors; a.k_scale = k_scale;
+  a.e_electronic = e_electronic; a.iterations = iterations; a.converged = converged; a.n_mo = n_mo;
+  a.coeff = coeff_all; a.eps = orbital_energies_all; a.density = density_all;
+  scf_fragment_batch(e, a);
   API_END
 }
 

@@ -49,6 +49,14 @@ fragment_jk_kernel(const double *__restrict__ packed, int L, int q_count,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int G = gridDim.x;
+  if (blockIdx.y != 0) {                     // fragment of a batch: its own slabs, weights, coefficients and partials
+    const int np_b = (16 * NT + 63) / 64;
+    packed += (size_t)blockIdx.y * (size_t)q_count * L;
+    w += (size_t)blockIdx.y * L;
+    ctf += (size_t)blockIdx.y * NT * nib * 128;
+    jpart += (size_t)blockIdx.y * (size_t)G * L;
+    kpart += (size_t)blockIdx.y * (size_t)G * (np_b * (np_b + 1) / 2) * 4096;
+  }
   const int my_count = (q_count - (int)blockIdx.x + G - 1) / G;  // auxiliary functions of this CTA
 
   if (tid == 0) {
@@ -259,11 +267,11 @@ FragPlan plan_fragment(int n, int n_occ, int q_count, int sm_count) {
 
 void launch_fragment_jk(const double *d_packed, int q_count, const double *d_w, const double *d_ctf,
                         const FragPlan &p, bool want_j, bool want_k, double *d_jpart, double *d_kpart,
-                        cudaStream_t s) {
+                        cudaStream_t s, int batch) {
   // only the lower-triangular 8x8 blocks of the K partial tiles are written -- exactly the
   // elements finalize_jk_kernel reads (row >= col), so no clearing is needed
 #define MQCB200_LAUNCH_FRAG(NT_)                                                                              \
-  fragment_jk_kernel<NT_><<<p.grid, FR_THREADS, p.smem_bytes, s>>>(d_packed, p.L, q_count, d_w, d_ctf, p.nib, \
+  fragment_jk_kernel<NT_><<<dim3((unsigned)p.grid, (unsigned)batch), FR_THREADS, p.smem_bytes, s>>>(d_packed, p.L, q_count, d_w, d_ctf, p.nib, \
                                                                    want_j ? 1 : 0, want_k ? 1 : 0, d_jpart, d_kpart)
   switch (p.nt) {
     case 1: MQCB200_LAUNCH_FRAG(1); break;

@@ -17,11 +17,13 @@ void launch_pack_tensor_lower(const double *d_lower, int n, int q_count, double 
 void launch_synth_tensor(double *d_packed, int n, int q_global_begin, int q_count, uint64_t seed,
                          double scale, cudaStream_t s);
 // w[L]: the density in packed order with the off-diagonal weight folded in.
-void launch_pack_density(const double *d_density, int n, double *d_w, const int *d_skip_flag, cudaStream_t s);
+// (batch > 1: blockIdx.y walks the fragments of a batch, every operand moving on by its stride -- doubles)
+void launch_pack_density(const double *d_density, int n, double *d_w, const int *d_skip_flag, cudaStream_t s, int batch = 1,
+                         size_t d_stride = 0, size_t w_stride = 0);
 // C(n x n_occ, ld) -> fragment-ordered, zero-padded [nt][nib][4][32] operand.
 // d_cep (nullable): the same coefficients in accumulator order, for the Coulomb-vector epilogue.
 void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib, double *d_ctf, double *d_cep,
-                       cudaStream_t s);
+                       cudaStream_t s, int batch = 1, size_t coeff_stride = 0, size_t ctf_stride = 0);
 // Sum the J / K partial buffers in fixed order and unpack to full n x n matrices.
 // Either output may be null.  k_factor multiplies K (2 for RHF, 1 per spin).
 // With d_fock non-null the Fock matrix F = H + jf*J - kf*K is assembled in the same pass.
@@ -29,7 +31,8 @@ void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib
 void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits,
                         int ktile, int n, double k_factor, double *d_j, double *d_k, cudaStream_t s,
                         const double *d_h = nullptr, double jf = 0.0, double kf = 0.0, double *d_fock = nullptr,
-                        int n_ksplits_diag = -1);
+                        int n_ksplits_diag = -1, int batch = 1, size_t jpart_stride = 0, size_t kpart_stride = 0,
+                        size_t out_stride = 0);
 // F = H + jf*J - kf*K  (any of J/K may be null == zero).
 void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf,
                           int n, double *d_fock, cudaStream_t s);
@@ -39,7 +42,8 @@ void launch_combine_g(const double *d_j, const double *d_ka, const double *d_kb,
 // e = 1/2 sum D (H + F) into d_out[0]; fixed-order two-level reduction.  d_scratch: 129 doubles,
 // zero-initialised once (the kernel leaves its counter at zero).
 void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n,
-                   double *d_scratch, double *d_out, cudaStream_t s);
+                   double *d_scratch, double *d_out, cudaStream_t s, int batch = 1, size_t mat_stride = 0,
+                   size_t out_stride = 0);   // batch > 1: d_scratch holds 130 doubles per fragment
 
 // ---- whitening: Bp = half . Tp on the packed tensor (build_df_tensor's GEMM), slab by slab ----
 constexpr int WHITEN_MAX_RANKS = 8;
@@ -116,7 +120,7 @@ FragPlan plan_fragment(int n, int n_occ, int q_count, int sm_count);
 // kpart [grid][n_ktiles][64*64] -- the layouts launch_finalize_jk sums (ktile = 64).
 void launch_fragment_jk(const double *d_packed, int q_count, const double *d_w, const double *d_ctf,
                         const FragPlan &p, bool want_j, bool want_k, double *d_jpart, double *d_kpart,
-                        cudaStream_t s);
+                        cudaStream_t s, int batch = 1);   // batch > 1: fragment f owns slabs [f*q_count, (f+1)*q_count), w/ctf/partials contiguous per fragment
 
 // ---- general strided-batched FP64 GEMM on DMMA + helpers of the gradient densities (gemm_kernels.cu)
 // C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b]; column-major, op(A) is M x K, op(B) is K x N.
@@ -131,6 +135,9 @@ void launch_gradient_gamma(const double *d_rho, const double *d_density, const d
 
 // ---- device-resident SCF step for fragment-sized problems (scf_kernels.cu) ---------------
 struct ScfStepLaunch {
+  int batch = 1;                 // fragments: one CTA each, every pointer below moving on by block_stride doubles
+  size_t block_stride = 0;
+  const int *n_mo_dev = nullptr; // batch: orbitals surviving the overlap threshold, per fragment (stride block_stride ints*2)
   int n, n_mo, n_occ, diis_max, mode /*0 guess, 1 iteration*/, guess /*0 core, 1 GWH*/;
   const double *h, *s, *x;
   double *fock, *density, *coeff, *eps, *work, *diis_f, *diis_e, *diis_b;
@@ -141,7 +148,8 @@ struct ScfStepLaunch {
 bool scf_path_applies(int n);                       // n <= 80
 void configure_scf_kernels();
 // x (n x n_mo) = U s^-1/2 over the eigenvalues of S above 1e-7; *d_n_mo = surviving orbitals.
-void launch_scf_orthogonalizer(const double *d_s, int n, double *d_x, int *d_n_mo, cudaStream_t s);
+void launch_scf_orthogonalizer(const double *d_s, int n, double *d_x, int *d_n_mo, cudaStream_t s, int batch = 1,
+                               size_t block_stride = 0);
 void launch_scf_step(const ScfStepLaunch &a, cudaStream_t s);
 
 // ---- K: half-transform + symmetric accumulation on the FP64 tensor pipe -----

@@ -76,8 +76,11 @@ __global__ void __launch_bounds__(256) synth_tensor_kernel(double *__restrict__ 
 
 __global__ void __launch_bounds__(256) pack_density_kernel(const double *__restrict__ d, int n, int nt,
                                                            double *__restrict__ w,
-                                                           const int *__restrict__ skip_flag) {
+                                                           const int *__restrict__ skip_flag, size_t d_stride,
+                                                           size_t w_stride) {
   if (skip_flag != nullptr && *skip_flag != 0) return;
+  d += (size_t)blockIdx.y * d_stride;               // blockIdx.y: fragment of a batch (strides 0 otherwise)
+  w += (size_t)blockIdx.y * w_stride;
   int tr, tc;
   tile_coords(blockIdx.x, nt, tr, tc);
   const int r = threadIdx.x & 15, c = threadIdx.x >> 4;
@@ -97,7 +100,10 @@ __global__ void __launch_bounds__(256) pack_density_kernel(const double *__restr
 //    one coalesced 16-byte load per accumulator pair)
 __global__ void __launch_bounds__(256) pack_coeff_kernel(const double *__restrict__ coeff, int ldc, int n,
                                                          int n_occ, int nib, int nt,
-                                                         double *__restrict__ ctf, double *__restrict__ cep) {
+                                                         double *__restrict__ ctf, double *__restrict__ cep,
+                                                         size_t coeff_stride, size_t ctf_stride) {
+  coeff += (size_t)blockIdx.y * coeff_stride;
+  ctf += (size_t)blockIdx.y * ctf_stride;
   const size_t total = (size_t)nt * nib * 128;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (size_t)gridDim.x * blockDim.x) {
@@ -128,7 +134,16 @@ __global__ void __launch_bounds__(256) finalize_jk_kernel(const double *__restri
                                                           double k_factor, double *__restrict__ j_out,
                                                           double *__restrict__ k_out,
                                                           const double *__restrict__ h, double jf, double kf,
-                                                          double *__restrict__ fock_out) {
+                                                          double *__restrict__ fock_out, size_t jpart_stride,
+                                                          size_t kpart_stride, size_t out_stride) {
+  if (blockIdx.y != 0) {                            // fragment of a batch: every operand moves on by its stride
+    if (jpart) jpart += (size_t)blockIdx.y * jpart_stride;
+    if (kpart) kpart += (size_t)blockIdx.y * kpart_stride;
+    if (j_out) j_out += (size_t)blockIdx.y * out_stride;
+    if (k_out) k_out += (size_t)blockIdx.y * out_stride;
+    if (h) h += (size_t)blockIdx.y * out_stride;
+    if (fock_out) fock_out += (size_t)blockIdx.y * out_stride;
+  }
   int tr, tc;
   tile_coords(blockIdx.x, nt, tr, tc);
   const int a = tr * 16 + (threadIdx.x >> 4);
@@ -206,7 +221,13 @@ __global__ void __launch_bounds__(256) combine_g_kernel(const double *__restrict
 // on scheduling.  scratch: [128 partial slots | 1 counter at a FIXED slot (left at 0)].
 __global__ void __launch_bounds__(256) energy_kernel(const double *__restrict__ d, const double *__restrict__ h,
                                                      const double *__restrict__ f, size_t nn,
-                                                     double *__restrict__ scratch, double *__restrict__ out) {
+                                                     double *__restrict__ scratch, double *__restrict__ out,
+                                                     size_t mat_stride, size_t out_stride) {
+  d += (size_t)blockIdx.y * mat_stride;             // fragment of a batch: own matrices, own scratch (130 doubles), own result
+  h += (size_t)blockIdx.y * mat_stride;
+  f += (size_t)blockIdx.y * mat_stride;
+  scratch += (size_t)blockIdx.y * 130;
+  out += (size_t)blockIdx.y * out_stride;
   __shared__ double red[8];
   __shared__ bool last;
   double s = 0.0;
@@ -269,9 +290,11 @@ void launch_synth_tensor(double *d_packed, int n, int q_global_begin, int q_coun
   }
 }
 
-void launch_pack_density(const double *d_density, int n, double *d_w, const int *d_skip_flag, cudaStream_t s) {
+void launch_pack_density(const double *d_density, int n, double *d_w, const int *d_skip_flag, cudaStream_t s, int batch,
+                         size_t d_stride, size_t w_stride) {
   const int nt = num_tiles(n);
-  pack_density_kernel<<<(unsigned)num_lower_tiles(nt), 256, 0, s>>>(d_density, n, nt, d_w, d_skip_flag);
+  dim3 grid((unsigned)num_lower_tiles(nt), (unsigned)batch);
+  pack_density_kernel<<<grid, 256, 0, s>>>(d_density, n, nt, d_w, d_skip_flag, d_stride, w_stride);
 }
 
 // Density packing (w[L], as pack_density_kernel) fused with the on-device decision whether the
@@ -362,24 +385,27 @@ void launch_stack_factors(const double *d_x, int ldx, const double *d_c, int ldc
 }
 
 void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib, double *d_ctf, double *d_cep,
-                       cudaStream_t s) {
+                       cudaStream_t s, int batch, size_t coeff_stride, size_t ctf_stride) {
   const int nt = num_tiles(n);
   const size_t total = (size_t)nt * nib * 128;
   unsigned blocks = (unsigned)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_coeff_kernel<<<blocks, 256, 0, s>>>(d_coeff, ldc, n, n_occ, nib, nt, d_ctf, d_cep);
+  dim3 grid(blocks, (unsigned)batch);
+  pack_coeff_kernel<<<grid, 256, 0, s>>>(d_coeff, ldc, n, n_occ, nib, nt, d_ctf, d_cep, coeff_stride, ctf_stride);
 }
 
 void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits, int ktile,
                         int n, double k_factor, double *d_j, double *d_k, cudaStream_t s, const double *d_h,
-                        double jf, double kf, double *d_fock, int n_ksplits_diag) {
+                        double jf, double kf, double *d_fock, int n_ksplits_diag, int batch, size_t jpart_stride,
+                        size_t kpart_stride, size_t out_stride) {
   const int nt = num_tiles(n);
   const int ktile_log2 = ktile == 128 ? 7 : 6;
   const int np = (n + ktile - 1) / ktile;
-  finalize_jk_kernel<<<(unsigned)num_lower_tiles(nt), 256, 0, s>>>(d_jpart, n_jslices, packed_row_len(n), d_kpart, n_ksplits,
+  dim3 grid((unsigned)num_lower_tiles(nt), (unsigned)batch);
+  finalize_jk_kernel<<<grid, 256, 0, s>>>(d_jpart, n_jslices, packed_row_len(n), d_kpart, n_ksplits,
                                           n_ksplits_diag < 0 ? n_ksplits : n_ksplits_diag,
                                           np * (np + 1) / 2, ktile_log2, n, nt, k_factor, d_j, d_k, d_h, jf, kf,
-                                          d_fock);
+                                          d_fock, jpart_stride, kpart_stride, out_stride);
 }
 
 void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf, int n,
@@ -399,12 +425,13 @@ void launch_combine_g(const double *d_j, const double *d_ka, const double *d_kb,
 }
 
 void launch_energy(const double *d_density, const double *d_h, const double *d_fock, int n, double *d_scratch,
-                   double *d_out, cudaStream_t s) {
+                   double *d_out, cudaStream_t s, int batch, size_t mat_stride, size_t out_stride) {
   const size_t nn = (size_t)n * n;
   unsigned blocks = (unsigned)((nn + 4095) / 4096);
   if (blocks > 128) blocks = 128;
   if (blocks < 1) blocks = 1;
-  energy_kernel<<<blocks, 256, 0, s>>>(d_density, d_h, d_fock, nn, d_scratch, d_out);
+  dim3 grid(blocks, (unsigned)batch);
+  energy_kernel<<<grid, 256, 0, s>>>(d_density, d_h, d_fock, nn, d_scratch, d_out, mat_stride, out_stride);
 }
 
 }  // namespace mqcb200

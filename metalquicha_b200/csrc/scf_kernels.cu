@@ -282,9 +282,12 @@ struct ScfShared {
 // X = U s^-1/2 over the eigenvalues of S above 1e-7 (ascending order kept): x (n x n_mo), *n_mo_out.
 __global__ void __launch_bounds__(SCF_THREADS, 1) scf_orthogonalizer_kernel(const double *__restrict__ s, int n,
                                                                             double *__restrict__ x,
-                                                                            int *__restrict__ n_mo_out) {
+                                                                            int *__restrict__ n_mo_out, size_t block_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScfShared &sh = *reinterpret_cast<ScfShared *>(smem_raw);
+  s += (size_t)blockIdx.x * block_stride;            // one CTA per fragment of a batch
+  x += (size_t)blockIdx.x * block_stride;
+  n_mo_out += (size_t)blockIdx.x * block_stride * 2; // (ints inside a block of doubles)
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) sh.a[(e % n) + SCF_LD * (e / n)] = s[e];
   __syncthreads();
   jacobi_eigh(sh.a, sh.v, n, sh.red, &sh.rotated);
@@ -305,6 +308,8 @@ __global__ void __launch_bounds__(SCF_THREADS, 1) scf_orthogonalizer_kernel(cons
 }
 
 struct ScfStepArgs {
+  size_t block_stride;      // doubles between the state blocks of consecutive fragments (one CTA each)
+  const int *n_mo_dev;      // non-null: read n_mo from the device (per fragment) instead of the argument
   int n, n_mo, n_occ, diis_max;
   int mode;                 // 0: guess step (diagonalise the starting Fock, build D; no DIIS, no test)
                             // 1: SCF iteration
@@ -324,7 +329,19 @@ __global__ void __launch_bounds__(SCF_THREADS, 1) scf_step_kernel(ScfStepArgs p)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScfShared &sh = *reinterpret_cast<ScfShared *>(smem_raw);
   const int tid = threadIdx.x, nth = blockDim.x;
+  if (blockIdx.x != 0) {                               // fragment of a batch: its own state block
+    const size_t o = (size_t)blockIdx.x * p.block_stride;
+    p.h += o; p.s += o; p.x += o; p.fock += o; p.density += o; p.coeff += o; p.eps += o; p.work += o;
+    p.diis_f += o; p.diis_e += o; p.diis_b += o; p.scalars += o;
+    p.state += 2 * o;
+    if (p.n_mo_dev) p.n_mo_dev += 2 * o;
+  }
+  if (p.n_mo_dev) p.n_mo = *p.n_mo_dev;
   const int n = p.n, m = p.n_mo, nn = n * n, mm = m * m;
+  if (m <= 0 || p.n_occ > m) {                         // batch: a fragment whose basis collapsed is reported, not iterated
+    if (tid == 0 && p.mode == 1) p.state[3] = -1;
+    return;
+  }
   if (p.mode == 1 && p.state[3] != 0) return;            // already converged: later queued iterations are no-ops
   double *w0 = p.work, *w1 = w0 + nn, *w2 = w1 + nn, *w3 = w2 + nn;
   const double *f_use = p.fock;
@@ -495,17 +512,19 @@ void configure_scf_kernels() {
 
 bool scf_path_applies(int n) { return n >= 1 && n <= SCF_MAX_N; }
 
-void launch_scf_orthogonalizer(const double *d_s, int n, double *d_x, int *d_n_mo, cudaStream_t s) {
-  scf_orthogonalizer_kernel<<<1, SCF_THREADS, sizeof(ScfShared), s>>>(d_s, n, d_x, d_n_mo);
+void launch_scf_orthogonalizer(const double *d_s, int n, double *d_x, int *d_n_mo, cudaStream_t s, int batch,
+                               size_t block_stride) {
+  scf_orthogonalizer_kernel<<<batch, SCF_THREADS, sizeof(ScfShared), s>>>(d_s, n, d_x, d_n_mo, block_stride);
 }
 
 void launch_scf_step(const ScfStepLaunch &a, cudaStream_t s) {
   ScfStepArgs p;
+  p.block_stride = a.block_stride; p.n_mo_dev = a.n_mo_dev;
   p.n = a.n; p.n_mo = a.n_mo; p.n_occ = a.n_occ; p.diis_max = a.diis_max; p.mode = a.mode; p.guess = a.guess;
   p.h = a.h; p.s = a.s; p.x = a.x; p.fock = a.fock; p.density = a.density; p.coeff = a.coeff; p.eps = a.eps;
   p.work = a.work; p.diis_f = a.diis_f; p.diis_e = a.diis_e; p.diis_b = a.diis_b; p.state = a.state; p.scalars = a.scalars;
   p.energy_tol = a.energy_tol; p.density_tol = a.density_tol;
-  scf_step_kernel<<<1, SCF_THREADS, sizeof(ScfShared), s>>>(p);
+  scf_step_kernel<<<a.batch, SCF_THREADS, sizeof(ScfShared), s>>>(p);
 }
 
 }  // namespace mqcb200

@@ -414,6 +414,39 @@ class B200FockEngine:
             _ptr(gamma), _ptr(omega)))
         return gamma, omega
 
+    def run_scf_fragment_batch(self, h_all, s_all, n_electrons: int, max_iter: int = 100, energy_tol: float = 1e-10,
+                               density_tol: float = 1e-8, diis_vectors: int = 8, guess: str = "gwh", k_scale=None,
+                               slot: int = SLOT_FULL_RANGE, check_every: int = 1, want_matrices: bool = True) -> dict:
+        """A batch of fragments of one kind in lock-step (``mqcb200_scf_fragment_batch``): ``h_all`` and
+        ``s_all`` are ``(n_fragments, n, n)`` stacks (each matrix symmetric), the slot holds the
+        fragments' tensors back to back (``set_tensor(np.hstack([b_0, b_1, ...]))``).  Returns arrays
+        over the fragments: electronic, iterations, converged (1 / 0 / -1), n_mo, and -- with
+        ``want_matrices`` -- density ``(n_fragments, n, n)``, orbitals, orbital_energies."""
+        h_all = np.ascontiguousarray(np.asarray(h_all, dtype=np.float64))
+        s_all = np.ascontiguousarray(np.asarray(s_all, dtype=np.float64))
+        nf, n = h_all.shape[0], h_all.shape[1]
+        if h_all.shape != (nf, n, n) or s_all.shape != (nf, n, n):
+            raise ValueError("h_all and s_all must both be (n_fragments, n, n)")
+        self._check_operand(n, slot)
+        _check(self._lib.mqcb200_set_scf_check_every(self._h, int(check_every)))
+        e = np.zeros(nf)
+        it = np.zeros(nf, dtype=np.int32)
+        conv = np.zeros(nf, dtype=np.int32)
+        nmo = np.zeros(nf, dtype=np.int32)
+        coeff = np.zeros((nf, n, n)) if want_matrices else None     # [f] holds the column-major (n, n_mo) image
+        eps = np.zeros((nf, n)) if want_matrices else None
+        dens = np.zeros((nf, n, n)) if want_matrices else None
+        _check(self._lib.mqcb200_scf_fragment_batch(
+            self._h, slot, nf, _ptr(h_all), _ptr(s_all), int(n_electrons), {"core": 0, "gwh": 1}[guess], int(max_iter),
+            c_double(energy_tol), c_double(density_tol), int(diis_vectors), c_double(1.0 if k_scale is None else k_scale),
+            _ptr(e), _ptr(it), _ptr(conv), _ptr(nmo), _ptr(coeff), _ptr(eps), _ptr(dens)))
+        out = {"electronic": e, "iterations": it, "converged": conv, "n_mo": nmo}
+        if want_matrices:
+            out["density"] = dens                                    # symmetric: the row-major view equals the column-major image
+            out["orbitals"] = [np.asfortranarray(coeff[f].reshape(-1)[:n * nmo[f]].reshape((n, nmo[f]), order="F")) for f in range(nf)]
+            out["orbital_energies"] = [eps[f, :nmo[f]].copy() for f in range(nf)]
+        return out
+
     def last_energy(self) -> float:
         """``electronic_energy(h, fock, density)`` of the last ``build_fock_df`` (rhf.f90:1691-1697)."""
         e = c_double(0.0)

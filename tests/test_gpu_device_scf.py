@@ -113,3 +113,48 @@ def test_refusals(engine):
     engine.set_tensor(big)
     with pytest.raises(B200Error, match="fragment-sized"):
         engine.run_scf_fragment(np.eye(96), np.eye(96), 4)
+
+
+@pytest.mark.parametrize("n,n_occ,naux,nf", [(72, 15, 340, 6), (24, 5, 113, 33), (40, 8, 60, 3)])
+def test_batch_of_fragments_in_lock_step(engine, n, n_occ, naux, nf):
+    """mqcb200_scf_fragment_batch: nf fragments of one kind, tensors back to back on the slot, every
+    kernel launched once per iteration with the fragment index on a grid axis.  Each fragment must
+    follow the oracle's SCF (its own iteration count included) and agree with the one-at-a-time path."""
+    problems = [_synthetic_fragment(4000 + 17 * f + n, n, n_occ, naux, coupling=0.25 + 0.02 * (f % 5),
+                                    null_mode=(n == 40 and f == 1)) for f in range(nf)]
+    s_all = np.stack([p[0] for p in problems])
+    h_all = np.stack([p[1] for p in problems])
+    engine.set_tensor(np.asfortranarray(np.hstack([p[2] for p in problems])), n=n)
+    out = engine.run_scf_fragment_batch(h_all, s_all, 2 * n_occ)
+    check = range(nf) if nf <= 8 else (0, 7, nf - 1)
+    for f in check:
+        s, h, b = problems[f]
+        ref, hist = _oracle_scf(h, s, b, 2 * n_occ)
+        assert out["converged"][f] == 1 and ref["converged"]
+        assert out["iterations"][f] == ref["iterations"]
+        assert abs(out["electronic"][f] - ref["electronic"]) <= TOL_E
+        assert np.max(np.abs(out["density"][f] - ref["density"])) <= 1e-7
+        assert out["orbitals"][f].shape == ref["orbitals"].shape
+    # one-at-a-time on the same handle gives the same energies (different partial-sum grouping: 1e-11)
+    s, h, b = problems[0]
+    engine.set_tensor(b)
+    one = engine.run_scf_fragment(h, s, 2 * n_occ)
+    assert abs(one["electronic"] - out["electronic"][0]) <= 1e-10 and one["iterations"] == out["iterations"][0]
+    # repeat: bit-identical; queued iterations change nothing
+    engine.set_tensor(np.asfortranarray(np.hstack([p[2] for p in problems])), n=n)
+    again = engine.run_scf_fragment_batch(h_all, s_all, 2 * n_occ, check_every=3, want_matrices=False)
+    assert np.array_equal(again["electronic"], out["electronic"]) and np.array_equal(again["iterations"], out["iterations"])
+
+
+def test_batch_refusals(engine):
+    n, n_occ, naux = 30, 4, 20
+    s, h, b = _synthetic_fragment(5, n, n_occ, naux)
+    engine.set_tensor(np.asfortranarray(np.hstack([b, b, b])), n=n)
+    with pytest.raises(B200Error, match="back to back"):
+        engine.run_scf_fragment_batch(np.stack([h] * 7), np.stack([s] * 7), 2 * n_occ)    # 60 slabs do not split in 7
+    out = engine.run_scf_fragment_batch(np.stack([h] * 3), np.stack([s] * 3), 2 * n_occ)
+    assert np.all(out["converged"] == 1) and out["electronic"][0] == out["electronic"][1] == out["electronic"][2]
+    # a fragment whose overlap leaves fewer orbitals than occupied is reported (-1), the others still converge
+    bad = np.zeros_like(s); bad[0, 0] = 1.0
+    out = engine.run_scf_fragment_batch(np.stack([h, h, h]), np.stack([s, bad, s]), 2 * n_occ)
+    assert list(out["converged"]) == [1, -1, 1]

@@ -1649,11 +1649,46 @@ static void whiten_push(Engine *e, int slot, int nu_begin, int nu_count, const d
   const long long tile0 = tile_index(tc0, tc0, nt);
   const long long tile1 = tc1 >= nt ? num_lower_tiles(nt) : tile_index(tc1, tc1, nt);
   const long long l_slab = (tile1 - tile0) * TILE_ELEMS;
-  const size_t slab_elems = (size_t)n * nu_count;
+  // Only the rows the packed layout reads cross PCIe (mu >= nu_begin: on average half of the slab), gathered by a
+  // few host threads into two pinned buffers so that the gather of chunk k+1 overlaps the DMA of chunk k.
+  const size_t rows = (size_t)(n - nu_begin);
+  const size_t slab_elems = rows * nu_count;
   w.d_slab.ensure(slab_elems * w.naux * sizeof(double));
   w.d_tp.ensure((size_t)l_slab * w.naux * sizeof(double));
-  CUDA_CHECK(cudaMemcpy2DAsync(w.d_slab.ptr, slab_elems * sizeof(double), three_cols, (size_t)ld_aux * sizeof(double),
-                               slab_elems * sizeof(double), (size_t)w.naux, cudaMemcpyHostToDevice, e->stream));
+  {
+    size_t chunk = std::max<size_t>(1, ((size_t)64 << 20) / (slab_elems * sizeof(double)));
+    chunk = std::min(chunk, (size_t)w.naux);
+    const int n_buf = chunk < (size_t)w.naux ? 2 : 1;
+    for (int i = 0; i < n_buf; ++i) {
+      e->h_stage[i].ensure(chunk * slab_elems * sizeof(double));
+      if (!e->ev_stage[i]) CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
+    }
+    size_t k = 0;
+    for (size_t p0 = 0; p0 < (size_t)w.naux; p0 += chunk, ++k) {
+      const size_t pc = std::min(chunk, (size_t)w.naux - p0);
+      const int buf = (int)(k % n_buf);
+      if (k >= (size_t)n_buf) CUDA_CHECK(cudaEventSynchronize(e->ev_stage[buf]));
+      double *dst = e->h_stage[buf].d();
+      auto work = [&](size_t lo, size_t hi) {
+        for (size_t p = lo; p < hi; ++p) {
+          const double *src = three_cols + (p0 + p) * (size_t)ld_aux + (size_t)nu_begin;   // (mu = nu_begin, nu = nu_begin)
+          double *d_p = dst + p * slab_elems;
+          for (int c = 0; c < nu_count; ++c) std::memcpy(d_p + (size_t)c * rows, src + (size_t)c * n, rows * sizeof(double));
+        }
+      };
+      const unsigned hw = std::thread::hardware_concurrency();
+      const size_t n_threads = pc * slab_elems * sizeof(double) >= ((size_t)16 << 20) ? std::min<size_t>({(size_t)8, (size_t)(hw ? hw : 1), pc}) : 1;
+      if (n_threads <= 1) {
+        work(0, pc);
+      } else {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < n_threads; ++t) pool.emplace_back(work, pc * t / n_threads, pc * (t + 1) / n_threads);
+        for (auto &th : pool) th.join();
+      }
+      CUDA_CHECK(cudaMemcpyAsync(w.d_slab.d() + p0 * slab_elems, dst, pc * slab_elems * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+      CUDA_CHECK(cudaEventRecord(e->ev_stage[buf], e->stream));
+    }
+  }
   launch_pack_slab(w.d_slab.d(), n, w.naux, nu_begin, nu_count, w.d_tp.d(), e->stream);
   if (w.m_rows > 0) {
     WhitenDst d = w.dst;

@@ -188,7 +188,8 @@ void launch_whiten_slab(const double *d_af, int m_rows, int naux, const double *
   }
 }
 
-// A nu-slab of (mu nu|P) as it arrives from the host -- d_slab[P][mu + n (nu - nu_begin)], P = 0..naux-1 --
+// A nu-slab of (mu nu|P) as it was shipped from the host -- only the rows the packed layout reads,
+// mu >= nu_begin: d_slab[P][(mu - nu_begin) + (n - nu_begin) (nu - nu_begin)], P = 0..naux-1 --
 // into packed fragment order: d_tp[P][tile columns tc0..tc1 of the packed row].
 __global__ void __launch_bounds__(256) pack_slab_kernel(const double *__restrict__ slab, int n, int nt, int nu_begin,
                                                         int nu_count, int tc0, long long tile0, long long l_slab,
@@ -205,7 +206,8 @@ __global__ void __launch_bounds__(256) pack_slab_kernel(const double *__restrict
   double v = 0.0;
   if (mu < n && nu < n) {
     if (mu < nu) { const int tmp = mu; mu = nu; nu = tmp; }   // diagonal tile: mirror the lower triangle
-    v = slab[(size_t)p * n * nu_count + (size_t)mu + (size_t)n * (nu - nu_begin)];
+    const size_t rows = (size_t)(n - nu_begin);
+    v = slab[(size_t)p * rows * nu_count + (size_t)(mu - nu_begin) + rows * (nu - nu_begin)];
   }
   tp[(size_t)p * l_slab + (size_t)blockIdx.x * TILE_ELEMS + in_tile_offset(r, c)] = v;
 }
@@ -219,7 +221,7 @@ void launch_pack_slab(const double *d_slab, int n, int naux, int nu_begin, int n
   for (int p0 = 0; p0 < naux; p0 += 65535) {
     const int pc = naux - p0 < 65535 ? naux - p0 : 65535;
     dim3 grid((unsigned)n_tiles, (unsigned)pc);
-    pack_slab_kernel<<<grid, 256, 0, s>>>(d_slab + (size_t)p0 * n * nu_count, n, nt, nu_begin, nu_count, tc0, tile0,
+    pack_slab_kernel<<<grid, 256, 0, s>>>(d_slab + (size_t)p0 * (size_t)(n - nu_begin) * nu_count, n, nt, nu_begin, nu_count, tc0, tile0,
                                           n_tiles * TILE_ELEMS, d_tp + (size_t)p0 * n_tiles * TILE_ELEMS);
   }
 }

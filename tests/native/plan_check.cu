@@ -113,6 +113,25 @@ static void check_plan_k() {
     }
 }
 
+// rank-2 (SYR2K-form) plans: the stacked operand has 2*ceil16(o) columns, X-chunk k pairs with chunk
+// k + pair_off of the C half, every tile (diagonal ones too) takes the full two-panel path
+static void check_plan_rank2() {
+  for (int n : {17, 58, 72, 130, 688, 1450})
+    for (int o : {1, 9, 15, 16, 17, 33, 80, 81, 129, 241}) {
+      if (o > n) continue;
+      for (int q : {1, 12, 70, 340, 1800}) {
+        const KPlan p = plan_k(n, /*ignored*/ 0, q, (size_t)4 << 30, 148, o);
+        const int o16 = (o + 15) / 16 * 16;
+        CHECK(p.pair_off == o16 / 16 && p.npairs == o16 / 16, "pairs (o=%d): off=%d n=%d", o, p.pair_off, p.npairs);
+        CHECK(p.nib * 8 >= 2 * o16 && p.nkc * 2 == p.nib, "stacked width nib=%d o16=%d", p.nib, o16);
+        CHECK(p.pair_off + p.npairs <= p.nkc, "the C half must lie inside the half-transformed chunks");
+        CHECK(p.ks_last >= 1 && p.ks_last <= 4 && 16 * (p.npairs - 1) + 4 * p.ks_last >= o, "ks_last=%d o=%d", p.ks_last, o);
+        CHECK(p.n_splits_diag == p.n_splits, "rank-2 diagonal tiles are full tiles: %d vs %d", p.n_splits_diag, p.n_splits);
+        CHECK(p.kpart_elems == (size_t)p.n_splits * p.n_ktiles * p.ktile * p.ktile, "kpart size");
+      }
+    }
+}
+
 static void check_plan_j_and_fragment() {
   for (int n : {1, 16, 24, 72, 80, 81, 688, 1450})
     for (int q : {1, 7, 64, 340, 1800, 6800}) {
@@ -140,6 +159,7 @@ static void check_plan_j_and_fragment() {
 int main() {
   check_layout();
   check_plan_k();
+  check_plan_rank2();
   check_plan_j_and_fragment();
   if (failures) { printf("%d planner/layout checks FAILED\n", failures); return 1; }
   printf("planner and layout invariants hold\n");

@@ -74,3 +74,19 @@ def test_general_batched_gemm_shapes_through_the_gradient_path(engine):
     pad = np.zeros((n + 5, n_occ + 2), order="F"); pad[:n, :n_occ] = c
     g2, o2 = engine.df_gradient_densities(half, d, pad[:n, :], n_occ)
     assert np.array_equal(g2, gamma) and np.array_equal(o2, omega)
+
+
+def test_nothing_asked_nothing_built(engine):
+    """exx_fraction = 0 with the Coulomb shapes dropped leaves both densities exactly zero
+    (gradient.f90:1672, :1691-1695, :1701); a pure functional keeps only the Coulomb shapes."""
+    n, naux, n_occ = 30, 44, 6
+    three, metric, half = _problem(21, n, naux)
+    c = synth.synth_orbitals(21, n, n_occ)
+    d = np.asfortranarray(2.0 * c @ c.T)
+    engine.set_tensor_from_3c(three, half, n)
+    gamma, omega = engine.df_gradient_densities(half, d, c, n_occ, exx_fraction=0.0, with_coulomb=False)
+    assert not gamma.any() and not omega.any()
+    gamma, omega = engine.df_gradient_densities(half, d, c, n_occ, exx_fraction=0.0)
+    g_ref, o_ref, rho, _ = grad.df_gradient_densities(three, metric, d, c, n_occ, exx_fraction=0.0)
+    assert _close(gamma, g_ref) and _close(omega, o_ref)
+    assert _close(gamma[:, :, 3], rho[3] * d)

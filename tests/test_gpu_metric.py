@@ -46,3 +46,34 @@ def test_singular_and_indefinite_metrics(engine):
     ref = oracle.metric_inverse_sqrt(0.5 * (m + m.T))
     assert engine.last_metric_kept == 11
     assert float(np.max(np.abs(half - ref))) <= 1e-9 * max(1.0, float(np.max(np.abs(ref))))
+
+
+def test_slab_streamed_whitening_refusals(engine):
+    """The slab API refuses what it cannot place, with a message, and leaves the handle usable."""
+    from metalquicha_b200 import synth
+    n, naux = 40, 24
+    three, metric = synth.synth_physical_like_tensor(4, n, naux, n_null=0)
+    half = engine.metric_inverse_sqrt(metric)
+    blk = np.asfortranarray(three.reshape(n, n, naux, order="F")[:, 0:16, :].reshape(n * 16, naux, order="F"))
+    with pytest.raises(B200Error, match="no whitening in progress"):
+        engine._whiten = (0, n, naux, 0, naux)
+        engine.whiten_push(0, blk)
+    engine.whiten_begin(n, naux, half)
+    with pytest.raises(B200Error, match="already in progress"):
+        engine.whiten_begin(n, naux, half)
+    # a failed push (nu_begin not on a 16-column boundary) ends the whitening on a lone rank
+    with pytest.raises(B200Error, match="16-wide column tiles"):
+        engine.whiten_push(8, blk)
+    with pytest.raises(B200Error, match="no whitening in progress"):
+        engine.whiten_end()
+    # ... and the handle still works
+    engine.whiten_begin(n, naux, half)
+    three3 = three.reshape(n, n, naux, order="F")
+    for nu0, nu1 in ((0, 16), (16, 32), (32, 40)):
+        engine.whiten_push(nu0, np.asfortranarray(three3[:, nu0:nu1, :].reshape(n * (nu1 - nu0), naux, order="F")))
+    engine.whiten_end()
+    _, h, d, c = synth.synth_problem(4, n, 6, naux, with_tensor=False)
+    b = np.asfortranarray(three @ oracle.metric_inverse_sqrt(metric))
+    f = engine.build_fock_df(h, d, c, 6)
+    ref = oracle.build_fock_df(h, b, d, c, 6)
+    assert float(np.max(np.abs(f - ref))) <= 1e-10 * max(1.0, float(np.max(np.abs(ref))))

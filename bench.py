@@ -610,7 +610,7 @@ def run_setup_timings(ctx, name):
         out["whiten"] = {"skipped": "the host-side stand-in for (mu nu|P) is sized for c2; run --workload c2 for this block"}
         return out
     # build_df_tensor's last two stages on the device: metric^(-1/2) (one-sided Jacobi + GEMM), then
-    # b = three . half streamed nu-slab by nu-slab (16 orbital columns per push, every push the same
+    # b = three . half streamed nu-slab by nu-slab (64 orbital columns per push, every push the same
     # host block: the arithmetic does not care, the PCIe traffic is the real one)
     u, _ = np.linalg.qr(rng.standard_normal((naux, naux)))
     lam = np.exp(rng.uniform(-2.0, 2.0, size=naux))
@@ -622,13 +622,14 @@ def run_setup_timings(ctx, name):
     m_ms, m_sweeps = eng.last_metric()
     out["metric_inverse_sqrt"] = {"naux": naux, "device_ms": m_ms, "wall_ms": 1e3 * wall_metric, "jacobi_sweeps": m_sweeps,
                                   "what": "mqcb200_metric_inverse_sqrt: one-sided Jacobi on the GPU + (U s^-1/2) U^T"}
-    block = np.asfortranarray(rng.standard_normal((n * 16, naux)))
+    slab_nu = 64
+    block = np.asfortranarray(rng.standard_normal((n * slab_nu, naux)))
     eng.whiten_begin(n, naux, half, slot=1)
     t0 = time.perf_counter()
     nu, pcie = 0, 0.0
     while nu < n:
-        cnt = min(16, n - nu)
-        eng.whiten_push(nu, block[: n * cnt, :] if cnt < 16 else block, slot=1)
+        cnt = min(slab_nu, n - nu)
+        eng.whiten_push(nu, block[: n * cnt, :] if cnt < slab_nu else block, slot=1)
         pcie += 8.0 * (n - nu) * cnt * naux              # only the rows mu >= nu of a slab cross the bus
         nu += cnt
     eng.whiten_end(slot=1)

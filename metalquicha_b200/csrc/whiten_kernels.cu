@@ -25,6 +25,8 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+#include <cmath>
+
 namespace mqcb200 {
 
 struct WhitenCfg {
@@ -230,11 +232,12 @@ void launch_pack_slab(const double *d_slab, int n, int naux, int nu_begin, int n
 // metric^(-1/2): one-sided Jacobi on the columns of the symmetric metric
 // ------------------------------------------------------------------------------------------------
 // One CTA per pair (p, q) of the round (round-robin ordering, as in scf_kernels.cu): alpha = |g_p|^2,
-// beta = |g_q|^2, gamma = g_p . g_q in fixed order; if |gamma| > 1e-15 sqrt(alpha beta) the two columns
-// of G and of V are rotated so that g_p . g_q = 0.  At convergence G = V diag(lambda): the columns of V
+// beta = |g_q|^2, gamma = g_p . g_q in fixed order; if |gamma| > tol sqrt(alpha beta) the two columns
+// of G and of V are rotated so that g_p . g_q = 0.  tol = 4 * 2^-53 * sqrt(n): the rounding error of an
+// n-term dot product -- a smaller threshold only chases that noise (18 sweeps instead of ~11 at n = 1800).  At convergence G = V diag(lambda): the columns of V
 // are the eigenvectors, lambda_i = v_i . g_i.
 __global__ void __launch_bounds__(256) hestenes_round_kernel(double *__restrict__ g, double *__restrict__ v, int n,
-                                                             int round, int *__restrict__ rotated) {
+                                                             int round, int *__restrict__ rotated, double tol) {
   const int n_e = (n + 1) & ~1;
   const int k = blockIdx.x;
   const int pa = k == 0 ? 0 : 1 + (k - 1 + round) % (n_e - 1);
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(256) hestenes_round_kernel(double *__restrict_
     double al = 0.0, be = 0.0, ga = 0.0;
     for (int w = 0; w < 8; ++w) { al += red[0][w]; be += red[1][w]; ga += red[2][w]; }
     double cc = 1.0, ss = 0.0;
-    if (fabs(ga) > 1.0e-15 * sqrt(al * be) && fabs(ga) > 0.0) {
+    if (fabs(ga) > tol * sqrt(al * be) && fabs(ga) > 0.0) {
       const double d = be - al;
       const double num = d >= 0.0 ? 2.0 * ga : -2.0 * ga;
       const double t = num / (fabs(d) + sqrt(fma(d, d, 4.0 * ga * ga)));
@@ -315,7 +318,8 @@ __global__ void __launch_bounds__(256) metric_scale_kernel(const double *__restr
 
 void launch_hestenes_round(double *d_g, double *d_v, int n, int round, int *d_rotated, cudaStream_t s) {
   const int n_e = (n + 1) & ~1;
-  hestenes_round_kernel<<<n_e / 2, 256, 0, s>>>(d_g, d_v, n, round, d_rotated);
+  const double tol = 4.0 * 1.1102230246251565e-16 * sqrt((double)(n > 16 ? n : 16));
+  hestenes_round_kernel<<<n_e / 2, 256, 0, s>>>(d_g, d_v, n, round, d_rotated, tol);
 }
 
 void launch_set_identity(double *d_v, int n, cudaStream_t s) {

@@ -130,3 +130,58 @@ def test_two_gpus_as_threads_of_one_process():
         f1, f2 = out[rank]
         assert np.max(np.abs(f1 - ref)) <= 1e-10 and np.array_equal(f1, f2)
     assert np.array_equal(out[0][0], out[1][0])          # bit-identical on both GPUs
+
+
+RECOVERY_WORKER = r"""
+import os, sys, time
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["MQC_ROOT"])
+from metalquicha_b200 import B200Error, B200FockEngine, synth
+from metalquicha_b200.sharded import ShardedFockBuilder
+from oracle import df_fock_oracle as oracle
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+n, n_occ, naux = 120, 20, 60
+b, h, d, c = synth.synth_problem(9, n, n_occ, naux)
+ref = oracle.build_fock_df(h, b, d, c, n_occ)
+eng = B200FockEngine(lr)
+sb = ShardedFockBuilder(eng, rank, world)
+sb.set_tensor(b, n, naux)
+ok = float(np.max(np.abs(sb.build_fock_df(h, d, c, n_occ) - ref))) <= 1e-10
+# rank 1 falls 3 s behind with a 1 s exchange timeout: BOTH ranks must report the failed build ...
+dist.barrier()
+if rank == 1:
+    time.sleep(3.0)
+failed = False
+try:
+    sb.build_fock_df(h, d, c, n_occ)
+except B200Error as ex:
+    failed = "timed out" in str(ex)
+# ... and the next build resynchronises the ranks and is right again
+f = sb.build_fock_df(h, d, c, n_occ)
+good_again = float(np.max(np.abs(f - ref))) <= 1e-10
+f2 = sb.build_fock_df(h, d, c, n_occ)
+print(f"rank {rank}: first ok={ok} failed_as_expected={failed} recovered={good_again} repeat={np.array_equal(f, f2)}", flush=True)
+eng.close()
+dist.destroy_process_group()
+sys.exit(0 if (ok and failed and good_again and np.array_equal(f, f2)) else 1)
+"""
+
+
+def test_exchange_timeout_is_reported_and_the_ranks_recover(tmp_path):
+    """A rank that falls behind by more than MQCB200_XGPU_TIMEOUT_S fails THAT build on every rank
+    (no hang, no silently incomplete [J|K]); the next sharded build re-synchronises flags and epochs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "recovery_worker.py"
+    script.write_text(RECOVERY_WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MQC_ROOT=ROOT, MQCB200_XGPU_TIMEOUT_S="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]

@@ -145,3 +145,23 @@ def test_c5_shape_two_spin_subrange_parity(engine):
     assert np.max(np.abs(fa - (h + j_ref - ka_ref))) <= 1e-10 and np.max(np.abs(fb - (h + j_ref - kb_ref))) <= 1e-10
     e = oracle.uhf_electronic_energy(h, fa, fb, da, db)
     assert abs(e - oracle.uhf_electronic_energy(h, h + j_ref - ka_ref, h + j_ref - kb_ref, da, db)) <= 1e-9
+
+
+def test_c2_full_auxiliary_range_against_the_oracle(engine, c2):
+    """All 1800 auxiliary functions of BASELINE configs[1], not a sub-range: the oracle's J and K are
+    accumulated over eight 225-function chunks regenerated on the host (J and K are sums over the
+    auxiliary index), the engine builds from the full 3.5 GB resident tensor in one go."""
+    scale, h, d, c = c2
+    engine.synth_tensor(N, NAUX, SEED, scale)
+    j, k = engine.build_jk(d, c, NOCC)
+    f = engine.build_fock_df(h, d, c, NOCC)
+    j_ref, k_ref = np.zeros((N, N)), np.zeros((N, N))
+    for q0 in range(0, NAUX, 225):
+        b = synth.synth_tensor(SEED, N, NAUX, scale, q_begin=q0, q_count=225)
+        jq, kq, _ = oracle.jk_df_fast(b, d, c, NOCC)
+        j_ref += jq
+        k_ref += kq
+    assert np.max(np.abs(j - j_ref)) <= 1e-10 and np.max(np.abs(k - k_ref)) <= 1e-10
+    f_ref = h + j_ref - 0.5 * k_ref
+    assert np.max(np.abs(f - f_ref)) <= 1e-10
+    assert abs(engine.last_energy() - oracle.electronic_energy(h, f_ref, d)) <= 1e-9

@@ -209,6 +209,18 @@ int mqcb200_scf_fragment(void *handle, int slot, const double *hcore, const doub
                          double *e_electronic, int *iterations, int *converged, int *n_mo,
                          double *coeff, double *orbital_energies, double *density,
                          double *e_history);
+/* The same loop for ANY size (and for a tensor sharded over GPUs: every rank then runs the same
+ * bit-identical step around the exchanged Fock matrix): mqcb200_scf takes the one-CTA fragment route
+ * when the problem fits it and otherwise keeps every matrix on the GPU with the general Fock-build
+ * kernels, the batched DMMA GEMM for the dense algebra, and a one-sided Jacobi iteration on the shifted
+ * F' = Y^T F Y (Y = the previous orbitals) in place of dsyev.  Per iteration the host sees the DIIS
+ * overlaps of the newest error vector (<= 8 doubles), the eigensolver's "rotated anything?" flags and
+ * the energy / rms(dD) scalars.  Same arguments and outputs as mqcb200_scf_fragment. */
+int mqcb200_scf(void *handle, int slot, const double *hcore, const double *overlap,
+                int n_electrons, int guess, int max_iter,
+                double energy_tol, double density_tol, int diis_vectors, double k_scale,
+                double *e_electronic, int *iterations, int *converged, int *n_mo,
+                double *coeff, double *orbital_energies, double *density, double *e_history);
 /* The same for a BATCH of fragments of one kind, driven in lock-step: the slot holds n_fragments
  * tensors of equal size back to back (set it with naux = n_fragments * naux_per_fragment: fragment f
  * owns auxiliary slabs [f*naux_per_fragment, (f+1)*naux_per_fragment)), hcore_all / overlap_all are

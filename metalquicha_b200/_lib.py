@@ -61,6 +61,9 @@ SIGNATURES = {
     "mqcb200_scf_fragment": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_int,
                                      c_double, _dp, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mqcb200_scf": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_int,
+                            c_double, _dp, POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                            c_void_p, c_void_p, c_void_p, c_void_p]),
     "mqcb200_scf_fragment_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double,
                                            c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mqcb200_set_scf_check_every": (c_int, [c_void_p, c_int]),

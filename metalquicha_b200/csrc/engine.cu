@@ -164,6 +164,7 @@ struct Engine {
   DevBuf d_scf;                  // device-resident SCF of a fragment: H, S, X, F, D, C, eps, work, DIIS history, scalars
   PinnedBuf h_scf;               // its per-iteration scalars on the host side
   int scf_check_every = 1;       // iterations queued between two looks at the convergence flag
+  int scf_last_sweeps = 0;       // Jacobi sweeps of the last diagonalisation of the general-size SCF
   DevBuf d_jk;       // [J | K | K_beta] contiguous so one all-reduce covers them
   DevBuf d_scalar, d_stage, d_escratch;
   DevBuf d_in;                   // [H | D | C_a | C_b] of a host-operand build, contiguous
@@ -1224,6 +1225,232 @@ static void scf_fragment(Engine *e, const ScfArgs &a) {
   if (a.n_mo) *a.n_mo = n_mo;
 }
 
+// ------------------------------- device-resident SCF, any size ------------------------------
+// The same loop (run_libcint_rhf, rhf.f90:566-649) for problems beyond the one-CTA step: every
+// matrix stays on the GPU, the Fock build is the general path above (two streams, fused Coulomb
+// vector, the cross-GPU exchange when the tensor is sharded -- every rank then runs the same,
+// bit-identical step), the dense algebra is the batched DMMA GEMM, and LAPACK's dsyev is replaced by
+// a one-sided Jacobi iteration on the (shifted, hence positive definite) F' = Y^T F Y with Y the
+// previous orbitals: nearly diagonal, three or four sweeps.  Per iteration the host sees the DIIS
+// overlaps of the newest error vector, the Jacobi "rotated anything?" flags and three scalars.
+static bool diis_solve_host(const double *overlap /*[8][8] slot coords*/, int newest, int n_stored, int dmax, double *coef,
+                            int *slots) {
+  // diis_coefficients + solve_diis (src/methods/mqc_diis.f90:146-273): ages oldest -> newest
+  if (n_stored < 2) return false;
+  const int nb = n_stored + 1;
+  double aug[9][10];
+  double scale = 0.0;
+  for (int i = 0; i < n_stored; ++i) slots[i] = ((newest - n_stored + i) % dmax + dmax) % dmax;
+  for (int i = 0; i < n_stored; ++i)
+    for (int j = 0; j < n_stored; ++j) {
+      aug[i][j] = overlap[slots[i] * 8 + slots[j]];
+      scale = std::max(scale, std::fabs(aug[i][j]));
+    }
+  for (int i = 0; i < n_stored; ++i)
+    for (int j = 0; j < n_stored; ++j)
+      if (scale > 0.0) aug[i][j] /= scale;
+  for (int i = 0; i < n_stored; ++i) { aug[i][n_stored] = -1.0; aug[n_stored][i] = -1.0; aug[i][nb] = 0.0; }
+  aug[n_stored][n_stored] = 0.0;
+  aug[n_stored][nb] = -1.0;
+  for (int i = 0; i < nb; ++i) {
+    int piv = i;
+    for (int j = i + 1; j < nb; ++j)
+      if (std::fabs(aug[j][i]) > std::fabs(aug[piv][i])) piv = j;
+    if (piv != i)
+      for (int c = 0; c <= nb; ++c) std::swap(aug[i][c], aug[piv][c]);
+    const double pivot = aug[i][i];
+    if (std::fabs(pivot) < 1.0e-14) return false;                  // PIVOT_FLOOR
+    for (int j = i + 1; j < nb; ++j) {
+      const double factor = aug[j][i] / pivot;
+      for (int c = i; c <= nb; ++c) aug[j][c] -= factor * aug[i][c];
+    }
+  }
+  double sol[9];
+  for (int i = nb - 1; i >= 0; --i) {
+    double sum = 0.0;
+    for (int c = i + 1; c < nb; ++c) sum += aug[i][c] * sol[c];
+    sol[i] = (aug[i][nb] - sum) / aug[i][i];
+  }
+  for (int i = 0; i < n_stored; ++i) coef[i] = sol[i];
+  return true;
+}
+
+static void scf_general(Engine *e, const ScfArgs &a) {
+  if (a.slot < 0 || a.slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  TensorSlot &sl = e->slots[a.slot];
+  if (!sl.set) throw Failure("mqcb200: no fitted tensor has been set on this slot (call mqcb200_set_tensor first)");
+  if (!a.h || !a.s || !a.e_electronic || !a.iterations || !a.converged) throw Failure("mqcb200: null argument to scf");
+  if (a.n_electrons < 0 || (a.n_electrons & 1)) throw Failure("mqcb200: closed-shell SCF needs an even, non-negative electron count");
+  if (a.diis_vectors < 0 || a.diis_vectors > 8) throw Failure("mqcb200: diis_vectors must lie in 0..8");
+  if (a.max_iter < 1) throw Failure("mqcb200: max_iter must be positive");
+  const int n = sl.n, n_occ = a.n_electrons / 2, dmax = a.diis_vectors;
+  const size_t nn = (size_t)n * n;
+  e->bind();
+  cudaStream_t st = e->stream;
+  int total_launches = 0;
+  DevBuf blk;
+  size_t off = 0;
+  auto take = [&](size_t count) { const size_t o = off; off += (count + 1) & ~(size_t)1; return o; };
+  const size_t o_h = take(nn), o_s = take(nn), o_x = take(nn), o_f = take(nn), o_d = take(nn), o_c = take(nn), o_cn = take(nn);
+  const size_t o_g = take(nn), o_v = take(nn), o_w0 = take(nn), o_w1 = take(nn), o_lam = take(n), o_eps = take(n);
+  const size_t o_df = take((size_t)std::max(dmax, 1) * nn), o_de = take((size_t)std::max(dmax, 1) * nn);
+  const size_t o_bm = take(16), o_coef = take(16), o_scal = take(16), o_scr = take(130);
+  const size_t o_order = take((size_t)n / 2 + 2), o_slots = take(8), o_flags = take(2);
+  try {
+    blk.ensure(off * sizeof(double));
+    double *b = blk.d();
+    double *d_h = b + o_h, *d_s = b + o_s, *d_x = b + o_x, *d_f = b + o_f, *d_d = b + o_d, *d_c = b + o_c, *d_cn = b + o_cn;
+    double *d_g = b + o_g, *d_v = b + o_v, *d_w0 = b + o_w0, *d_w1 = b + o_w1, *d_lam = b + o_lam, *d_eps = b + o_eps;
+    double *d_df = b + o_df, *d_de = b + o_de, *d_bm = b + o_bm, *d_coef = b + o_coef, *d_scal = b + o_scal, *d_scr = b + o_scr;
+    int *d_order = reinterpret_cast<int *>(b + o_order), *d_slots = reinterpret_cast<int *>(b + o_slots);
+    int *d_flag = reinterpret_cast<int *>(b + o_flags), *d_ndrop = d_flag + 1;
+    CUDA_CHECK(cudaMemsetAsync(b, 0, off * sizeof(double), st));
+    CUDA_CHECK(cudaMemcpyAsync(d_h, a.h, nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(d_s, a.s, nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    auto gemm = [&](int M, int N, int K, double alpha, const double *A, int lda, bool ta, const double *B, int ldb, bool tb, double *C,
+                    int ldc) {
+      launch_dgemm_batched(M, N, K, alpha, A, lda, 0, ta, B, ldb, 0, tb, 0.0, C, ldc, 0, 1, st);
+      ++total_launches;
+    };
+    // one-sided Jacobi on the columns of the m x m positive definite matrix in d_g; eigenvectors accumulate in d_v
+    int last_sweeps = 0;
+    auto jacobi = [&](int m) {
+      launch_set_identity(d_v, m, st);
+      const int m_e = (m + 1) & ~1;
+      last_sweeps = 0;
+      for (int sweep = 0; sweep < 60; ++sweep) {
+        ++last_sweeps;
+        CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+        for (int r = 0; r < m_e - 1; ++r) launch_hestenes_round(d_g, d_v, m, r, d_flag, st);
+        total_launches += m_e - 1;
+        int rotated = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&rotated, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (!rotated) break;
+      }
+    };
+    // ---- orthogonaliser X = U s^-1/2 over eigenvalues > 1e-7, ascending (mqc_scf_common.f90:42-82)
+    CUDA_CHECK(cudaMemcpyAsync(d_g, d_s, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    jacobi(n);
+    launch_eig_lambda(d_g, d_v, n, nullptr, d_lam, st);
+    CUDA_CHECK(cudaMemsetAsync(d_ndrop, 0, sizeof(int), st));
+    launch_rank_sort(d_lam, n, 1.0e-7, d_order, d_ndrop, st);
+    int dropped = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&dropped, d_ndrop, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    const int m = n - dropped;
+    if (m <= 0) throw Failure("SCF: overlap matrix is singular");
+    if (n_occ > m)
+      throw Failure("RHF: more occupied orbitals than the basis supports after near-null modes were dropped (" +
+                    std::to_string(n_occ) + " occupied, " + std::to_string(m) + " of " + std::to_string(n) + " orbitals kept)");
+    launch_gather_columns(d_v, n, d_order, dropped, m, d_lam, true, d_x, st);
+    const size_t mm = (size_t)m * m;
+    // ---- diagonalize (rhf.f90:1464-1489) in the basis y (n x m, S-orthonormal): C <- y V, eps
+    auto diagonalize = [&](const double *f_in, const double *y) {
+      gemm(n, m, n, 1.0, f_in, n, false, y, n, false, d_w1, n);             // F y
+      gemm(m, m, n, 1.0, y, n, true, d_w1, n, false, d_g, m);               // y^T F y
+      launch_reduce(d_g, nullptr, mm, 2, d_scr, d_scal + 8, st);            // shift = |F'|_F  >= every |eigenvalue|
+      launch_symmetrize_shift(d_g, m, d_scal + 8, st);
+      jacobi(m);
+      launch_eig_lambda(d_g, d_v, m, d_scal + 8, d_lam, st);
+      launch_rank_sort(d_lam, m, -1.0e300, d_order, nullptr, st);
+      launch_gather_columns(d_v, m, d_order, 0, m, nullptr, false, d_w0, st);   // V, columns ascending
+      launch_gather_columns(d_lam, 1, d_order, 0, m, nullptr, false, d_eps, st);
+      gemm(n, m, m, 1.0, y, n, false, d_w0, m, false, d_cn, n);             // C = y V
+      CUDA_CHECK(cudaMemcpyAsync(d_c, d_cn, (size_t)n * m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      total_launches += 6;
+    };
+    auto new_density = [&]() {                                              // D = 2 C_occ C_occ^T, sum (dD)^2 -> scal[3]
+      if (n_occ > 0) gemm(n, n, n_occ, 2.0, d_c, n, false, d_c, n, true, d_w1, n);
+      else CUDA_CHECK(cudaMemsetAsync(d_w1, 0, nn * sizeof(double), st));
+      launch_reduce(d_w1, d_d, nn, 1, d_scr, d_scal + 3, st);
+      CUDA_CHECK(cudaMemcpyAsync(d_d, d_w1, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      ++total_launches;
+    };
+    auto fock_build = [&]() {
+      BuildArgs ba;
+      ba.slot = a.slot; ba.device_operands = true; ba.h = d_h; ba.density = d_d; ba.coeff_a = d_c; ba.lda = n; ba.n_a = n_occ;
+      ba.k_scale = a.k_scale; ba.j_scale = 1.0; ba.fock_a = d_f; ba.assemble = true; ba.sync = false;
+      ba.want_j = true; ba.want_k = a.k_scale != 0.0 && n_occ > 0;
+      build(e, ba);
+      total_launches += e->launches;
+      launch_energy(d_d, d_h, d_f, n, e->d_escratch.d(), d_scal, st);
+      ++total_launches;
+    };
+    // ---- guess
+    launch_scf_guess(d_h, d_s, n, a.guess == 1, d_f, st);
+    diagonalize(d_f, d_x);
+    new_density();
+    // ---- iterations
+    double overlap[64] = {0.0};
+    int n_stored = 0, newest = 0;                                           // newest: 1-based slot, as in diis_state_t
+    double e_old = 0.0;
+    int iterations = 0, converged = 0;
+    double hs[4];
+    for (int it = 1; it <= a.max_iter && !converged; ++it) {
+      fock_build();
+      const double *f_use = d_f;
+      if (dmax > 0) {
+        gemm(n, n, n, 1.0, d_f, n, false, d_d, n, false, d_w0, n);          // F D
+        gemm(n, n, n, 1.0, d_w0, n, false, d_s, n, false, d_w1, n);         // F D S
+        launch_antisym(d_w1, n, d_w0, st);                                  // F D S - S D F
+        gemm(n, m, n, 1.0, d_w0, n, false, d_x, n, false, d_w1, n);         // (..) X
+        newest = newest % dmax + 1;                                         // diis_push, mqc_diis.f90:94-119
+        if (n_stored < dmax) ++n_stored;
+        const int slot = newest - 1;
+        gemm(m, m, n, 1.0, d_x, n, true, d_w1, n, false, d_de + (size_t)slot * nn, m);   // e = X^T (..) X
+        CUDA_CHECK(cudaMemcpyAsync(d_df + (size_t)slot * nn, d_f, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        int others[8];
+        for (int age = 0; age < n_stored; ++age) {
+          others[age] = ((newest - n_stored + age) % dmax + dmax) % dmax;
+          launch_reduce(d_de + (size_t)slot * nn, d_de + (size_t)others[age] * nn, mm, 0, d_scr, d_bm + age, st);
+        }
+        total_launches += 1 + n_stored;
+        double row[8];
+        CUDA_CHECK(cudaMemcpyAsync(row, d_bm, n_stored * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int age = 0; age < n_stored; ++age) { overlap[slot * 8 + others[age]] = row[age]; overlap[others[age] * 8 + slot] = row[age]; }
+        double coef[8];
+        int slots[8];
+        if (diis_solve_host(overlap, newest, n_stored, dmax, coef, slots)) {
+          CUDA_CHECK(cudaMemcpyAsync(d_coef, coef, n_stored * sizeof(double), cudaMemcpyHostToDevice, st));
+          CUDA_CHECK(cudaMemcpyAsync(d_slots, slots, n_stored * sizeof(int), cudaMemcpyHostToDevice, st));
+          launch_lincomb(d_df, nn, d_coef, d_slots, n_stored, d_w0, st);    // extrapolated Fock, oldest first
+          f_use = d_w0;                                                     // (read once, by the first GEMM of diagonalize)
+          ++total_launches;
+        }
+      }
+      diagonalize(f_use, d_c);                                              // F' in the basis of the previous orbitals
+      new_density();
+      CUDA_CHECK(cudaMemcpyAsync(hs, d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      const double e_elec = hs[0], de = std::fabs(e_elec - e_old), drms = std::sqrt(hs[3] / (double)nn);
+      if (a.e_history) a.e_history[it - 1] = e_elec;
+      e_old = e_elec;
+      iterations = it;
+      if (it > 1 && de < a.energy_tol && drms < a.density_tol) converged = 1;
+    }
+    fock_build();                                                           // final rebuild, rhf.f90:646-649
+    CUDA_CHECK(cudaMemcpyAsync(hs, d_scal, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (a.coeff) CUDA_CHECK(cudaMemcpyAsync(a.coeff, d_c, (size_t)n * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (a.eps) CUDA_CHECK(cudaMemcpyAsync(a.eps, d_eps, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (a.density) CUDA_CHECK(cudaMemcpyAsync(a.density, d_d, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (e->comm && e->n_ranks > 1) p2p_raise_if_failed(e);
+    *a.e_electronic = hs[0];
+    *a.iterations = iterations;
+    *a.converged = converged;
+    if (a.n_mo) *a.n_mo = m;
+    e->launches = total_launches;
+    e->scf_last_sweeps = last_sweeps;
+  } catch (...) {
+    blk.release();
+    throw;
+  }
+  blk.release();
+}
+
 // ------------------------------- a batch of fragment SCFs, in lock-step ----------------------
 // MBE fragments of one kind (all trimers of a water cluster, say) have the same (n, naux, n_occ).
 // `n_frag` of them are driven together: their tensors sit back to back on the slot (fragment f owns
@@ -2212,6 +2439,26 @@ int mqcb200_df_gradient_densities(void *handle, int slot, const double *half, co
   a.cb = orbitals_beta; a.ldb = ldb; a.n_b = n_occupied_beta; a.unrestricted = unrestricted != 0;
   a.kf = exx_fraction; a.with_coulomb = with_coulomb != 0; a.gamma = gamma; a.omega = omega;
   df_gradient_densities(e, a);
+  API_END
+}
+
+int mqcb200_scf(void *handle, int slot, const double *hcore, const double *overlap, int n_electrons, int guess, int max_iter,
+                double energy_tol, double density_tol, int diis_vectors, double k_scale, double *e_electronic,
+                int *iterations, int *converged, int *n_mo, double *coeff, double *orbital_energies, double *density,
+                double *e_history) {
+  GET_ENGINE(handle)
+  API_BEGIN
+  ScfArgs a;
+  a.slot = slot; a.h = hcore; a.s = overlap; a.n_electrons = n_electrons; a.guess = guess; a.max_iter = max_iter;
+  a.energy_tol = energy_tol; a.density_tol = density_tol; a.diis_vectors = diis_vectors; a.k_scale = k_scale;
+  a.e_electronic = e_electronic; a.iterations = iterations; a.converged = converged; a.n_mo = n_mo;
+  a.coeff = coeff; a.eps = orbital_energies; a.density = density; a.e_history = e_history;
+  if (slot < 0 || slot >= MQCB200_NUM_SLOTS) throw Failure("mqcb200: tensor slot out of range");
+  const TensorSlot &sl = e->slots[slot];
+  const bool fragment_sized = sl.set && scf_path_applies(sl.n) && fragment_path_applies(sl.n, std::max(n_electrons / 2, 1)) &&
+                              !(e->comm && e->n_ranks > 1) && sl.q_count == sl.naux_total && fragment_path_enabled();
+  if (fragment_sized) scf_fragment(e, a);
+  else scf_general(e, a);
   API_END
 }
 

@@ -206,3 +206,164 @@ void launch_gradient_gamma(const double *d_rho, const double *d_density, const d
 }
 
 }  // namespace mqcb200
+
+// =================================================================================================
+// Elementwise / reduction helpers of the general-size device-resident SCF step (engine.cu: scf_general)
+// =================================================================================================
+namespace mqcb200 {
+
+// Generalised Wolfsberg-Helmholz starting Fock (rhf.f90:1354-1380) or the core guess (F = H).
+__global__ void __launch_bounds__(256) scf_guess_kernel(const double *__restrict__ h, const double *__restrict__ s, int n,
+                                                        int gwh, double *__restrict__ f) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)n * n; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % n), j = (int)(e / n);
+    double v = h[e];
+    if (gwh && i != j) v = 0.5 * 1.75 * s[e] * (h[(size_t)i * n + i] + h[(size_t)j * n + j]);
+    f[e] = v;
+  }
+}
+
+// out = a - a^T  (n x n)
+__global__ void __launch_bounds__(256) antisym_kernel(const double *__restrict__ a, int n, double *__restrict__ out) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)n * n; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = e % n, j = e / n;
+    out[e] = a[e] - a[j + (size_t)n * i];
+  }
+}
+
+// g = (g + g^T)/2 + shift * 1, lower and upper written by the thread that owns (i >= j); shift read from the device
+__global__ void __launch_bounds__(256) symmetrize_shift_kernel(double *__restrict__ g, int m, const double *__restrict__ shift) {
+  const double sg = shift ? *shift : 0.0;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)m * m; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = e % m, j = e / m;
+    if (i < j) continue;
+    const double v = 0.5 * (g[i + (size_t)m * j] + g[j + (size_t)m * i]) + (i == j ? sg : 0.0);
+    g[i + (size_t)m * j] = v;
+    g[j + (size_t)m * i] = v;
+  }
+}
+
+// Fixed-order two-level reduction, one of: 0: sum a*b   1: sum (a-b)^2   2: sqrt(sum a*a).  Each block reduces a fixed slice;
+// the block that finishes last adds the partials in index order.  scratch: 130 doubles, zero before first use (left zero).
+__global__ void __launch_bounds__(256) reduce_kernel(const double *__restrict__ a, const double *__restrict__ b, size_t count,
+                                                     int mode, double *__restrict__ scratch, double *__restrict__ out) {
+  __shared__ double red[8];
+  __shared__ bool last;
+  double s = 0.0;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x) {
+    if (mode == 0) s = fma(a[e], b[e], s);
+    else if (mode == 1) { const double d = a[e] - b[e]; s = fma(d, d, s); }
+    else s = fma(a[e], a[e], s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    scratch[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int *>(scratch + 128), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned int k = 0; k < gridDim.x; ++k) t += reinterpret_cast<volatile double *>(scratch)[k];
+    out[0] = mode == 2 ? sqrt(t) : t;
+    *reinterpret_cast<unsigned int *>(scratch + 128) = 0u;
+  }
+}
+
+// lambda_i = v_i . g_i - shift  (one CTA per column; fixed-order)
+__global__ void __launch_bounds__(256) eig_lambda_kernel(const double *__restrict__ g, const double *__restrict__ v, int m,
+                                                         const double *__restrict__ shift, double *__restrict__ lambda) {
+  const int i = blockIdx.x;
+  double s = 0.0;
+  for (int r = threadIdx.x; r < m; r += 256) s = fma(v[(size_t)i * m + r], g[(size_t)i * m + r], s);
+  __shared__ double red[8];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    lambda[i] = t - (shift ? *shift : 0.0);
+  }
+}
+
+// order[rank] = i for ascending lambda (ties by index); *n_dropped = number of lambda <= threshold
+__global__ void __launch_bounds__(256) rank_sort_kernel(const double *__restrict__ lambda, int m, double threshold,
+                                                        int *__restrict__ order, int *__restrict__ n_dropped) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double wi = lambda[i];
+  int rank = 0;
+  for (int j = 0; j < m; ++j) {
+    const double wj = lambda[j];
+    rank += (wj < wi || (wj == wi && j < i)) ? 1 : 0;
+  }
+  order[rank] = i;
+  if (n_dropped && wi <= threshold) atomicAdd(n_dropped, 1);
+}
+
+// dst(:, k) = src(:, order[k0 + k]) * (inv_sqrt ? 1/sqrt(lambda[order[k0+k]]) : 1),  k = 0..cols-1  (rows x cols, ld = rows)
+__global__ void __launch_bounds__(256) gather_columns_kernel(const double *__restrict__ src, int rows, const int *__restrict__ order,
+                                                             int k0, int cols, const double *__restrict__ lambda, int inv_sqrt,
+                                                             double *__restrict__ dst) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)rows * cols; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e % rows, k = e / rows;
+    const int c = order[k0 + (int)k];
+    const double f = inv_sqrt ? 1.0 / sqrt(lambda[c]) : 1.0;
+    dst[e] = f * src[r + (size_t)rows * c];
+  }
+}
+
+// out = sum_i coef[i] * vec[slot[i]]  (count elements each; coef and slot on the device, oldest first)
+__global__ void __launch_bounds__(256) lincomb_kernel(const double *__restrict__ vecs, size_t count, const double *__restrict__ coef,
+                                                      const int *__restrict__ slots, int n_terms, double *__restrict__ out) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int i = 0; i < n_terms; ++i) acc = acc + coef[i] * vecs[(size_t)slots[i] * count + e];
+    out[e] = acc;
+  }
+}
+
+static unsigned grid_for(size_t count) {
+  size_t b = (count + 255) / 256;
+  return (unsigned)(b > 148 * 8 ? 148 * 8 : (b < 1 ? 1 : b));
+}
+
+void launch_scf_guess(const double *d_h, const double *d_s, int n, bool gwh, double *d_f, cudaStream_t s) {
+  scf_guess_kernel<<<grid_for((size_t)n * n), 256, 0, s>>>(d_h, d_s, n, gwh ? 1 : 0, d_f);
+}
+void launch_antisym(const double *d_a, int n, double *d_out, cudaStream_t s) {
+  antisym_kernel<<<grid_for((size_t)n * n), 256, 0, s>>>(d_a, n, d_out);
+}
+void launch_symmetrize_shift(double *d_g, int m, const double *d_shift, cudaStream_t s) {
+  symmetrize_shift_kernel<<<grid_for((size_t)m * m), 256, 0, s>>>(d_g, m, d_shift);
+}
+void launch_reduce(const double *d_a, const double *d_b, size_t count, int mode, double *d_scratch, double *d_out, cudaStream_t s) {
+  unsigned blocks = (unsigned)((count + 4095) / 4096);
+  if (blocks > 128) blocks = 128;
+  if (blocks < 1) blocks = 1;
+  reduce_kernel<<<blocks, 256, 0, s>>>(d_a, d_b, count, mode, d_scratch, d_out);
+}
+void launch_eig_lambda(const double *d_g, const double *d_v, int m, const double *d_shift, double *d_lambda, cudaStream_t s) {
+  eig_lambda_kernel<<<m, 256, 0, s>>>(d_g, d_v, m, d_shift, d_lambda);
+}
+void launch_rank_sort(const double *d_lambda, int m, double threshold, int *d_order, int *d_n_dropped, cudaStream_t s) {
+  rank_sort_kernel<<<(m + 255) / 256, 256, 0, s>>>(d_lambda, m, threshold, d_order, d_n_dropped);
+}
+void launch_gather_columns(const double *d_src, int rows, const int *d_order, int k0, int cols, const double *d_lambda,
+                           bool inv_sqrt, double *d_dst, cudaStream_t s) {
+  if (cols <= 0) return;
+  gather_columns_kernel<<<grid_for((size_t)rows * cols), 256, 0, s>>>(d_src, rows, d_order, k0, cols, d_lambda, inv_sqrt ? 1 : 0, d_dst);
+}
+void launch_lincomb(const double *d_vecs, size_t count, const double *d_coef, const int *d_slots, int n_terms, double *d_out,
+                    cudaStream_t s) {
+  lincomb_kernel<<<grid_for(count), 256, 0, s>>>(d_vecs, count, d_coef, d_slots, n_terms, d_out);
+}
+
+}  // namespace mqcb200

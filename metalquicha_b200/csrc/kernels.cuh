@@ -133,6 +133,19 @@ void launch_unpack_tensor(const double *d_packed, int n, int q_count, double *d_
 void launch_gradient_gamma(const double *d_rho, const double *d_density, const double *d_z, double w, int n, int p_count,
                            bool accumulate, double *d_gamma, cudaStream_t s);
 
+// ---- pieces of the general-size device-resident SCF step (gemm_kernels.cu) ----------------
+void launch_scf_guess(const double *d_h, const double *d_s, int n, bool gwh, double *d_f, cudaStream_t s);
+void launch_antisym(const double *d_a, int n, double *d_out, cudaStream_t s);                       // out = a - a^T
+void launch_symmetrize_shift(double *d_g, int m, const double *d_shift, cudaStream_t s);           // g = (g+g^T)/2 + shift*1
+// mode 0: sum a*b, 1: sum (a-b)^2, 2: sqrt(sum a*a); fixed order; d_scratch: 130 doubles, zeroed once
+void launch_reduce(const double *d_a, const double *d_b, size_t count, int mode, double *d_scratch, double *d_out, cudaStream_t s);
+void launch_eig_lambda(const double *d_g, const double *d_v, int m, const double *d_shift, double *d_lambda, cudaStream_t s);
+void launch_rank_sort(const double *d_lambda, int m, double threshold, int *d_order, int *d_n_dropped, cudaStream_t s);
+void launch_gather_columns(const double *d_src, int rows, const int *d_order, int k0, int cols, const double *d_lambda,
+                           bool inv_sqrt, double *d_dst, cudaStream_t s);
+void launch_lincomb(const double *d_vecs, size_t count, const double *d_coef, const int *d_slots, int n_terms, double *d_out,
+                    cudaStream_t s);
+
 // ---- device-resident SCF step for fragment-sized problems (scf_kernels.cu) ---------------
 struct ScfStepLaunch {
   int batch = 1;                 // fragments: one CTA each, every pointer below moving on by block_stride doubles

@@ -360,9 +360,16 @@ class B200FockEngine:
                                                           c_double(1.0 if k_scale is None else k_scale), _ptr(g)))
         return g
 
+    def run_scf(self, h, s, n_electrons: int, **kw) -> dict:
+        """``run_libcint_rhf``'s loop on the GPU for any size (``mqcb200_scf``): the one-CTA fragment
+        route when it fits, the general kernels + batched GEMM + one-sided Jacobi otherwise; also for a
+        tensor sharded over GPUs.  Same arguments and result as :meth:`run_scf_fragment`."""
+        return self.run_scf_fragment(h, s, n_electrons, _entry="mqcb200_scf", **kw)
+
     def run_scf_fragment(self, h, s, n_electrons: int, max_iter: int = 100, energy_tol: float = 1e-10,
                          density_tol: float = 1e-8, diis_vectors: int = 8, guess: str = "gwh", k_scale=None,
-                         e_nuc: float = 0.0, slot: int = SLOT_FULL_RANGE, check_every: int = 1) -> dict:
+                         e_nuc: float = 0.0, slot: int = SLOT_FULL_RANGE, check_every: int = 1,
+                         _entry: str = "mqcb200_scf_fragment") -> dict:
         """``run_libcint_rhf`` (mqc_libcint_rhf.f90:321-680) on the resident tensor with the SCF
         step on the GPU (fragment-sized problems, n <= 80).  Returns the fields of the reference's
         ``rhf_result_t`` (:117-141): energy, electronic, nuclear_repulsion, iterations, converged,
@@ -379,7 +386,7 @@ class B200FockEngine:
         eps = np.zeros(n)
         density = np.empty((n, n), order="F")
         hist = np.zeros(max_iter)
-        _check(self._lib.mqcb200_scf_fragment(
+        _check(getattr(self._lib, _entry)(
             self._h, slot, _ptr(h), _ptr(s), int(n_electrons), {"core": 0, "gwh": 1}[guess], int(max_iter),
             c_double(energy_tol), c_double(density_tol), int(diis_vectors),
             c_double(1.0 if k_scale is None else k_scale), byref(e_el), byref(it), byref(conv), byref(n_mo),

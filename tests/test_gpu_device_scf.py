@@ -158,3 +158,57 @@ def test_batch_refusals(engine):
     bad = np.zeros_like(s); bad[0, 0] = 1.0
     out = engine.run_scf_fragment_batch(np.stack([h, h, h]), np.stack([s, bad, s]), 2 * n_occ)
     assert list(out["converged"]) == [1, -1, 1]
+
+
+# ---- the general-size route of mqcb200_scf (n > 80 or n_occ > 64): general Fock-build kernels, batched DMMA
+# GEMM for the dense algebra, one-sided Jacobi on the shifted F' in place of dsyev
+@pytest.mark.parametrize("n,n_occ,naux,kw", [
+    (96, 20, 80, {}),
+    (130, 70, 60, {"k_scale": 0.2}),                      # n_occ > 64
+    (150, 33, 90, {"guess": "core", "diis_vectors": 4}),
+    (97, 11, 50, {"diis_vectors": 0, "max_iter": 80, "coupling": 0.1}),   # odd n, plain iteration
+])
+def test_general_size_device_scf_matches_the_oracle_scf(engine, n, n_occ, naux, kw):
+    kw = dict(kw)
+    s, h, b = _synthetic_fragment(7000 + n, n, n_occ, naux, coupling=kw.pop("coupling", 0.3))
+    engine.set_tensor(b)
+    dev = engine.run_scf(h, s, 2 * n_occ, **kw)
+    ref, hist = _oracle_scf(h, s, b, 2 * n_occ, **kw)
+    _compare(dev, ref, hist)
+    c = dev["orbitals"]
+    assert np.max(np.abs(c.T @ s @ c - np.eye(c.shape[1]))) <= 1e-9
+    again = engine.run_scf(h, s, 2 * n_occ, **kw)
+    assert again["electronic"] == dev["electronic"] and np.array_equal(again["density"], dev["density"])
+
+
+def test_general_size_route_on_real_integrals_and_dispatch(engine):
+    """Water/STO-3G padded to n = 96 runs the general route to the reference-held energy; at n = 7 mqcb200_scf
+    dispatches to the one-CTA route and gives what mqcb200_scf_fragment gives."""
+    symbols, coords, n_electrons, e_ref = gto.H2O_STO3G
+    s0, h0, eri, e_nuc = gto.molecule_integrals(symbols, coords)
+    b0 = scf.exact_fit_tensor(eri)
+    n0, n, naux = h0.shape[0], 96, b0.shape[1]
+    s_p, h_p = np.eye(n), 1.0e3 * np.eye(n)
+    s_p[:n0, :n0], h_p[:n0, :n0] = s0, h0
+    b_p = np.zeros((n * n, naux), order="F")
+    for p in range(naux):
+        slab = np.zeros((n, n)); slab[:n0, :n0] = b0[:, p].reshape(n0, n0, order="F")
+        b_p[:, p] = slab.reshape(n * n, order="F")
+    engine.set_tensor(b_p)
+    dev = engine.run_scf(h_p, s_p, n_electrons, e_nuc=e_nuc)
+    assert dev["converged"] and abs(dev["energy"] - e_ref) < TOL_E          # validation/check_rhf.f90:152
+    engine.set_tensor(b0)
+    small = engine.run_scf(h0, s0, n_electrons, e_nuc=e_nuc)
+    frag = engine.run_scf_fragment(h0, s0, n_electrons, e_nuc=e_nuc)
+    assert small["electronic"] == frag["electronic"] and small["iterations"] == frag["iterations"]
+    assert abs(small["energy"] - e_ref) < TOL_E
+
+
+def test_general_size_linear_dependence(engine):
+    n, n_occ, naux = 100, 12, 40
+    s, h, b = _synthetic_fragment(88, n, n_occ, naux, null_mode=True)
+    engine.set_tensor(b)
+    dev = engine.run_scf(h, s, 2 * n_occ)
+    ref, hist = _oracle_scf(h, s, b, 2 * n_occ)
+    assert dev["orbitals"].shape == (n, n - 1) and ref["orbitals"].shape == (n, n - 1)
+    _compare(dev, ref, hist, tol=1e-8)

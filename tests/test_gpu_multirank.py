@@ -58,8 +58,25 @@ for i, (nu0, nu1) in enumerate(zip(edges[:-1], edges[1:])):
 eng.whiten_end()
 f4 = eng.build_fock_df(hw, dw, cw, 12)
 err4 = float(np.max(np.abs(f4 - oracle.build_fock_df(hw, bw, dw, cw, 12))))
-ok = err <= 1e-10 and errjk <= 1e-10 and err3 <= 1e-10 and err4 <= 1e-10 * max(1.0, float(np.max(np.abs(f4)))) and same and np.array_equal(f, f2)
-print(f"rank {rank}: err={err:.2e} errjk={errjk:.2e} err3={err3:.2e} whiten={err4:.2e} same_across_ranks={same} repeat={np.array_equal(f, f2)}", flush=True)
+# the device-resident SCF on a SHARDED tensor: every rank runs the same step around the exchanged Fock matrix
+from oracle import scf_oracle
+ns, nos, nauxs = 110, 14, 70
+rng = np.random.default_rng(3)
+a_ = rng.standard_normal((ns, ns)) * (0.15 / np.sqrt(ns)); s_ = np.asfortranarray(np.eye(ns) + a_ + a_.T)
+h_ = np.asfortranarray(synth.synth_core_hamiltonian(3, ns) - 2.0 * np.diag(np.linspace(1.0, 0.0, ns)))
+b_ = np.asfortranarray(0.3 * synth.synth_tensor(3, ns, nauxs))
+sb.set_tensor(b_, ns, nauxs)
+res = eng.run_scf(h_, s_, 2 * nos)
+def fb(hh, dd, cc, no):
+    ff = oracle.build_fock_df(hh, b_, dd, cc, no)
+    return ff, oracle.electronic_energy(hh, ff, dd)
+ref_scf = scf_oracle.run_rhf(h_, s_, 2 * nos, fb)
+err5 = abs(res["electronic"] - ref_scf["electronic"])
+energies = [None] * world
+dist.all_gather_object(energies, res["electronic"])
+scf_ok = res["converged"] and res["iterations"] == ref_scf["iterations"] and err5 <= 1e-9 and all(x == energies[0] for x in energies)
+ok = err <= 1e-10 and errjk <= 1e-10 and err3 <= 1e-10 and err4 <= 1e-10 * max(1.0, float(np.max(np.abs(f4)))) and same and np.array_equal(f, f2) and scf_ok
+print(f"rank {rank}: err={err:.2e} errjk={errjk:.2e} err3={err3:.2e} whiten={err4:.2e} scf={err5:.2e}/{scf_ok} same_across_ranks={same} repeat={np.array_equal(f, f2)}", flush=True)
 eng.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

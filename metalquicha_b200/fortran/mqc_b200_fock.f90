@@ -325,7 +325,7 @@ contains
 
    subroutine b200_run_rhf_fragment(h, overlap, nelec, max_iter, energy_tol, density_tol, electronic, iterations, &
                                     converged, orbitals, orbital_energies, density, error, diis_vectors, k_scale)
-      !! run_libcint_rhf's loop (mqc_libcint_rhf.f90:566-649) for a fragment-sized problem with every
+      !! run_libcint_rhf's loop (mqc_libcint_rhf.f90:566-649) with every
       !! matrix staying on the GPU: H, S and the resident tensor in, the converged SCF out
       real(dp), intent(in), contiguous :: h(:, :), overlap(:, :)
       integer, intent(in) :: nelec, max_iter
@@ -348,7 +348,8 @@ contains
       converged = .false.
       if (.not. operands_match_tensor(MQCB200_SLOT_FULL_RANGE, size(h, 1), error)) return
       allocate (history(max_iter))
-      if (mqcb200_scf_fragment(shared_handle, MQCB200_SLOT_FULL_RANGE, h, overlap, int(nelec, c_int), 1_c_int, &
+      ! mqcb200_scf: the one-CTA route for fragment-sized problems, the general kernels beyond (any nao, sharded tensors too)
+      if (mqcb200_scf(shared_handle, MQCB200_SLOT_FULL_RANGE, h, overlap, int(nelec, c_int), 1_c_int, &
                                int(max_iter, c_int), energy_tol, density_tol, diis, kf, e, it, conv, n_mo, &
                                orbitals, orbital_energies, density, history) /= MQCB200_OK) then
          call engine_failure("b200: scf_fragment", error)

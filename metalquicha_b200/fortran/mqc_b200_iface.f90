@@ -28,7 +28,7 @@ module mqc_b200_iface
    public :: mqcb200_comm_unique_id, mqcb200_comm_init, mqcb200_comm_destroy
    public :: mqcb200_queue_create, mqcb200_queue_pop, mqcb200_queue_is_empty, mqcb200_queue_destroy
    public :: mqcb200_tensor_shape, mqcb200_response_operator, mqcb200_fitted_potential_general
-   public :: mqcb200_scf_fragment, mqcb200_scf_fragment_batch, mqcb200_df_gradient_densities
+   public :: mqcb200_scf, mqcb200_scf_fragment, mqcb200_scf_fragment_batch, mqcb200_df_gradient_densities
    public :: mqcb200_metric_inverse_sqrt, mqcb200_build_df_tensor
    public :: mqcb200_whiten_begin, mqcb200_whiten_push, mqcb200_whiten_end
    public :: MQCB200_OK, MQCB200_FAIL, MQCB200_BAD_HANDLE
@@ -304,6 +304,20 @@ module mqc_b200_iface
          real(c_double), intent(out) :: e_electronic(*)
          integer(c_int), intent(out) :: iterations(*), converged(*), n_mo(*)
          real(c_double), intent(out) :: coeff_all(*), orbital_energies_all(*), density_all(*)
+         integer(c_int) :: status
+      end function
+      function mqcb200_scf(handle, slot, hcore, overlap, n_electrons, guess, max_iter, energy_tol, &
+                           density_tol, diis_vectors, k_scale, e_electronic, iterations, converged, &
+                           n_mo, coeff, orbital_energies, density, e_history) &
+         bind(C, name="mqcb200_scf") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot, n_electrons, guess, max_iter, diis_vectors
+         real(c_double), intent(in) :: hcore(*), overlap(*)
+         real(c_double), value :: energy_tol, density_tol, k_scale
+         real(c_double), intent(out) :: e_electronic
+         integer(c_int), intent(out) :: iterations, converged, n_mo
+         real(c_double), intent(out) :: coeff(*), orbital_energies(*), density(*), e_history(*)
          integer(c_int) :: status
       end function
    end interface

@@ -271,6 +271,15 @@ static bool fragment_path_enabled() {
   return v == 1;
 }
 
+static bool use_cooperative_jacobi() {
+  static int v = -1;
+  if (v < 0) {
+    const char *env = getenv("MQCB200_JACOBI_PER_ROUND");   // development switch: one kernel per round instead
+    v = (env && env[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool fuse_gamma_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1295,7 +1304,7 @@ static void scf_general(Engine *e, const ScfArgs &a) {
   const size_t o_g = take(nn), o_v = take(nn), o_w0 = take(nn), o_w1 = take(nn), o_lam = take(n), o_eps = take(n);
   const size_t o_df = take((size_t)std::max(dmax, 1) * nn), o_de = take((size_t)std::max(dmax, 1) * nn);
   const size_t o_bm = take(16), o_coef = take(16), o_scal = take(16), o_scr = take(130);
-  const size_t o_order = take((size_t)n / 2 + 2), o_slots = take(8), o_flags = take(2);
+  const size_t o_order = take((size_t)n / 2 + 2), o_slots = take(8), o_flags = take(4);
   try {
     blk.ensure(off * sizeof(double));
     double *b = blk.d();
@@ -1303,7 +1312,7 @@ static void scf_general(Engine *e, const ScfArgs &a) {
     double *d_g = b + o_g, *d_v = b + o_v, *d_w0 = b + o_w0, *d_w1 = b + o_w1, *d_lam = b + o_lam, *d_eps = b + o_eps;
     double *d_df = b + o_df, *d_de = b + o_de, *d_bm = b + o_bm, *d_coef = b + o_coef, *d_scal = b + o_scal, *d_scr = b + o_scr;
     int *d_order = reinterpret_cast<int *>(b + o_order), *d_slots = reinterpret_cast<int *>(b + o_slots);
-    int *d_flag = reinterpret_cast<int *>(b + o_flags), *d_ndrop = d_flag + 1;
+    int *d_flag = reinterpret_cast<int *>(b + o_flags), *d_ndrop = d_flag + 2;   // d_flag[0..1]: the eigensolver's state
     CUDA_CHECK(cudaMemsetAsync(b, 0, off * sizeof(double), st));
     CUDA_CHECK(cudaMemcpyAsync(d_h, a.h, nn * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(d_s, a.s, nn * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1318,6 +1327,11 @@ static void scf_general(Engine *e, const ScfArgs &a) {
       launch_set_identity(d_v, m, st);
       const int m_e = (m + 1) & ~1;
       last_sweeps = 0;
+      if (use_cooperative_jacobi() && launch_hestenes_solve(d_g, d_v, m, 60, d_flag, st)) {
+        total_launches += 1;                              // no host synchronisation: the flag and the sweeps stay on the device
+        return;
+      }
+      cudaGetLastError();
       for (int sweep = 0; sweep < 60; ++sweep) {
         ++last_sweeps;
         CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
@@ -1729,7 +1743,7 @@ static int metric_inverse_sqrt_device(Engine *e, int naux, const double *metric_
     d_s.ensure(qq * sizeof(double));
     d_misc.ensure((size_t)naux * sizeof(double) + 64);
     int *d_flag = reinterpret_cast<int *>(static_cast<char *>(d_misc.ptr) + (size_t)naux * sizeof(double));
-    int *d_kept = d_flag + 1;
+    int *d_kept = d_flag + 2;                     // d_flag[0..1]: rotation flag and sweep count of the eigensolver
     cudaEvent_t t0, t1;
     CUDA_CHECK(cudaEventCreate(&t0));
     CUDA_CHECK(cudaEventCreate(&t1));
@@ -1738,15 +1752,23 @@ static int metric_inverse_sqrt_device(Engine *e, int naux, const double *metric_
     launch_set_identity(d_v.d(), naux, e->stream);
     const int n_e = (naux + 1) & ~1;
     int sweeps = 0;
-    for (int sweep = 0; sweep < 60; ++sweep) {
-      ++sweeps;
-      CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), e->stream));
-      for (int r = 0; r < n_e - 1; ++r) launch_hestenes_round(d_g.d(), d_v.d(), naux, r, d_flag, e->stream);
-      int rotated = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&rotated, d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (use_cooperative_jacobi() && launch_hestenes_solve(d_g.d(), d_v.d(), naux, 60, d_flag, e->stream)) {
+      int st2[2] = {0, 0};
+      CUDA_CHECK(cudaMemcpyAsync(st2, d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
       CUDA_CHECK(cudaStreamSynchronize(e->stream));
-      CUDA_CHECK(cudaGetLastError());
-      if (!rotated) break;
+      sweeps = st2[1];
+    } else {
+      cudaGetLastError();
+      for (int sweep = 0; sweep < 60; ++sweep) {
+        ++sweeps;
+        CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), e->stream));
+        for (int r = 0; r < n_e - 1; ++r) launch_hestenes_round(d_g.d(), d_v.d(), naux, r, d_flag, e->stream);
+        int rotated = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&rotated, d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        CUDA_CHECK(cudaGetLastError());
+        if (!rotated) break;
+      }
     }
     CUDA_CHECK(cudaMemsetAsync(d_kept, 0, sizeof(int), e->stream));
     launch_metric_scale(d_g.d(), d_v.d(), naux, threshold, d_s.d(), static_cast<double *>(d_misc.ptr), d_kept, e->stream);

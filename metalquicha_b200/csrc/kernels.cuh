@@ -61,6 +61,9 @@ void launch_whiten_slab(const double *d_af, int m_rows, int naux, const double *
                         const WhitenDst &dst, cudaStream_t s);
 // metric^(-1/2) pieces: one round of one-sided Jacobi on the columns of g (and v); identity; scaling by lambda^-1/2
 void launch_hestenes_round(double *d_g, double *d_v, int n, int round, int *d_rotated, cudaStream_t s);
+// The whole iteration (all rounds, all sweeps, convergence test) in one cooperative launch; d_state: 2 ints
+// ([1] receives the sweep count).  False when the device cannot launch cooperatively: use the per-round kernels.
+bool launch_hestenes_solve(double *d_g, double *d_v, int n, int max_sweeps, int *d_state, cudaStream_t s);
 void launch_set_identity(double *d_v, int n, cudaStream_t s);
 void launch_metric_scale(const double *d_g, const double *d_v, int n, double threshold, double *d_scaled, double *d_lambda,
                          int *d_n_kept, cudaStream_t s);

@@ -26,6 +26,7 @@
 #include "kernels.cuh"
 
 #include <cmath>
+#include <cooperative_groups.h>
 
 namespace mqcb200 {
 
@@ -287,6 +288,79 @@ __global__ void __launch_bounds__(256) hestenes_round_kernel(double *__restrict_
   }
 }
 
+// The whole iteration in ONE cooperative launch: every round is followed by a grid-wide barrier instead
+// of a kernel boundary, and the "did this sweep rotate anything?" test stays on the device -- no host
+// synchronisation inside an eigensolve.  A CTA takes the pairs k = blockIdx.x, += gridDim.x.
+// state[0]: rotation flag of the current sweep, state[1]: sweeps done (written at the end).
+__global__ void __launch_bounds__(256) hestenes_solve_kernel(double *__restrict__ g, double *__restrict__ v, int n,
+                                                             double tol, int max_sweeps, int *__restrict__ state) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const int n_e = (n + 1) & ~1, half = n_e / 2;
+  __shared__ double red[3][8];
+  __shared__ double cs[2];
+  int sweeps = 0;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    ++sweeps;
+    if (blockIdx.x == 0 && threadIdx.x == 0) state[0] = 0;
+    grid.sync();
+    for (int round = 0; round < n_e - 1; ++round) {
+      for (int k = blockIdx.x; k < half; k += gridDim.x) {
+        const int pa = k == 0 ? 0 : 1 + (k - 1 + round) % (n_e - 1);
+        const int pb = 1 + (n_e - 2 - k + round) % (n_e - 1);
+        const int p = pa < pb ? pa : pb, q = pa < pb ? pb : pa;
+        if (q >= n) continue;                                   // (uniform per CTA)
+        double *gp = g + (size_t)p * n, *gq = g + (size_t)q * n;
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int i = threadIdx.x; i < n; i += 256) {
+          const double x = gp[i], y = gq[i];
+          a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+          c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        __syncthreads();                                        // the previous pair's readers of red/cs are done
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; red[2][threadIdx.x >> 5] = c; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double al = 0.0, be = 0.0, ga = 0.0;
+          for (int w = 0; w < 8; ++w) { al += red[0][w]; be += red[1][w]; ga += red[2][w]; }
+          double cc = 1.0, ss = 0.0;
+          if (fabs(ga) > tol * sqrt(al * be) && fabs(ga) > 0.0) {
+            const double d = be - al;
+            const double num = d >= 0.0 ? 2.0 * ga : -2.0 * ga;
+            const double t = num / (fabs(d) + sqrt(fma(d, d, 4.0 * ga * ga)));
+            cc = rsqrt(fma(t, t, 1.0));
+            ss = t * cc;
+            state[0] = 1;
+          }
+          cs[0] = cc; cs[1] = ss;
+        }
+        __syncthreads();
+        const double cc = cs[0], ss = cs[1];
+        if (ss != 0.0) {
+          double *vp = v + (size_t)p * n, *vq = v + (size_t)q * n;
+          for (int i = threadIdx.x; i < n; i += 256) {
+            const double x = gp[i], y = gq[i];
+            gp[i] = cc * x - ss * y;
+            gq[i] = ss * x + cc * y;
+            const double u = vp[i], w = vq[i];
+            vp[i] = cc * u - ss * w;
+            vq[i] = ss * u + cc * w;
+          }
+        }
+      }
+      grid.sync();
+    }
+    const int rotated = *reinterpret_cast<volatile int *>(state);
+    grid.sync();                                                // everyone has read the flag before the next sweep clears it
+    if (!rotated) break;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) state[1] = sweeps;
+}
+
 __global__ void __launch_bounds__(256) set_identity_kernel(double *__restrict__ v, int n) {
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)n * n; e += (size_t)gridDim.x * blockDim.x)
     v[e] = (e % n) == (e / n) ? 1.0 : 0.0;
@@ -320,6 +394,32 @@ void launch_hestenes_round(double *d_g, double *d_v, int n, int round, int *d_ro
   const int n_e = (n + 1) & ~1;
   const double tol = 4.0 * 1.1102230246251565e-16 * sqrt((double)(n > 16 ? n : 16));
   hestenes_round_kernel<<<n_e / 2, 256, 0, s>>>(d_g, d_v, n, round, d_rotated, tol);
+}
+
+// Returns false when a cooperative launch is not possible (the caller then falls back to one kernel per round).
+bool launch_hestenes_solve(double *d_g, double *d_v, int n, int max_sweeps, int *d_state, cudaStream_t s) {
+  static int max_blocks = -1;
+  if (max_blocks < 0) {
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hestenes_solve_kernel, 256, 0);
+    max_blocks = coop ? sms * per_sm : 0;
+  }
+  if (max_blocks <= 0) return false;
+  const int n_e = (n + 1) & ~1;
+  // One CTA per pair.  Measured (B200): the grid-wide barrier costs more the more CTAs take part -- at 344 pairs
+  // (n = 688) a round is ~7 us against ~9 us for a kernel per round, at 900 pairs (n = 1800) ~18 us against ~14 us;
+  // a warp per pair (57 CTAs) was twice slower still (the pair's column walk is then one warp's latency chain).
+  // So: one cooperative launch up to 512 pairs, one kernel per round beyond.
+  if (n_e / 2 > 512 || n_e / 2 > max_blocks) return false;
+  int blocks = n_e / 2;
+  if (blocks < 1) blocks = 1;
+  double tol = 4.0 * 1.1102230246251565e-16 * sqrt((double)(n > 16 ? n : 16));
+  void *args[] = {&d_g, &d_v, &n, &tol, &max_sweeps, &d_state};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(hestenes_solve_kernel), dim3((unsigned)blocks), dim3(256), args, 0, s) ==
+         cudaSuccess;
 }
 
 void launch_set_identity(double *d_v, int n, cudaStream_t s) {

@@ -1736,6 +1736,7 @@ static int metric_inverse_sqrt_device(Engine *e, int naux, const double *metric_
   if (naux <= 0 || !metric_host) throw Failure("mqcb200: bad metric");
   const size_t qq = (size_t)naux * naux;
   DevBuf d_g, d_v, d_s, d_misc;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
   int kept = 0;
   try {
     d_g.ensure(qq * sizeof(double));
@@ -1744,7 +1745,6 @@ static int metric_inverse_sqrt_device(Engine *e, int naux, const double *metric_
     d_misc.ensure((size_t)naux * sizeof(double) + 64);
     int *d_flag = reinterpret_cast<int *>(static_cast<char *>(d_misc.ptr) + (size_t)naux * sizeof(double));
     int *d_kept = d_flag + 2;                     // d_flag[0..1]: rotation flag and sweep count of the eigensolver
-    cudaEvent_t t0, t1;
     CUDA_CHECK(cudaEventCreate(&t0));
     CUDA_CHECK(cudaEventCreate(&t1));
     CUDA_CHECK(cudaMemcpyAsync(d_g.ptr, metric_host, qq * sizeof(double), cudaMemcpyHostToDevice, e->stream));
@@ -1780,14 +1780,16 @@ static int metric_inverse_sqrt_device(Engine *e, int naux, const double *metric_
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, t0, t1);
-    cudaEventDestroy(t0);
-    cudaEventDestroy(t1);
     e->metric_ms = ms;
     e->metric_sweeps = sweeps;
   } catch (...) {
+    if (t0) cudaEventDestroy(t0);
+    if (t1) cudaEventDestroy(t1);
     d_g.release(); d_v.release(); d_s.release(); d_misc.release();
     throw;
   }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
   d_g.release(); d_v.release(); d_s.release(); d_misc.release();
   if (kept == 0) throw Failure("density fitting: the auxiliary metric is singular");      // integrals.F90:1015-1019
   return kept;

@@ -29,6 +29,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 namespace mqcb200 {
 
@@ -52,7 +53,8 @@ template <int NB>
 __global__ void __launch_bounds__(K_THREADS, 1)
 k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, int q_count,
                         const double *__restrict__ ctf, int nib, int n_ntiles, double *__restrict__ x, int nkc,
-                        int nmb, const double *__restrict__ cep, double *__restrict__ gamma_part) {
+                        int nmb, const double *__restrict__ cep, double *__restrict__ gamma_part, int n_full,
+                        int tail_split, int trim_last) {
   using Cfg = HalfCfg<NB>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stage_base = reinterpret_cast<double *>(smem_raw);
@@ -64,7 +66,30 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
   // costs two of the 168 registers this kernel is launched with
   const int total_rows = q_count * nt;                          // flattened (Q, tile-row)
   const int n_groups = (total_rows + K_SLOTS - 1) / K_SLOTS;
-  const int n_work = n_groups * n_ntiles;
+  const int n_units = n_groups * n_ntiles;
+  // The last, partly filled round of the round-robin walk is cut finer: units from n_full on are
+  // dealt as tail_split (2 or 4) pieces -- by warp column, then by the warp's slot -- to CTAs that
+  // would otherwise idle.  A piece runs the same DMMA sequence on its share of the accumulators, so
+  // X and the gamma partials keep their bits whatever the split.
+  const int n_work = n_full + (n_units - n_full) * tail_split;
+  // unit -> (row group, N tile).  The N tile is rotated by the round the group falls in, so that a CTA
+  // meets every N tile in turn: the last one is cheaper when its padding block is trimmed (trim_last),
+  // and a fixed tile per CTA would leave that saving as idle time at the end.
+  const int groups_per_round = (int)gridDim.x / n_ntiles > 0 ? (int)gridDim.x / n_ntiles : 1;
+  auto coords = [&](int unit, int &group, int &ntile) {
+    group = unit / n_ntiles;
+    ntile = (unit % n_ntiles + group / groups_per_round) % n_ntiles;
+  };
+  auto decode = [&](int work, int &unit, int &part_wn, int &part_sl) {
+    unit = work; part_wn = -1; part_sl = -1;
+    if (work >= n_full) {
+      const int r = work - n_full;
+      unit = n_full + r / tail_split;
+      const int p = r % tail_split;
+      part_wn = p & 1;
+      part_sl = tail_split == 4 ? (p >> 1) : -1;
+    }
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -79,11 +104,17 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
     reg_dealloc_producer();
     if (warp != K_CONSUMER_WARPS) return;
     // ===== TMA producer warp: lanes 0..7 own one slot each, lane 8 owns the C operand =====
-    constexpr uint32_t stage_bytes = (uint32_t)(Cfg::kAElems + Cfg::kBElems) * sizeof(double);
     uint32_t it = 0;                                            // ring position, continuous over tiles
     for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
-      const int f0 = (work / n_ntiles) * K_SLOTS;
-      const int ib0 = (work % n_ntiles) * (2 * NB);
+      int unit, part_wn, part_sl;
+      decode(work, unit, part_wn, part_sl);
+      int group, ntile;
+      coords(unit, group, ntile);
+      const int f0 = group * K_SLOTS;
+      const int ib0 = ntile * (2 * NB);
+      // a piece that owns one slot per warp needs only those four rows of the tensor
+      const bool load_slot = part_sl < 0 || (lane & 1) == part_sl;
+      const uint32_t stage_bytes = (uint32_t)((part_sl < 0 ? Cfg::kAElems : Cfg::kAElems / 2) + Cfg::kBElems) * sizeof(double);
       // slots past the end of the tensor re-load the last row; their results are not stored
       int f = f0 + lane;
       if (f > total_rows - 1) f = total_rows - 1;
@@ -98,7 +129,8 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
         __syncwarp();
         if (lane < K_SLOTS) {
           const int a = tr > kc ? tr : kc, b = tr > kc ? kc : tr;
-          tma_load_1d(a_s + lane * TILE_ELEMS, row + (size_t)tile_index(a, b, nt) * TILE_ELEMS,
+          if (load_slot)
+            tma_load_1d(a_s + lane * TILE_ELEMS, row + (size_t)tile_index(a, b, nt) * TILE_ELEMS,
                       TILE_ELEMS * sizeof(double), &full_bar[st]);
         } else if (lane == K_SLOTS) {
           tma_load_1d(a_s + Cfg::kAElems, ctf + ((size_t)kc * nib + ib0) * 128, Cfg::kBElems * sizeof(double),
@@ -146,9 +178,20 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
     load_frags(fa[0], fb[0], 0, 0, false, false);
   }
 
-  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
-    const int f0 = (work / n_ntiles) * K_SLOTS;
-    const int ib0 = (work % n_ntiles) * (2 * NB);
+  // One work item.  MODE 0: the warp's whole share (both 16-row slots); 1 / 2: slot 0 / slot 1 only;
+  // 3: nothing -- the warp only walks the ring, so the stage protocol is the same for whole units and
+  // pieces.  The modes are compile-time: a predicated-off DMMA still takes its turn in the pipe.
+  // NBW: n8-blocks of this warp -- NB, or NB - 1 for the right-hand warp column of the last N tile when the
+  // occupied range ends at least eight columns short of the padded width (trim_last): that block would
+  // multiply zeros, and the accumulation never reads its columns (ks_last).
+  auto run_item = [&](auto mode_tag, auto nbw_tag, int work, int unit) {
+    constexpr int MODE = decltype(mode_tag)::value;
+    constexpr int NBW = decltype(nbw_tag)::value;
+    constexpr int SL0 = MODE == 2 ? 1 : 0, SL1 = MODE == 0 ? 2 : (MODE == 3 ? 0 : SL0 + 1);   // slots [SL0, SL1)
+    int group, ntile;
+    coords(unit, group, ntile);
+    const int f0 = group * K_SLOTS;
+    const int ib0 = ntile * (2 * NB);
     const bool more_work = work + (int)gridDim.x < n_work;
     // the two 16-row slots of this warp
     int tr_s[2], q_s[2];
@@ -162,11 +205,11 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
       tr_s[sl] = f % nt;
     }
 
-    double acc[4][NB][2];
+    double acc[4][NBW][2];
 #pragma unroll
     for (int m = 0; m < 4; ++m)
 #pragma unroll
-      for (int j = 0; j < NB; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
+      for (int j = 0; j < NBW; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
 
     for (int kc = 0; kc < nt; ++kc, ++it) {
       const int st = it % Cfg::kStages;
@@ -174,31 +217,32 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         if (ks < 3) {
-          load_frags(fa[(ks + 1) & 1], fb[(ks + 1) & 1], st, ks + 1, tp0, tp1);
+          if (MODE != 3) load_frags(fa[(ks + 1) & 1], fb[(ks + 1) & 1], st, ks + 1, tp0, tp1);
         } else if (kc + 1 < nt || more_work) {
           const uint32_t it1 = it + 1;
           const int st1 = it1 % Cfg::kStages;
           mbar_wait(&full_bar[st1], (it1 / Cfg::kStages) & 1);
           const bool in_tile = kc + 1 < nt;                    // the next tile starts at kc = 0: direct
-          load_frags(fa[0], fb[0], st1, 0, in_tile && tr_s[0] < kc + 1, in_tile && tr_s[1] < kc + 1);
+          if (MODE != 3 || !in_tile)
+            load_frags(fa[0], fb[0], st1, 0, in_tile && tr_s[0] < kc + 1, in_tile && tr_s[1] < kc + 1);
         }
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+        for (int m = 2 * SL0; m < 2 * SL1; ++m)
 #pragma unroll
-          for (int j = 0; j < NB; ++j) dmma884(acc[m][j][0], acc[m][j][1], fa[ks & 1][m], fb[ks & 1][j]);
+          for (int j = 0; j < NBW; ++j) dmma884(acc[m][j][0], acc[m][j][1], fa[ks & 1][m], fb[ks & 1][j]);
       }
       release_stage(&empty_bar[st], lane);
     }
 
     // epilogue: X[q][kc_out][mb][ks_out][g*4 + t_out], two adjacent i per thread (16-byte stores)
 #pragma unroll
-    for (int sl = 0; sl < 2; ++sl) {
+    for (int sl = SL0; sl < SL1; ++sl) {
       if (!ok_s[sl]) continue;
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh) {
         const int mb = 2 * tr_s[sl] + rh;
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
+        for (int j = 0; j < NBW; ++j) {
           const int i0 = (ib0 + wn * NB + j) * 8;                 // first i of this n8 block
           const int kc_out = i0 >> 4;
           const int ks_out = ((i0 & 15) >> 2) + (t >> 1);
@@ -213,15 +257,14 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
     // its 16-row slot against the C fragments and writes one partial per (Q, tile-row,
     // N tile, N half); they are summed in fixed order by gamma_from_x_kernel.
     if (gamma_part != nullptr) {
-      const int ntile = work % n_ntiles;
 #pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
+      for (int sl = SL0; sl < SL1; ++sl) {
         double sum = 0.0;
         if (ok_s[sl]) {
 #pragma unroll
           for (int rh = 0; rh < 2; ++rh) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
+            for (int j = 0; j < NBW; ++j) {
               const int ib = ib0 + wn * NB + j;
               const double2 c2 = *reinterpret_cast<const double2 *>(
                   cep + ((((size_t)tr_s[sl] * nib + ib) * 2 + rh) * 32 + lane) * 2);
@@ -234,6 +277,29 @@ k_half_transform_kernel(const double *__restrict__ packed, long long L, int nt, 
         if (lane == 0 && ok_s[sl])
           gamma_part[(((size_t)q_s[sl] * nt + tr_s[sl]) * n_ntiles + ntile) * 2 + wn] = sum;
       }
+    }
+  };
+
+  using Whole = std::integral_constant<int, 0>;
+  using AllBlocks = std::integral_constant<int, NB>;
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+    if (work < n_full) {
+      if constexpr (NB > 1) {
+        int group, ntile;
+        coords(work, group, ntile);
+        if (trim_last && wn == 1 && ntile == n_ntiles - 1) {
+          run_item(Whole{}, std::integral_constant<int, NB - 1>{}, work, work);
+          continue;
+        }
+      }
+      run_item(Whole{}, AllBlocks{}, work, work);
+    } else {
+      int unit, part_wn, part_sl;
+      decode(work, unit, part_wn, part_sl);
+      if (wn != part_wn) run_item(std::integral_constant<int, 3>{}, AllBlocks{}, work, unit);
+      else if (part_sl < 0) run_item(Whole{}, AllBlocks{}, work, unit);
+      else if (part_sl == 0) run_item(std::integral_constant<int, 1>{}, AllBlocks{}, work, unit);
+      else run_item(std::integral_constant<int, 2>{}, AllBlocks{}, work, unit);
     }
   }
 }
@@ -521,6 +587,8 @@ KPlan plan_k(int n, int n_occ_in, int q_count, size_t workspace_limit_bytes, int
     p.ks_last = valid_last >= 16 ? 4 : (valid_last <= 0 ? 0 : (valid_last + 3) / 4);
     if (rank2_occ > 0) p.ks_last = (rank2_occ - 16 * (p.npairs - 1) + 3) / 4;   // of the last pair of chunks
   }
+  // the last n8-block of the padded width: all padding, and past everything the accumulation reads?
+  p.trim_last = (p.nb > 1 && p.nib * 8 - (n_occ > 0 ? n_occ : 1) >= 8 && !getenv("MQCB200_NO_TRIM")) ? 1 : 0;
   const int steps_per_q = rank2_occ > 0 ? 2 * p.npairs : p.nkc;
   // K tile edge: 64 trims the diagonal/padding waste of the SYRK; 128 halves the operand
   // traffic per flop and wins once n is large enough that the waste is small.
@@ -574,17 +642,35 @@ KPlan plan_k(int n, int n_occ_in, int q_count, size_t workspace_limit_bytes, int
   return p;
 }
 
+// How the last round of the half-transform's round-robin walk is cut (see the kernel): the units
+// that do not fill a whole round of `ctas` are dealt as 2 or 4 pieces each when that many pieces
+// still fit one round.
+HalfTail plan_half_tail(long long n_units, int ctas) {
+  HalfTail t;
+  t.n_full = n_units;
+  t.split = 1;
+  if (getenv("MQCB200_NO_TAIL_SPLIT") || ctas <= 0) return t;
+  const long long rest = n_units % ctas;
+  if (rest == 0) return t;
+  int split = rest * 4 <= ctas ? 4 : (rest * 2 <= ctas ? 2 : 1);
+  if (const char *e = getenv("MQCB200_TAIL_SPLIT")) split = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1);   // development override
+  if (split > 1) { t.n_full = n_units - rest; t.split = split; }
+  return t;
+}
+
 template <int NB>
 static void launch_half_nb(const double *d_packed, long long L, int n, int q_count, const double *d_ctf,
                            const double *d_cep, const KPlan &plan, double *d_x, double *d_gamma_part,
                            cudaStream_t s) {
   const int nt = num_tiles(n);
   const long long rows = (long long)q_count * nt;
-  const long long n_work = (rows + K_SLOTS - 1) / K_SLOTS * plan.n_ntiles;
+  const long long n_units = (rows + K_SLOTS - 1) / K_SLOTS * plan.n_ntiles;
+  const HalfTail tail = plan_half_tail(n_units, plan.sm_count);
+  const long long n_work = tail.n_full + (n_units - tail.n_full) * tail.split;
   const unsigned grid = (unsigned)(n_work < plan.sm_count ? n_work : plan.sm_count);
   k_half_transform_kernel<NB><<<grid, K_THREADS, HalfCfg<NB>::kSmemBytes, s>>>(
       d_packed, L, nt, q_count, d_ctf, plan.nib, plan.n_ntiles, d_x, plan.nkc, plan.nmb, d_cep,
-      d_cep ? d_gamma_part : nullptr);
+      d_cep ? d_gamma_part : nullptr, (int)tail.n_full, tail.split, plan.trim_last);
 }
 
 void launch_k_half_transform(const double *d_packed, long long L, int n, int q_count, const double *d_ctf,

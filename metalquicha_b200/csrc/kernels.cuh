@@ -186,6 +186,7 @@ struct KPlan {
   int gamma_stride;  // Coulomb-vector partials per auxiliary function written by the half-transform
   int pair_off;      // rank-2 form: chunk k of the X half pairs with chunk k + pair_off of the C half (0 = SYRK)
   int npairs;        // rank-2 form: 16-wide chunks per half
+  int trim_last;     // half-transform: the last n8-block of the padded occupied range is all padding and is skipped
   size_t x_elems_per_q;     // doubles of X per auxiliary function
   size_t kpart_elems;       // n_splits * n_ktiles * ktile*ktile
 };
@@ -196,6 +197,8 @@ KPlan plan_k(int n, int n_occ, int q_count, size_t workspace_limit_bytes, int sm
 void launch_stack_factors(const double *d_x, int ldx, const double *d_c, int ldc, int n, int n_occ, double *d_s,
                           cudaStream_t s);
 // d_gamma_part (nullable, needs d_cep): [q_count][plan.gamma_stride] partials of sum_{mu,i} X_Q[mu,i] C[mu,i].
+struct HalfTail { long long n_full; int split; };
+HalfTail plan_half_tail(long long n_units, int ctas);
 void launch_k_half_transform(const double *d_packed, long long L, int n, int q_count,
                              const double *d_ctf, const double *d_cep, const KPlan &plan, double *d_x,
                              double *d_gamma_part, cudaStream_t s);

@@ -93,6 +93,10 @@ static void check_plan_k() {
           CHECK(p.kpart_elems == (size_t)p.n_splits * p.n_ktiles * p.ktile * p.ktile, "kpart size");
           CHECK(p.kpart_elems * 8 <= ((size_t)256 << 20) || p.n_splits == 1, "partial buffer cap");
           CHECK(p.gamma_stride == nt * p.n_ntiles * 2, "gamma stride");
+          // a trimmed last n8-block holds only padding, and the accumulation stops short of its columns
+          CHECK(!p.trim_last || (p.nb > 1 && p.nib * 8 - o >= 8 && 16 * (p.nkc - 1) + 4 * p.ks_last <= p.nib * 8 - 8),
+                "trim_last reaches live columns (o=%d nib=%d nkc=%d ks_last=%d)", o, p.nib, p.nkc, p.ks_last);
+          CHECK(p.trim_last || p.nb == 1 || p.nib * 8 - o < 8, "a whole padding block is left untrimmed (o=%d nib=%d)", o, p.nib);
           // every (tile, split < its split count) is produced by exactly one unit
           const int units = p.n_splits_diag * p.n_ktiles + (p.n_splits - p.n_splits_diag) * (p.n_ktiles - p.n_panels);
           if ((long long)units <= 200000) {
@@ -126,6 +130,7 @@ static void check_plan_rank2() {
         CHECK(p.nib * 8 >= 2 * o16 && p.nkc * 2 == p.nib, "stacked width nib=%d o16=%d", p.nib, o16);
         CHECK(p.pair_off + p.npairs <= p.nkc, "the C half must lie inside the half-transformed chunks");
         CHECK(p.ks_last >= 1 && p.ks_last <= 4 && 16 * (p.npairs - 1) + 4 * p.ks_last >= o, "ks_last=%d o=%d", p.ks_last, o);
+        CHECK(!p.trim_last || 16 * (p.pair_off + p.npairs) <= p.nib * 8 - 8, "rank-2 trim_last reaches live columns (o=%d nib=%d)", o, p.nib);
         CHECK(p.n_splits_diag == p.n_splits, "rank-2 diagonal tiles are full tiles: %d vs %d", p.n_splits_diag, p.n_splits);
         CHECK(p.kpart_elems == (size_t)p.n_splits * p.n_ktiles * p.ktile * p.ktile, "kpart size");
       }
@@ -156,8 +161,32 @@ static void check_plan_j_and_fragment() {
   CHECK(!fragment_path_applies(81, 5) && !fragment_path_applies(72, 65), "fragment path limits");
 }
 
+// the half-transform's last round: whole rounds stay whole, the pieces of the rest fit ONE round, and the
+// (unit, warp column, slot) pieces the kernel decodes cover every unit of the rest exactly once
+static void check_half_tail() {
+  for (int ctas : {1, 2, 100, 132, 148})
+    for (long long units = 0; units <= 5000; units += (units < 700 ? 1 : 37)) {
+      const HalfTail t = plan_half_tail(units, ctas);
+      CHECK(t.split == 1 || t.split == 2 || t.split == 4, "split=%d", t.split);
+      CHECK(t.n_full >= 0 && t.n_full <= units && t.n_full % ctas == 0 || t.split == 1, "n_full=%lld units=%lld ctas=%d", t.n_full, units, ctas);
+      if (t.split == 1) { CHECK(t.n_full == units, "no split but n_full=%lld != %lld", t.n_full, units); continue; }
+      const long long rest = units - t.n_full;
+      CHECK(rest > 0 && rest < ctas && rest * t.split <= ctas, "pieces %lld x %d do not fit %d CTAs", rest, t.split, ctas);
+      CHECK(t.split == 4 || rest * 4 > ctas, "a finer split would have fitted (rest=%lld ctas=%d)", rest, ctas);
+      std::set<long long> seen;
+      for (long long work = t.n_full; work < t.n_full + rest * t.split; ++work) {       // the kernel's decode
+        const long long r = work - t.n_full, unit = t.n_full + r / t.split;
+        const int p = (int)(r % t.split), wn = p & 1, sl = t.split == 4 ? (p >> 1) : -1;
+        for (int s = 0; s < 2; ++s)
+          if (sl < 0 || sl == s) seen.insert((unit * 2 + wn) * 2 + s);
+      }
+      CHECK((long long)seen.size() == rest * 4 && *seen.begin() == t.n_full * 4, "tail pieces do not tile the rest (units=%lld ctas=%d)", units, ctas);
+    }
+}
+
 int main() {
   check_layout();
+  check_half_tail();
   check_plan_k();
   check_plan_rank2();
   check_plan_j_and_fragment();

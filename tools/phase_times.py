@@ -17,7 +17,9 @@ e1.record(st); e1.synchronize()
 ph = {k: round(v / steps, 4) for k, v in eng.last_timings().items()}
 ms = e0.elapsed_time(e1) / steps
 npair = n * (n + 1) // 2
-print(json.dumps({"shape": [n, o, q], "ktile": os.environ.get("MQCB200_KTILE", "default"), "ms_per_build": round(ms, 4), "phases_ms": ph,
+import hashlib
+fp = hashlib.sha256(df.cpu().numpy().tobytes()).hexdigest()[:16]
+print(json.dumps({"shape": [n, o, q], "tail_split": "off" if os.environ.get("MQCB200_NO_TAIL_SPLIT") else "on", "fock_sha": fp, "ktile": os.environ.get("MQCB200_KTILE", "default"), "ms_per_build": round(ms, 4), "phases_ms": ph,
                   "k1_tflops": round(2.0 * n * n * o * q / ph["k_half_transform"] * 1e-9, 2) if ph["k_half_transform"] else None,
                   "k2_tflops_alg": round(1.0 * n * n * o * q / ph["k_accumulate"] * 1e-9, 2) if ph["k_accumulate"] else None,
                   "j1_gbs": round(8.0 * npair * q / ph["j_gamma"] * 1e-6, 1) if ph["j_gamma"] else None,

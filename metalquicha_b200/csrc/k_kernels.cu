@@ -491,66 +491,87 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
   const int wm = warp % Cfg::kWarpsM, wn = warp / Cfg::kWarpsM;
   const int g = lane >> 2, t = lane & 3;
   constexpr int TN = Cfg::kTN;
-  double acc[4][TN][2];
-#pragma unroll
-  for (int m = 0; m < 4; ++m)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
-
-  // register double-buffered fragments, loaded one k-sub ahead (see the half-transform)
-  double fa[2][4], fb[2][TN];
-  auto load_frags = [&](double (&a)[4], double (&b)[TN], int st, int ks) {
-    const double *a_s = stage_base + (size_t)st * Cfg::kStageElems + (4 * wm) * 128;
-    const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + (diag ? 0 : Cfg::kPanelElems) + (TN * wn) * 128;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) a[m] = a_s[(m * 4 + ks) * 32 + lane];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
-  };
-  if (n_steps > 0) {
-    mbar_wait(&full_bar[0], 0);
-    load_frags(fa[0], fb[0], 0, 0);
-  }
-  int kc_idx = 0;                                   // position of this step inside its auxiliary function
-  const int last_from = rank2 ? per_q - 2 : per_q - 1;    // rank-2: both orders of the last pair
-  for (int step = 0; step < n_steps; ++step) {
-    const int st = step % Cfg::kStages;
-    // the last 16-wide chunk of the padded occupied range may hold fewer than four valid
-    // 4-wide k-subs (n_occ = 241: one): the rest is zero padding, skip its DMMAs
-    const int ks_lim = (kc_idx >= last_from) ? ks_last : 4;
-    kc_idx = (kc_idx + 1 == per_q) ? 0 : kc_idx + 1;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      if (ks < 3) {
-        load_frags(fa[(ks + 1) & 1], fb[(ks + 1) & 1], st, ks + 1);
-      } else if (step + 1 < n_steps) {
-        const int st1 = (step + 1) % Cfg::kStages;
-        mbar_wait(&full_bar[st1], ((step + 1) / Cfg::kStages) & 1);
-        load_frags(fa[0], fb[0], st1, 0);
-      }
-      if (ks < ks_lim) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-          for (int j = 0; j < TN; ++j) dmma884(acc[m][j][0], acc[m][j][1], fa[ks & 1][m], fb[ks & 1][j]);
-      }
-    }
-    release_stage(&empty_bar[st], lane);
-  }
-
   double *out = kpart + ((size_t)split * n_ktiles + tile) * (TILE * TILE);
+
+  // MC: 8-row blocks of this warp that lie inside the matrix.  Four, except in the last panel row,
+  // where the rows past n are padding nobody reads back (finalize_jk_kernel stops at n): a warp whose
+  // 32 rows are half or wholly padding runs half or none of the DMMAs.  Compile-time, because a
+  // predicated-off DMMA still takes its turn in the pipe.
+  auto consume = [&](auto mc_tag) {
+    constexpr int MC = decltype(mc_tag)::value;
+    if constexpr (MC == 0) {
+      for (int step = 0; step < n_steps; ++step) {          // nothing to compute: just walk the ring
+        const int st = step % Cfg::kStages;
+        mbar_wait(&full_bar[st], (step / Cfg::kStages) & 1);
+        release_stage(&empty_bar[st], lane);
+      }
+    } else {
+      double acc[MC][TN][2];
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    const int r = 32 * wm + 8 * m + g;
+      for (int m = 0; m < MC; ++m)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int c = 8 * TN * wn + 8 * j + 2 * t;
-      double2 *p = reinterpret_cast<double2 *>(out + r * TILE + c);
-      double2 v = make_double2(acc[m][j][0], acc[m][j][1]);
-      if (accumulate) { const double2 o = *p; v.x += o.x; v.y += o.y; }
-      *p = v;
+        for (int j = 0; j < TN; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
+
+      // register double-buffered fragments, loaded one k-sub ahead (see the half-transform)
+      double fa[2][MC], fb[2][TN];
+      auto load_frags = [&](double (&a)[MC], double (&b)[TN], int st, int ks) {
+        const double *a_s = stage_base + (size_t)st * Cfg::kStageElems + (4 * wm) * 128;
+        const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + (diag ? 0 : Cfg::kPanelElems) + (TN * wn) * 128;
+#pragma unroll
+        for (int m = 0; m < MC; ++m) a[m] = a_s[(m * 4 + ks) * 32 + lane];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
+      };
+      if (n_steps > 0) {
+        mbar_wait(&full_bar[0], 0);
+        load_frags(fa[0], fb[0], 0, 0);
+      }
+      int kc_idx = 0;                                   // position of this step inside its auxiliary function
+      const int last_from = rank2 ? per_q - 2 : per_q - 1;    // rank-2: both orders of the last pair
+      for (int step = 0; step < n_steps; ++step) {
+        const int st = step % Cfg::kStages;
+        // the last 16-wide chunk of the padded occupied range may hold fewer than four valid
+        // 4-wide k-subs (n_occ = 241: one): the rest is zero padding, skip its DMMAs
+        const int ks_lim = (kc_idx >= last_from) ? ks_last : 4;
+        kc_idx = (kc_idx + 1 == per_q) ? 0 : kc_idx + 1;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          if (ks < 3) {
+            load_frags(fa[(ks + 1) & 1], fb[(ks + 1) & 1], st, ks + 1);
+          } else if (step + 1 < n_steps) {
+            const int st1 = (step + 1) % Cfg::kStages;
+            mbar_wait(&full_bar[st1], ((step + 1) / Cfg::kStages) & 1);
+            load_frags(fa[0], fb[0], st1, 0);
+          }
+          if (ks < ks_lim) {
+#pragma unroll
+            for (int m = 0; m < MC; ++m)
+#pragma unroll
+              for (int j = 0; j < TN; ++j) dmma884(acc[m][j][0], acc[m][j][1], fa[ks & 1][m], fb[ks & 1][j]);
+          }
+        }
+        release_stage(&empty_bar[st], lane);
+      }
+
+#pragma unroll
+      for (int m = 0; m < MC; ++m) {
+        const int r = 32 * wm + 8 * m + g;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          const int c = 8 * TN * wn + 8 * j + 2 * t;
+          double2 *p = reinterpret_cast<double2 *>(out + r * TILE + c);
+          double2 v = make_double2(acc[m][j][0], acc[m][j][1]);
+          if (accumulate) { const double2 o = *p; v.x += o.x; v.y += o.y; }
+          *p = v;
+        }
+      }
     }
-  }
+  };
+  // 8-row blocks are present in pairs (the matrix is padded to 16 rows), so a warp holds 4, 2 or none
+  const int live = valid_a - 4 * wm;
+  if (TILE == 64 && live <= 0) consume(std::integral_constant<int, 0>{});
+  else if (TILE == 64 && live == 2) consume(std::integral_constant<int, 2>{});
+  else consume(std::integral_constant<int, 4>{});
 }
 
 // ------------------------------------------------------------------------------------

@@ -165,11 +165,12 @@ ref = oracle.build_fock_df(h, b, d, c, n_occ)
 eng = B200FockEngine(lr)
 sb = ShardedFockBuilder(eng, rank, world)
 sb.set_tensor(b, n, naux)
+dist.barrier()            # the exchange timeout is short here: start the builds together
 ok = float(np.max(np.abs(sb.build_fock_df(h, d, c, n_occ) - ref))) <= 1e-10
-# rank 1 falls 3 s behind with a 1 s exchange timeout: BOTH ranks must report the failed build ...
+# rank 1 falls 6 s behind with a 2 s exchange timeout: BOTH ranks must report the failed build ...
 dist.barrier()
 if rank == 1:
-    time.sleep(3.0)
+    time.sleep(6.0)
 failed = False
 try:
     sb.build_fock_df(h, d, c, n_occ)
@@ -197,7 +198,7 @@ def test_exchange_timeout_is_reported_and_the_ranks_recover(tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    env = dict(os.environ, MQC_ROOT=ROOT, MQCB200_XGPU_TIMEOUT_S="1")
+    env = dict(os.environ, MQC_ROOT=ROOT, MQCB200_XGPU_TIMEOUT_S="2")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          env=env, capture_output=True, text=True, timeout=600)

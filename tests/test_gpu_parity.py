@@ -43,6 +43,21 @@ def test_build_fock_df_matches_oracle(engine, n, n_occ, naux):
     assert engine.last_launches() > 0
 
 
+@pytest.mark.parametrize("n,n_occ,naux", [(24, 5, 116), (130, 33, 97), (256, 241, 12), (140, 130, 10), (688, 80, 30), (300, 120, 80)])
+def test_half_transform_schedule_does_not_change_the_bits(engine, monkeypatch, n, n_occ, naux):
+    """The half-transform cuts its last round into pieces and skips an all-padding last n8-block
+    (csrc/k_kernels.cu); both are schedules of the same DMMA sequences, so F must not move by a bit
+    when either is switched off."""
+    b, h, density, coeff = synth.synth_problem(900 + n, n, n_occ, naux)
+    engine.set_tensor(b)
+    fock = engine.build_fock_df(h, density, coeff, n_occ)
+    assert _maxabs(fock, oracle.build_fock_df(h, b, density, coeff, n_occ)) <= TOL
+    for switch in ("MQCB200_NO_TAIL_SPLIT", "MQCB200_NO_TRIM"):
+        monkeypatch.setenv(switch, "1")
+        assert np.array_equal(engine.build_fock_df(h, density, coeff, n_occ), fock), switch
+        monkeypatch.delenv(switch)
+
+
 @pytest.mark.parametrize("n,n_occ,naux", [(24, 5, 116), (72, 15, 340), (130, 33, 64), (200, 50, 96)])
 def test_jk_match_oracle(engine, n, n_occ, naux):
     b, h, density, coeff = synth.synth_problem(7, n, n_occ, naux)

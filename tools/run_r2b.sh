@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_multirank.py -x -q > gpurun_out/r2b_pytest_n$N.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2b_pytest_n$N.log
 tail -12 gpurun_out/r2b_pytest_n$N.log
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29711 \
-  bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r2b_bench_n$N.json 2> gpurun_out/r2b_bench_n$N.err; echo "bench rc=$?"
+  bench.py --gpus $N --steps ${STEPS:-20} --warmup ${WARMUP:-5} > gpurun_out/r2b_bench_n$N.json 2> gpurun_out/r2b_bench_n$N.err; echo "bench rc=$?"
 grep "\[bench\]" gpurun_out/r2b_bench_n$N.err | tail -20
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29712 \
   bench.py --impl reference --gpus $N --steps 3 --warmup 1 > gpurun_out/r2b_ref_n$N.json 2> gpurun_out/r2b_ref_n$N.err; echo "ref rc=$?"

@@ -188,9 +188,10 @@ def _config(name, cfg, world, workers=None):
 def _cpu_sample_size(cfg, override=None):
     if override:
         return int(min(cfg["naux"], override))
-    # ~1.3e11 reference-count flops per sampled build: well under a second on all threads
+    # ~4e11 reference-count flops per sampled build (c4: 197 of 6800 auxiliary functions): about a second on
+    # all threads and five on one, so the baseline block costs ~10 s and the reference arm under a minute
     per_aux = 4.0 * cfg["n"] ** 2 * max(cfg["n_occ"] + cfg["n_beta"], 1)
-    return int(min(cfg["naux"], max(16, min(PARITY_NAUX * 8, 1.3e11 / per_aux))))
+    return int(min(cfg["naux"], max(16, min(PARITY_NAUX * 8, 4.0e11 / per_aux))))
 
 
 def _cpu_problem(cfg, qs):

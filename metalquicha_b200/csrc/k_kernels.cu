@@ -686,6 +686,10 @@ static void launch_half_nb(const double *d_packed, long long L, int n, int q_cou
   const int nt = num_tiles(n);
   const long long rows = (long long)q_count * nt;
   const long long n_units = (rows + K_SLOTS - 1) / K_SLOTS * plan.n_ntiles;
+  if (rows > 0x3fffffffLL || n_units > 0x1fffffffLL) {     // the kernel indexes rows and work items with 32-bit ints
+    std::fprintf(stderr, "mqcb200: half-transform chunk too large (%lld rows); lower the workspace limit\n", rows);
+    std::abort();
+  }
   const HalfTail tail = plan_half_tail(n_units, plan.sm_count);
   const long long n_work = tail.n_full + (n_units - tail.n_full) * tail.split;
   const unsigned grid = (unsigned)(n_work < plan.sm_count ? n_work : plan.sm_count);

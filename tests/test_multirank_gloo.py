@@ -77,6 +77,20 @@ def _worker(rank, world, port, out_dir):
         if rank == 0:
             assert sorted(sum(gathered, [])) == sorted(order)
         assert q.pop() == (-1, False)
+
+        # several ids claimed per round trip to the store (what the fragment farm of bench.py does):
+        # still every fragment exactly once, and each rank works its claims off in queue order
+        q3 = farm.DistributedWorkQueue(order, store, name="t3", batch=3)
+        mine3 = list(farm.worker_loop(q3, lambda i: sizes[i]).keys())
+        pos3 = [order.index(i) for i in mine3]
+        assert pos3 == sorted(pos3)
+        for a in range(0, len(pos3) - len(pos3) % 3, 3):           # claims are runs of consecutive queue positions
+            assert pos3[a + 1] == pos3[a] + 1 and pos3[a + 2] == pos3[a] + 2
+        gathered3 = [None] * world
+        dist.all_gather_object(gathered3, mine3)
+        if rank == 0:
+            assert sorted(sum(gathered3, [])) == sorted(order)
+        assert q3.pop() == (-1, False)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -802,10 +802,22 @@ def run_farm(ctx, primary):
                 "d2h_bytes_per_step": 8 * trimer["n"] ** 2 * 256 * FARM_BUILDS_PER_FRAGMENT * world,
                 "note": "every build goes through mqcb200_build_fock with host buffers"},
         "gpu_launches": int(launches_all),
-        "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
-                     "note": "79 MFLOP and 14 MB per trimer build: launch/latency-bound, see DESIGN.md"},
+        "roofline": _farm_roofline(trimer, builds_dev / t_dev / world),
         "cpu_baseline": cpu_baseline, "clocks": clocks, "device_resident_scf": scf_block,
     }
+
+
+def _farm_roofline(trimer, builds_per_s_per_gpu):
+    """One fragment build streams its packed tensor once (fragment_jk_kernel: gamma, J, X, K per slab in one
+    pass): 8 * npair * naux algorithmic bytes.  Against the HBM peak that is a few per cent -- the farm is
+    bound by launch latency and the host, not by a device roofline; the figure says how far."""
+    hbm_peak, hbm_src = _peaks()
+    by = 8.0 * (trimer["n"] * (trimer["n"] + 1) // 2) * trimer["naux"]
+    ach = by * builds_per_s_per_gpu * 1e-9
+    return {"kernel": "fragment_jk_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+            "frac": ach / hbm_peak if hbm_peak else None, "traffic": None, "peak_source": hbm_src,
+            "note": "per GPU, tensors resident (value_tensor_synthesised_on_device): 79 MFLOP and 7 MB per trimer build "
+                    "are launch/latency-bound, see DESIGN.md 4.3"}
 
 
 def _synthetic_fragment(seed, n, naux, coupling=0.35):

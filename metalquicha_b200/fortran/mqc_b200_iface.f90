@@ -25,6 +25,7 @@ module mqc_b200_iface
    public :: mqcb200_build_g_two_factor
    public :: mqcb200_build_fock, mqcb200_build_jk, mqcb200_build_jk_uhf, mqcb200_build_fock_uhf
    public :: mqcb200_last_energy
+   public :: mqcb200_build_fock_device, mqcb200_build_fock_uhf_device, mqcb200_get_stream, mqcb200_tensor_bytes
    public :: mqcb200_comm_unique_id, mqcb200_comm_init, mqcb200_comm_destroy
    public :: mqcb200_queue_create, mqcb200_queue_pop, mqcb200_queue_is_empty, mqcb200_queue_destroy
    public :: mqcb200_tensor_shape, mqcb200_response_operator, mqcb200_fitted_potential_general
@@ -115,6 +116,41 @@ module mqc_b200_iface
          real(c_double), intent(in) :: h(*), density(*), coeff(*)
          real(c_double), value :: k_scale, j_scale
          real(c_double), intent(out) :: fock(*)
+         integer(c_int) :: status
+      end function
+      !! Device-operand builds: h, density, coeff and fock are DEVICE addresses (type(c_ptr), value -- the style of
+      !! the reference's own GPU bindings, backends/cuest/bindings/cublas.f90:20-44), contiguous column-major,
+      !! queued on the engine's stream; sync = 0 returns at once.  For a GPU-resident SCF driver of the kind
+      !! backends/cuest/backend/mqc_cuest_scf.f90:444-553 runs.
+      function mqcb200_build_fock_device(handle, slot, d_h, d_density, d_coeff, n_occ, k_scale, j_scale, d_fock, sync) &
+         bind(C, name="mqcb200_build_fock_device") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle, d_h, d_density, d_coeff, d_fock
+         integer(c_int), value :: slot, n_occ, sync
+         real(c_double), value :: k_scale, j_scale
+         integer(c_int) :: status
+      end function
+      function mqcb200_build_fock_uhf_device(handle, slot, d_h, d_density_total, d_coeff_a, n_alpha, d_coeff_b, n_beta, &
+                                             k_scale, d_fock_a, d_fock_b, sync) &
+         bind(C, name="mqcb200_build_fock_uhf_device") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle, d_h, d_density_total, d_coeff_a, d_coeff_b, d_fock_a, d_fock_b
+         integer(c_int), value :: slot, n_alpha, n_beta, sync
+         real(c_double), value :: k_scale
+         integer(c_int) :: status
+      end function
+      !! the CUDA stream the engine queues on (a cudaStream_t), so that a caller's own kernels can be ordered with it
+      function mqcb200_get_stream(handle, stream) bind(C, name="mqcb200_get_stream") result(status)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         type(c_ptr), intent(out) :: stream
+         integer(c_int) :: status
+      end function
+      function mqcb200_tensor_bytes(handle, slot, bytes) bind(C, name="mqcb200_tensor_bytes") result(status)
+         import :: c_int, c_ptr, c_size_t
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot
+         integer(c_size_t), intent(out) :: bytes
          integer(c_int) :: status
       end function
       function mqcb200_build_jk(handle, slot, density, coeff, ldc, n_occ, j, k) &

@@ -396,7 +396,7 @@ template <int TILE>
 __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads, SyrkCfg<TILE>::kMinBlocks)
 k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count, int n_ktiles, int n_splits,
                     int n_splits_diag, int n_panels, double *__restrict__ kpart, int accumulate, int ks_last,
-                    int pair_off, int npairs) {
+                    int pair_off, int npairs, int edge_tiles) {
   using Cfg = SyrkCfg<TILE>;
   constexpr int PB = Cfg::kPanelBlocks;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -567,7 +567,75 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
       }
     }
   };
-  // 8-row blocks are present in pairs (the matrix is padded to 16 rows), so a warp holds 4, 2 or none
+  // A tile of the last panel row holds LB < 8 live row blocks.  Skipping the dead blocks warp by warp
+  // (consume<2>, consume<0>) idles two of the four sub-partitions while the CTA still waits for the other
+  // two; here the LB x 8 live blocks are dealt evenly instead -- every warp takes all LB row blocks of two
+  // column blocks -- so the whole CTA finishes in LB/8 of the time and its slot goes to the next unit.
+  // Each element is still one accumulator summed over the same steps in the same order: same bits.
+  auto consume_edge = [&](auto lb_tag) {
+    constexpr int LB = decltype(lb_tag)::value;
+    double acc[LB][2][2];
+#pragma unroll
+    for (int m = 0; m < LB; ++m)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { acc[m][j][0] = 0.0; acc[m][j][1] = 0.0; }
+    double fa[2][LB], fb[2][2];
+    auto load_frags = [&](double (&a)[LB], double (&b)[2], int st, int ks) {
+      const double *a_s = stage_base + (size_t)st * Cfg::kStageElems;
+      const double *b_s = stage_base + (size_t)st * Cfg::kStageElems + Cfg::kPanelElems + (2 * warp) * 128;
+#pragma unroll
+      for (int m = 0; m < LB; ++m) a[m] = a_s[(m * 4 + ks) * 32 + lane];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = b_s[(j * 4 + ks) * 32 + lane];
+    };
+    if (n_steps > 0) {
+      mbar_wait(&full_bar[0], 0);
+      load_frags(fa[0], fb[0], 0, 0);
+    }
+    int kc_idx = 0;
+    const int last_from = rank2 ? per_q - 2 : per_q - 1;
+    for (int step = 0; step < n_steps; ++step) {
+      const int st = step % Cfg::kStages;
+      const int ks_lim = (kc_idx >= last_from) ? ks_last : 4;
+      kc_idx = (kc_idx + 1 == per_q) ? 0 : kc_idx + 1;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        if (ks < 3) {
+          load_frags(fa[(ks + 1) & 1], fb[(ks + 1) & 1], st, ks + 1);
+        } else if (step + 1 < n_steps) {
+          const int st1 = (step + 1) % Cfg::kStages;
+          mbar_wait(&full_bar[st1], ((step + 1) / Cfg::kStages) & 1);
+          load_frags(fa[0], fb[0], st1, 0);
+        }
+        if (ks < ks_lim) {
+#pragma unroll
+          for (int m = 0; m < LB; ++m)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) dmma884(acc[m][j][0], acc[m][j][1], fa[ks & 1][m], fb[ks & 1][j]);
+        }
+      }
+      release_stage(&empty_bar[st], lane);
+    }
+#pragma unroll
+    for (int m = 0; m < LB; ++m) {
+      const int r = 8 * m + g;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = 16 * warp + 8 * j + 2 * t;
+        double2 *p = reinterpret_cast<double2 *>(out + r * TILE + c);
+        double2 v = make_double2(acc[m][j][0], acc[m][j][1]);
+        if (accumulate) { const double2 o = *p; v.x += o.x; v.y += o.y; }
+        *p = v;
+      }
+    }
+  };
+  if (TILE == 64 && edge_tiles && !diag && valid_a < PB) {
+    // 8-row blocks are present in pairs (the matrix is padded to 16 rows): 2, 4 or 6 live ones
+    if (valid_a <= 2) consume_edge(std::integral_constant<int, 2>{});
+    else if (valid_a <= 4) consume_edge(std::integral_constant<int, 4>{});
+    else consume_edge(std::integral_constant<int, 6>{});
+    return;
+  }
   const int live = valid_a - 4 * wm;
   if (TILE == 64 && live <= 0) consume(std::integral_constant<int, 0>{});
   else if (TILE == 64 && live == 2) consume(std::integral_constant<int, 2>{});
@@ -718,16 +786,17 @@ void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, doub
   // A short last chunk still touches every (split, tile) partial -- splits with an empty
   // auxiliary range write (or add) zeros -- so the fixed-order sum in finalize is defined.
   const int splits = plan.n_splits;
+  const int edge = getenv("MQCB200_NO_EDGE_TILES") ? 0 : 1;       // development switch (same bits either way)
   const unsigned units = (unsigned)(plan.n_splits_diag * plan.n_ktiles +
                                     (plan.n_splits - plan.n_splits_diag) * (plan.n_ktiles - plan.n_panels));
   if (plan.ktile == 128)
     k_accumulate_kernel<128><<<units, SyrkCfg<128>::kThreads, SyrkCfg<128>::kSmemBytes, s>>>(
         d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, plan.n_splits_diag, plan.n_panels, d_kpart, accumulate,
-        plan.ks_last, plan.pair_off, plan.npairs);
+        plan.ks_last, plan.pair_off, plan.npairs, edge);
   else
     k_accumulate_kernel<64><<<units, SyrkCfg<64>::kThreads, SyrkCfg<64>::kSmemBytes, s>>>(
         d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, plan.n_splits_diag, plan.n_panels, d_kpart, accumulate,
-        plan.ks_last, plan.pair_off, plan.npairs);
+        plan.ks_last, plan.pair_off, plan.npairs, edge);
 }
 
 template <int NB>

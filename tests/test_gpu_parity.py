@@ -43,16 +43,18 @@ def test_build_fock_df_matches_oracle(engine, n, n_occ, naux):
     assert engine.last_launches() > 0
 
 
-@pytest.mark.parametrize("n,n_occ,naux", [(24, 5, 116), (130, 33, 97), (256, 241, 12), (140, 130, 10), (688, 80, 30), (300, 120, 80)])
+@pytest.mark.parametrize("n,n_occ,naux", [(24, 5, 116), (130, 33, 97), (256, 241, 12), (140, 130, 10), (688, 80, 30), (300, 120, 80),
+                                         (160, 81, 40), (223, 50, 33)])
 def test_half_transform_schedule_does_not_change_the_bits(engine, monkeypatch, n, n_occ, naux):
-    """The half-transform cuts its last round into pieces and skips an all-padding last n8-block
-    (csrc/k_kernels.cu); both are schedules of the same DMMA sequences, so F must not move by a bit
-    when either is switched off."""
+    """The half-transform cuts its last round into pieces and skips an all-padding last n8-block, and the
+    accumulation deals the live 8-row blocks of a last-panel-row tile (2, 4 or 6 of 8: n = 130, 160, 300
+    here) evenly to its warps (csrc/k_kernels.cu); all three are schedules of the same DMMA sequences, so
+    F must not move by a bit when any of them is switched off."""
     b, h, density, coeff = synth.synth_problem(900 + n, n, n_occ, naux)
     engine.set_tensor(b)
     fock = engine.build_fock_df(h, density, coeff, n_occ)
     assert _maxabs(fock, oracle.build_fock_df(h, b, density, coeff, n_occ)) <= TOL
-    for switch in ("MQCB200_NO_TAIL_SPLIT", "MQCB200_NO_TRIM"):
+    for switch in ("MQCB200_NO_TAIL_SPLIT", "MQCB200_NO_TRIM", "MQCB200_NO_EDGE_TILES"):
         monkeypatch.setenv(switch, "1")
         assert np.array_equal(engine.build_fock_df(h, density, coeff, n_occ), fock), switch
         monkeypatch.delenv(switch)
@@ -298,7 +300,7 @@ def test_response_operator_and_general_density_potential(engine):
 
 
 @pytest.mark.parametrize("n,n_occ,naux", [(58, 9, 70), (130, 33, 40), (97, 16, 30), (200, 81, 12), (72, 15, 64), (150, 129, 9)])
-def test_response_operator_keeps_relative_accuracy_for_a_small_trial_vector(engine, n, n_occ, naux):
+def test_response_operator_keeps_relative_accuracy_for_a_small_trial_vector(engine, monkeypatch, n, n_occ, naux):
     """Near CPHF convergence |X| ~ 1e-8 |C|.  The direct rank-2 form keeps ~16 digits of g there;
     a difference of squares K[X+C] - K[X-C] keeps eight.  Tolerance is
     RELATIVE to |g|.  Shapes: ragged n, n_occ on and off the 16-wide chunk boundary, two N tiles
@@ -315,6 +317,9 @@ def test_response_operator_keeps_relative_accuracy_for_a_small_trial_vector(engi
     assert 1e-10 < scale < 1e-5
     assert _maxabs(g, g_ref) <= 1e-10 * scale
     assert np.array_equal(g, engine.response_operator_df(x, c_occ, dtilde, k_scale=1.0))      # bit-reproducible
+    monkeypatch.setenv("MQCB200_NO_EDGE_TILES", "1")          # the rank-2 mode takes the edge-tile schedule too
+    assert np.array_equal(g, engine.response_operator_df(x, c_occ, dtilde, k_scale=1.0))
+    monkeypatch.delenv("MQCB200_NO_EDGE_TILES")
     # coefficient matrices with a leading dimension
     pad = np.zeros((n + 3, 2 * n_occ), order="F")
     pad[:n, :n_occ], pad[:n, n_occ:] = x, c_occ

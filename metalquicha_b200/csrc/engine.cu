@@ -571,7 +571,9 @@ static size_t lower_len(int n) { return (size_t)n * (n + 1) / 2; }
 // column costs more than the bytes it moves; here a column goes in fixed 64-byte pieces, the last piece running
 // over into the next column's place -- which the next copy then overwrites -- so there is no tail handling at
 // all (2.0 -> 0.83 ms per trimer tensor on the build host).  The last columns of the range are copied exactly:
-// nothing is read past the caller's array or written past this range's share of dst.
+// nothing is read past the caller's array or written past this range's share of dst.  (A piece runs over by
+// at most 7 doubles, which must stay inside the NEXT slab of the range: true once a slab's triangle holds 7
+// doubles, so matrices smaller than 8 are copied exactly throughout.)
 #if defined(__x86_64__)
 __attribute__((target("avx2")))
 #endif
@@ -580,7 +582,7 @@ static void gather_lower_range(const double *src, int n, size_t q_lo, size_t q_h
   for (size_t q = q_lo; q < q_hi; ++q) {
     const double *s_q = src + q * src_slab_stride;
     double *d = dst + q * tri;
-    const int exact_from = (q + 1 == q_hi) ? (n > 8 ? n - 8 : 0) : n;
+    const int exact_from = (q + 1 == q_hi || n < 8) ? (n > 8 ? n - 8 : 0) : n;
     for (int nu = 0; nu < n; ++nu) {
       const double *sc = s_q + (size_t)nu * n + nu;
       const int len = n - nu;
@@ -594,7 +596,7 @@ static void gather_lower_range(const double *src, int n, size_t q_lo, size_t q_h
   }
 }
 
-static void gather_lower(const double *src, int n, size_t q_count, size_t src_slab_stride, double *dst) {
+void gather_lower(const double *src, int n, size_t q_count, size_t src_slab_stride, double *dst) {
   const size_t tri = lower_len(n);
   auto work = [&](size_t q_lo, size_t q_hi) {
 #if defined(__x86_64__)

@@ -204,6 +204,10 @@ void launch_k_half_transform(const double *d_packed, long long L, int n, int q_c
                              double *d_gamma_part, cudaStream_t s);
 void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, double *d_kpart,
                          int accumulate, cudaStream_t s);
+// Host side of set_tensor: the lower triangles (column nu: rows nu..n-1) of q_count full-square column-major
+// slabs, src_slab_stride doubles apart, gathered back to back into dst (n(n+1)/2 doubles per slab).  Reads
+// nothing outside the q_count slabs and writes nothing outside dst's q_count triangles (tests/native).
+void gather_lower(const double *src, int n, size_t q_count, size_t src_slab_stride, double *dst);
 // One-time (per process and device) opt-in to large dynamic shared memory.
 void configure_kernels();            // K kernels; calls the two below
 void configure_fragment_kernels();

@@ -1,6 +1,9 @@
 // Host-side invariants of the launch planners and of the packed-layout arithmetic, over a
 // grid of shapes far wider than the GPU parity suite.  Built and run on the CPU by
 // tests/test_native_planners.py (links libmqcb200.so; launches nothing).
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <set>
@@ -184,7 +187,61 @@ static void check_half_tail() {
     }
 }
 
+// gather_lower (the host side of set_tensor) copies columns in fixed 64-byte pieces that run over into the
+// next column's place.  Source and destination are laid out so that they END on a page the process may not
+// touch: a read past the caller's array or a write past the triangles faults instead of passing silently.
+struct Guarded {
+  char *base = nullptr;
+  size_t map_bytes = 0;
+  double *p = nullptr;
+  explicit Guarded(size_t n_doubles) {
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t bytes = n_doubles * sizeof(double);
+    const size_t data_pages = (bytes + page - 1) / page + 1;
+    map_bytes = (data_pages + 1) * page;
+    base = static_cast<char *>(mmap(nullptr, map_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+    if (base == MAP_FAILED) { perror("mmap"); exit(2); }
+    mprotect(base + data_pages * page, page, PROT_NONE);
+    p = reinterpret_cast<double *>(base + data_pages * page - bytes);
+  }
+  ~Guarded() { munmap(base, map_bytes); }
+};
+
+static void check_gather_lower() {
+  const int ns[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 15, 16, 17, 24, 31, 72};
+  const size_t qs[] = {1, 2, 3, 5, 17};
+  for (int n : ns)
+    for (size_t q : qs) {
+      const size_t nn = (size_t)n * n, tri = (size_t)n * (n + 1) / 2;
+      Guarded src(q * nn), dst(q * tri);
+      for (size_t i = 0; i < q * nn; ++i) src.p[i] = (double)(i + 1);
+      gather_lower(src.p, n, q, nn, dst.p);
+      bool ok = true;
+      for (size_t s = 0; s < q && ok; ++s) {
+        size_t off = 0;
+        for (int nu = 0; nu < n && ok; ++nu)
+          for (int mu = nu; mu < n; ++mu, ++off) ok = ok && dst.p[s * tri + off] == src.p[s * nn + (size_t)nu * n + mu];
+      }
+      CHECK(ok, "gather_lower n=%d q=%zu", n, q);
+    }
+  {  // large enough (>= 16 MiB of triangles) for the threaded split of the slab range
+    const int n = 72;
+    const size_t q = 820, nn = (size_t)n * n, tri = (size_t)n * (n + 1) / 2;
+    Guarded src(q * nn), dst(q * tri);
+    for (size_t i = 0; i < q * nn; ++i) src.p[i] = (double)(i % 1000003);
+    gather_lower(src.p, n, q, nn, dst.p);
+    bool ok = true;
+    for (size_t s = 0; s < q && ok; ++s) {
+      size_t off = 0;
+      for (int nu = 0; nu < n && ok; ++nu)
+        for (int mu = nu; mu < n; ++mu, ++off) ok = ok && dst.p[s * tri + off] == src.p[s * nn + (size_t)nu * n + mu];
+    }
+    CHECK(ok, "gather_lower threaded n=%d q=%zu", n, q);
+  }
+}
+
 int main() {
+  check_gather_lower();
   check_layout();
   check_half_tail();
   check_plan_k();

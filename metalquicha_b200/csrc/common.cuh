@@ -31,6 +31,64 @@ __host__ __device__ inline int in_tile_offset(int r, int c) {
   return (((r >> 3) << 2) + (c >> 2)) * 32 + ((r & 7) << 2) + (c & 3);
 }
 
+// ---------------------------------------------------------------------------
+// Work units of the exchange accumulation (k_accumulate_kernel): unit u -> K tile (mp, np), np <= mp,
+// and split `split` of that tile's auxiliary range.  Tiles come in three classes with their own split
+// counts, chosen so that every unit takes about the same time: off-diagonal tiles (n_splits),
+// DIAGONAL tiles (n_splits_diag: 9/16 of the DMMAs) and, when n_splits_edge != n_splits, the
+// off-diagonal tiles of the LAST panel row (n_splits_edge: only LB of their 8 row blocks are inside
+// the matrix).  Used by the kernel and by the host-side planner check (tests/native/plan_check.cu).
+// ---------------------------------------------------------------------------
+__host__ __device__ inline void k_unit_decode(int u, int n_ktiles, int n_panels, int n_splits, int n_splits_diag,
+                                              int n_splits_edge, int &mp, int &np, int &split) {
+  const int n_off = n_ktiles - n_panels;
+  if (n_splits_edge == n_splits) {
+    // every tile for the first n_splits_diag splits, then only the off-diagonal tiles
+    const int u_full = n_splits_diag * n_ktiles;
+    if (u < u_full) {
+      split = u / n_ktiles;
+      const int tile = u % n_ktiles;
+      mp = 0;
+      while ((mp + 1) * (mp + 2) / 2 <= tile) ++mp;
+      np = tile - mp * (mp + 1) / 2;
+    } else {
+      const int v = u - u_full;
+      split = n_splits_diag + v / n_off;
+      const int oi = v % n_off;                       // off-diagonal tiles: oi = mp*(mp-1)/2 + np, np < mp
+      mp = 1;
+      while ((mp + 1) * mp / 2 <= oi) ++mp;
+      np = oi - mp * (mp - 1) / 2;
+    }
+    return;
+  }
+  // class by class: the full off-diagonal tiles (panel rows 1 .. n_panels-2), the last panel row, the diagonal
+  const int n_edge = n_panels - 1, n_full = n_off - n_edge;
+  int v = u;
+  if (v < n_splits * n_full) {
+    split = v / n_full;
+    const int oi = v % n_full;
+    mp = 1;
+    while ((mp + 1) * mp / 2 <= oi) ++mp;
+    np = oi - mp * (mp - 1) / 2;
+    return;
+  }
+  v -= n_splits * n_full;
+  if (v < n_splits_edge * n_edge) {
+    split = v / n_edge;
+    mp = n_panels - 1;
+    np = v % n_edge;
+    return;
+  }
+  v -= n_splits_edge * n_edge;
+  split = v / n_panels;
+  mp = np = v % n_panels;
+}
+__host__ __device__ inline long long k_unit_count(int n_ktiles, int n_panels, int n_splits, int n_splits_diag,
+                                                  int n_splits_edge) {
+  const long long n_off = n_ktiles - n_panels, n_edge = n_splits_edge == n_splits ? 0 : n_panels - 1;
+  return (long long)n_splits * (n_off - n_edge) + (long long)n_splits_edge * n_edge + (long long)n_splits_diag * n_panels;
+}
+
 #ifdef __CUDACC__
 // --------------------------- PTX wrappers ----------------------------------
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {

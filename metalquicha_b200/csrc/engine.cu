@@ -825,7 +825,7 @@ static void build(Engine *e, const BuildArgs &a) {
   const double kfac = (a.two_spin || a.rank2) ? 1.0 : 2.0;
   JPlan jp = plan_j(n, sl.q_count);
   int n_jslices = jp.n_slices;          // partial-buffer shapes handed to finalize below
-  int n_ksplits = 0, n_ksplits_diag = -1, ktile = 64;
+  int n_ksplits = 0, n_ksplits_diag = -1, n_ksplits_edge = -1, ktile = 64;
   bool ka_finalized = false;
   const int max_occ = std::max(do_ka ? a.n_a : 0, do_kb ? a.n_b : 0);
   const bool frag = have && (do_j || do_ka || do_kb) && fragment_path_enabled() && !a.rank2 &&
@@ -910,7 +910,7 @@ static void build(Engine *e, const BuildArgs &a) {
       if (do_ka) {
         e->phase_begin(T_FINAL);
         launch_finalize_jk(nullptr, 0, e->d_kpart.d(), kp.n_splits, kp.ktile, n, kfac, nullptr, d_ka, e->stream,
-                           nullptr, 0.0, 0.0, nullptr, kp.n_splits_diag);
+                           nullptr, 0.0, 0.0, nullptr, kp.n_splits_diag, 1, 0, 0, 0, kp.n_splits_edge);
         e->phase_end(T_FINAL);
         e->launches += 1;
         ka_finalized = true;
@@ -922,7 +922,7 @@ static void build(Engine *e, const BuildArgs &a) {
             (overlap && fuse) ? e->ev_k1_done : nullptr);
       e->phase_begin(T_FINAL);
       launch_finalize_jk(nullptr, 0, e->d_kpart.d(), kpb.n_splits, kpb.ktile, n, kfac, nullptr, d_kb, e->stream,
-                         nullptr, 0.0, 0.0, nullptr, kpb.n_splits_diag);
+                         nullptr, 0.0, 0.0, nullptr, kpb.n_splits_diag, 1, 0, 0, 0, kpb.n_splits_edge);
       e->phase_end(T_FINAL);
       e->launches += 1;
     } else {
@@ -979,6 +979,7 @@ static void build(Engine *e, const BuildArgs &a) {
 
     n_ksplits = kp.n_splits;
     n_ksplits_diag = kp.n_splits_diag;
+    n_ksplits_edge = kp.n_splits_edge;
     ktile = kp.ktile ? kp.ktile : 64;
   }
 
@@ -1001,7 +1002,8 @@ static void build(Engine *e, const BuildArgs &a) {
     if (do_j || fin_k || fused_assemble) {
       launch_finalize_jk(do_j ? e->d_jpart.d() : nullptr, n_jslices, fin_k ? e->d_kpart.d() : nullptr, n_ksplits,
                          ktile, n, kfac, do_j ? d_j : nullptr, fin_k ? d_ka : nullptr, e->stream,
-                         fused_assemble ? d_h : nullptr, a.j_scale, 0.5 * a.k_scale, d_fa_early, n_ksplits_diag);
+                         fused_assemble ? d_h : nullptr, a.j_scale, 0.5 * a.k_scale, d_fa_early, n_ksplits_diag, 1, 0, 0, 0,
+                         n_ksplits_edge);
       e->launches += 1;
     }
   } else {

@@ -395,8 +395,8 @@ __device__ __forceinline__ void syrk_diag_warp(const double *stage_base, uint64_
 template <int TILE>
 __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads, SyrkCfg<TILE>::kMinBlocks)
 k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count, int n_ktiles, int n_splits,
-                    int n_splits_diag, int n_panels, double *__restrict__ kpart, int accumulate, int ks_last,
-                    int pair_off, int npairs, int edge_tiles) {
+                    int n_splits_diag, int n_splits_edge, int n_panels, double *__restrict__ kpart, int accumulate,
+                    int ks_last, int pair_off, int npairs, int edge_tiles) {
   using Cfg = SyrkCfg<TILE>;
   constexpr int PB = Cfg::kPanelBlocks;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -405,35 +405,19 @@ k_accumulate_kernel(const double *__restrict__ x, int nkc, int nmb, int q_count,
   uint64_t *empty_bar = full_bar + Cfg::kStages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // Units: every tile for the first n_splits_diag splits, then only the off-diagonal tiles.
-  // A diagonal tile does 9/16 of the DMMAs (lower triangle only, evenly dealt to the four
-  // warps), so it gets proportionally longer auxiliary ranges: all units take the same time.
-  int tile, split, mp = 0, np;
-  {
-    const int u_full = n_splits_diag * n_ktiles;
-    if ((int)blockIdx.x < u_full) {
-      split = blockIdx.x / n_ktiles;
-      tile = blockIdx.x % n_ktiles;
-      while ((mp + 1) * (mp + 2) / 2 <= tile) ++mp;
-      np = tile - mp * (mp + 1) / 2;
-    } else {
-      const int n_off = n_ktiles - n_panels;
-      const int v = blockIdx.x - u_full;
-      split = n_splits_diag + v / n_off;
-      const int oi = v % n_off;                       // off-diagonal tiles: oi = mp*(mp-1)/2 + np, np < mp
-      mp = 1;
-      while ((mp + 1) * mp / 2 <= oi) ++mp;
-      np = oi - mp * (mp - 1) / 2;
-      tile = mp * (mp + 1) / 2 + np;
-    }
-  }
+  // Units: (tile, split) pairs, class by class (k_unit_decode).  A diagonal tile does 9/16 of the DMMAs
+  // (lower triangle only, evenly dealt to the four warps) and a tile of the last panel row LB/8 of them
+  // (consume_edge), so they get proportionally longer auxiliary ranges: all units take the same time.
+  int tile, split, mp = 0, np = 0;
+  k_unit_decode((int)blockIdx.x, n_ktiles, n_panels, n_splits, n_splits_diag, n_splits_edge, mp, np, split);
+  tile = mp * (mp + 1) / 2 + np;
   // rank-2 mode (pair_off > 0): chunk k of the X half is paired with chunk k + pair_off of the C half,
   // once as (rows of panel mp: X, rows of panel np: C) and once reversed; every tile -- the
   // diagonal ones too -- then takes the two-panel path, and a step list per auxiliary function is
   // 2*npairs long instead of nkc.
   const bool rank2 = pair_off > 0;
   const bool diag = mp == np && !rank2;
-  const int my_splits = (mp == np) ? n_splits_diag : n_splits;
+  const int my_splits = (mp == np) ? n_splits_diag : (mp == n_panels - 1 ? n_splits_edge : n_splits);
   const int qa = (int)((long long)split * q_count / my_splits);
   const int qb = (int)((long long)(split + 1) * q_count / my_splits);
   const int per_q = rank2 ? 2 * npairs : nkc;
@@ -696,8 +680,6 @@ KPlan plan_k(int n, int n_occ_in, int q_count, size_t workspace_limit_bytes, int
   // waves * (steps per unit + ~12 of fixed per-CTA overhead) + what the later fixed-order sum
   // over the splits costs; small problems get a few dozen short units, big ones whole waves.
   // The partial buffer is capped at 256 MiB.
-  int best = 1;
-  double best_cost = 1e300;
   const size_t tile_bytes = (size_t)p.ktile * p.ktile * sizeof(double);
   const int n_diag = p.n_panels, n_off = p.n_ktiles - p.n_panels;
   auto diag_splits = [&](int s) {           // 64-wide diagonal tiles cost 9/16 of a full tile
@@ -705,21 +687,53 @@ KPlan plan_k(int n, int n_occ_in, int q_count, size_t workspace_limit_bytes, int
     int sd = (9 * s + 8) / 16;
     return sd < 1 ? 1 : sd;
   };
-  for (int s = 1; s <= 512 && s <= p.q_chunk; ++s) {
-    if ((size_t)s * p.n_ktiles * tile_bytes > ((size_t)256 << 20) && s > 1) break;
-    const int sd = diag_splits(s);
-    const long long units = (long long)s * n_off + (long long)sd * n_diag;
-    const long long waves = (units + slots - 1) / slots;
-    const double steps_off = (double)((p.q_chunk + s - 1) / s) * steps_per_q;
-    const double steps_diag = (double)((p.q_chunk + sd - 1) / sd) * steps_per_q * ((p.ktile == 64 && rank2_occ == 0) ? 9.0 / 16.0 : 1.0);
-    const double steps = n_off > 0 ? (steps_off > steps_diag ? steps_off : steps_diag) : steps_diag;
-    // + the fixed-order sum over the splits in finalize_jk_kernel (~3/4 of a step per split)
-    double cost = (double)waves * (steps + 12.0) + 0.75 * (double)s;
-    // a single wave of long units measures ~5 % slower than the same work in two waves of
-    // shorter ones (c2: 2.28 vs 2.18 ms; co-resident CTAs in lockstep, no second wave to
-    // absorb the stragglers)
-    if (waves == 1 && units > slots / 2) cost *= 1.05;
-    if (cost < best_cost * 0.995) { best_cost = cost; best = s; }
+  // Off-diagonal tiles of a partly filled last panel row: LB of their 8 row blocks are live (consume_edge),
+  // so they may get LB/8 of the splits -- a third class of units.  Not in the rank-2 form.
+  const int lb_edge = p.nmb - (p.ktile / 8) * (p.n_panels - 1);
+  const bool edge_possible = p.ktile == 64 && rank2_occ == 0 && p.n_panels >= 2 && lb_edge < 8;
+  auto edge_splits = [&](int s) {
+    int se = (lb_edge * s + 4) / 8;
+    return se < 1 ? 1 : se;
+  };
+  auto search = [&](bool use_edge, int &best) {
+    best = 1;
+    double best_cost = 1e300;
+    const int n_edge = use_edge ? p.n_panels - 1 : 0;
+    for (int s = 1; s <= 512 && s <= p.q_chunk; ++s) {
+      if ((size_t)s * p.n_ktiles * tile_bytes > ((size_t)256 << 20) && s > 1) break;
+      const int sd = diag_splits(s), se = use_edge ? edge_splits(s) : s;
+      const long long units = (long long)s * (n_off - n_edge) + (long long)se * n_edge + (long long)sd * n_diag;
+      const long long waves = (units + slots - 1) / slots;
+      const double steps_off = (double)((p.q_chunk + s - 1) / s) * steps_per_q;
+      const double steps_edge = n_edge > 0 ? (double)((p.q_chunk + se - 1) / se) * steps_per_q * lb_edge / 8.0 : 0.0;
+      const double steps_diag = (double)((p.q_chunk + sd - 1) / sd) * steps_per_q * ((p.ktile == 64 && rank2_occ == 0) ? 9.0 / 16.0 : 1.0);
+      double steps = n_off - n_edge > 0 ? (steps_off > steps_diag ? steps_off : steps_diag) : steps_diag;
+      if (steps_edge > steps) steps = steps_edge;
+      // + the fixed-order sum over the splits in finalize_jk_kernel (~3/4 of a step per split)
+      double cost = (double)waves * (steps + 12.0) + 0.75 * (double)s;
+      // a single wave of long units measures ~5 % slower than the same work in two waves of
+      // shorter ones (c2: 2.28 vs 2.18 ms; co-resident CTAs in lockstep, no second wave to
+      // absorb the stragglers)
+      if (waves == 1 && units > slots / 2) cost *= 1.05;
+      if (cost < best_cost * 0.995) { best_cost = cost; best = s; }
+    }
+    return best_cost;
+  };
+  int best = 1;
+  const double base_cost = search(false, best);
+  // The third class is taken only for launches of a few waves and only where the model sees more than 3 % in
+  // it.  With many waves the hardware's own dispatch already hands the slot of an early-finishing edge unit to
+  // the next unit, and re-cutting the splits only moves the wave boundary.  Measured in one call on one box
+  // (profiles/r02d_split_classes_ab.log): c2 (two waves -> four shorter ones) 6.72 -> 6.52 ms per build;
+  // c4 (15 waves) 313.6 ms on two classes against 315.4 (three classes, same 25 splits) and 317.4 (three
+  // classes, 5 splits, which the model rated 1.8 % better).
+  bool use_edge = false;
+  if (edge_possible && !getenv("MQCB200_NO_EDGE_SPLITS")) {
+    int best_e = 1;
+    const double edge_cost = search(true, best_e);
+    const long long base_units = (long long)best * n_off + (long long)diag_splits(best) * n_diag;
+    const bool few_waves = (base_units + slots - 1) / slots < 8;
+    if ((few_waves && edge_cost < 0.97 * base_cost) || getenv("MQCB200_EDGE_SPLITS")) { use_edge = true; best = best_e; }
   }
   if (const char *e = getenv("MQCB200_KSPLITS")) {   // development override
     const int v = atoi(e);
@@ -727,6 +741,7 @@ KPlan plan_k(int n, int n_occ_in, int q_count, size_t workspace_limit_bytes, int
   }
   p.n_splits = best;
   p.n_splits_diag = diag_splits(best);
+  p.n_splits_edge = use_edge ? edge_splits(best) : best;
   p.kpart_elems = (size_t)p.n_splits * p.n_ktiles * p.ktile * p.ktile;
   return p;
 }
@@ -787,16 +802,15 @@ void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, doub
   // auxiliary range write (or add) zeros -- so the fixed-order sum in finalize is defined.
   const int splits = plan.n_splits;
   const int edge = getenv("MQCB200_NO_EDGE_TILES") ? 0 : 1;       // development switch (same bits either way)
-  const unsigned units = (unsigned)(plan.n_splits_diag * plan.n_ktiles +
-                                    (plan.n_splits - plan.n_splits_diag) * (plan.n_ktiles - plan.n_panels));
+  const unsigned units = (unsigned)k_unit_count(plan.n_ktiles, plan.n_panels, plan.n_splits, plan.n_splits_diag, plan.n_splits_edge);
   if (plan.ktile == 128)
     k_accumulate_kernel<128><<<units, SyrkCfg<128>::kThreads, SyrkCfg<128>::kSmemBytes, s>>>(
-        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, plan.n_splits_diag, plan.n_panels, d_kpart, accumulate,
-        plan.ks_last, plan.pair_off, plan.npairs, edge);
+        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, plan.n_splits_diag, plan.n_splits_edge, plan.n_panels,
+        d_kpart, accumulate, plan.ks_last, plan.pair_off, plan.npairs, edge);
   else
     k_accumulate_kernel<64><<<units, SyrkCfg<64>::kThreads, SyrkCfg<64>::kSmemBytes, s>>>(
-        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, plan.n_splits_diag, plan.n_panels, d_kpart, accumulate,
-        plan.ks_last, plan.pair_off, plan.npairs, edge);
+        d_x, plan.nkc, plan.nmb, q_count, plan.n_ktiles, splits, plan.n_splits_diag, plan.n_splits_edge, plan.n_panels,
+        d_kpart, accumulate, plan.ks_last, plan.pair_off, plan.npairs, edge);
 }
 
 template <int NB>

@@ -27,12 +27,13 @@ void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib
 // Sum the J / K partial buffers in fixed order and unpack to full n x n matrices.
 // Either output may be null.  k_factor multiplies K (2 for RHF, 1 per spin).
 // With d_fock non-null the Fock matrix F = H + jf*J - kf*K is assembled in the same pass.
-// n_ksplits_diag: partials held by the DIAGONAL K tiles (<= n_ksplits; pass n_ksplits when equal).
+// n_ksplits_diag: partials held by the DIAGONAL K tiles (<= n_ksplits; -1 when equal).
+// n_ksplits_edge: partials held by the off-diagonal K tiles of the last panel row (-1 when equal to n_ksplits).
 void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits,
                         int ktile, int n, double k_factor, double *d_j, double *d_k, cudaStream_t s,
                         const double *d_h = nullptr, double jf = 0.0, double kf = 0.0, double *d_fock = nullptr,
                         int n_ksplits_diag = -1, int batch = 1, size_t jpart_stride = 0, size_t kpart_stride = 0,
-                        size_t out_stride = 0);
+                        size_t out_stride = 0, int n_ksplits_edge = -1);
 // F = H + jf*J - kf*K  (any of J/K may be null == zero).
 void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf,
                           int n, double *d_fock, cudaStream_t s);
@@ -181,6 +182,7 @@ struct KPlan {
   int n_ktiles;    // lower-triangular ktile x ktile tiles of K
   int n_splits;    // split of the auxiliary range in the accumulation (off-diagonal tiles)
   int n_splits_diag;  // ... of the diagonal tiles (fewer: they do 9/16 of the work per auxiliary function)
+  int n_splits_edge;  // ... of the off-diagonal tiles of a partly filled last panel row (LB/8 of the work); == n_splits when there is no such class
   int q_chunk;     // auxiliary functions per half-transform launch
   int sm_count;    // persistent grid size of the half-transform
   int gamma_stride;  // Coulomb-vector partials per auxiliary function written by the half-transform

@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(256) finalize_jk_kernel(const double *__restri
                                                           double *__restrict__ k_out,
                                                           const double *__restrict__ h, double jf, double kf,
                                                           double *__restrict__ fock_out, size_t jpart_stride,
-                                                          size_t kpart_stride, size_t out_stride) {
+                                                          size_t kpart_stride, size_t out_stride, int n_ksplits_edge,
+                                                          int edge_panel) {
   if (blockIdx.y != 0) {                            // fragment of a batch: every operand moves on by its stride
     if (jpart) jpart += (size_t)blockIdx.y * jpart_stride;
     if (kpart) kpart += (size_t)blockIdx.y * kpart_stride;
@@ -170,7 +171,8 @@ __global__ void __launch_bounds__(256) finalize_jk_kernel(const double *__restri
     const size_t off = ((size_t)(mp * (mp + 1) / 2 + np) << (2 * ktile_log2)) + ((size_t)(a & msk) << ktile_log2) + (b & msk);
     double s = 0.0;
     const size_t stride = (size_t)n_ktiles << (2 * ktile_log2);
-    const int n_sp = mp == np ? n_ksplits_diag : n_ksplits;    // diagonal tiles hold fewer partials
+    // diagonal tiles and the tiles of a partly filled last panel row hold fewer partials
+    const int n_sp = mp == np ? n_ksplits_diag : (mp == edge_panel ? n_ksplits_edge : n_ksplits);
     int sp = 0;
     for (; sp + 16 <= n_sp; sp += 16) {
       double v[16];
@@ -397,7 +399,7 @@ void launch_pack_coeff(const double *d_coeff, int ldc, int n, int n_occ, int nib
 void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kpart, int n_ksplits, int ktile,
                         int n, double k_factor, double *d_j, double *d_k, cudaStream_t s, const double *d_h,
                         double jf, double kf, double *d_fock, int n_ksplits_diag, int batch, size_t jpart_stride,
-                        size_t kpart_stride, size_t out_stride) {
+                        size_t kpart_stride, size_t out_stride, int n_ksplits_edge) {
   const int nt = num_tiles(n);
   const int ktile_log2 = ktile == 128 ? 7 : 6;
   const int np = (n + ktile - 1) / ktile;
@@ -405,7 +407,9 @@ void launch_finalize_jk(const double *d_jpart, int n_jslices, const double *d_kp
   finalize_jk_kernel<<<grid, 256, 0, s>>>(d_jpart, n_jslices, packed_row_len(n), d_kpart, n_ksplits,
                                           n_ksplits_diag < 0 ? n_ksplits : n_ksplits_diag,
                                           np * (np + 1) / 2, ktile_log2, n, nt, k_factor, d_j, d_k, d_h, jf, kf,
-                                          d_fock, jpart_stride, kpart_stride, out_stride);
+                                          d_fock, jpart_stride, kpart_stride, out_stride,
+                                          n_ksplits_edge < 0 ? n_ksplits : n_ksplits_edge,
+                                          (n_ksplits_edge < 0 || n_ksplits_edge == n_ksplits) ? -1 : np - 1);
 }
 
 void launch_assemble_fock(const double *d_h, const double *d_j, const double *d_k, double jf, double kf, int n,

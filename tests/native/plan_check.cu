@@ -44,26 +44,13 @@ static void check_layout() {
   CHECK(packed_row_len(688) == 946LL * 256 && packed_row_len(1450) == 4186LL * 256, "row lengths");
 }
 
-// the unit -> (tile, split) decode of k_accumulate_kernel, restated on the host
-static void decode_unit(int u, const KPlan &p, int &tile, int &split, bool &diag) {
-  const int u_full = p.n_splits_diag * p.n_ktiles;
-  int mp = 0, np = 0;
-  if (u < u_full) {
-    split = u / p.n_ktiles;
-    tile = u % p.n_ktiles;
-    while ((mp + 1) * (mp + 2) / 2 <= tile) ++mp;
-    np = tile - mp * (mp + 1) / 2;
-  } else {
-    const int n_off = p.n_ktiles - p.n_panels;
-    const int v = u - u_full;
-    split = p.n_splits_diag + v / n_off;
-    const int oi = v % n_off;
-    mp = 1;
-    while ((mp + 1) * mp / 2 <= oi) ++mp;
-    np = oi - mp * (mp - 1) / 2;
-    tile = mp * (mp + 1) / 2 + np;
-  }
-  diag = mp == np;
+// the unit -> (tile, split) decode k_accumulate_kernel uses (common.cuh: one function for both sides)
+static void decode_unit(int u, const KPlan &p, int &tile, int &split, int &mp, int &np) {
+  k_unit_decode(u, p.n_ktiles, p.n_panels, p.n_splits, p.n_splits_diag, p.n_splits_edge, mp, np, split);
+  tile = mp * (mp + 1) / 2 + np;
+}
+static int splits_of(const KPlan &p, int mp, int np) {      // what k_accumulate_kernel and finalize_jk_kernel use
+  return mp == np ? p.n_splits_diag : (mp == p.n_panels - 1 ? p.n_splits_edge : p.n_splits);
 }
 
 static void check_plan_k() {
@@ -100,20 +87,29 @@ static void check_plan_k() {
           CHECK(!p.trim_last || (p.nb > 1 && p.nib * 8 - o >= 8 && 16 * (p.nkc - 1) + 4 * p.ks_last <= p.nib * 8 - 8),
                 "trim_last reaches live columns (o=%d nib=%d nkc=%d ks_last=%d)", o, p.nib, p.nkc, p.ks_last);
           CHECK(p.trim_last || p.nb == 1 || p.nib * 8 - o < 8, "a whole padding block is left untrimmed (o=%d nib=%d)", o, p.nib);
+          // the last panel row gets its own split count only when it is partly filled, in proportion to its live row blocks
+          {
+            const int lb = p.nmb - 8 * (p.n_panels - 1);
+            CHECK(p.n_splits_edge >= 1 && p.n_splits_edge <= p.n_splits, "edge splits %d of %d", p.n_splits_edge, p.n_splits);
+            if (p.ktile != 64 || lb >= 8 || p.n_panels < 2) CHECK(p.n_splits_edge == p.n_splits, "edge class without an edge (n=%d)", n);
+            else CHECK(p.n_splits_edge == p.n_splits || p.n_splits_edge == (lb * p.n_splits + 4) / 8 || p.n_splits_edge == 1,
+                       "edge splits %d for lb=%d s=%d", p.n_splits_edge, lb, p.n_splits);
+          }
           // every (tile, split < its split count) is produced by exactly one unit
-          const int units = p.n_splits_diag * p.n_ktiles + (p.n_splits - p.n_splits_diag) * (p.n_ktiles - p.n_panels);
-          if ((long long)units <= 200000) {
+          const long long units = k_unit_count(p.n_ktiles, p.n_panels, p.n_splits, p.n_splits_diag, p.n_splits_edge);
+          if (units <= 200000) {
             std::set<std::pair<int, int>> got;
             bool ok = true;
-            for (int u = 0; u < units; ++u) {
-              int tile, split;
-              bool diag;
-              decode_unit(u, p, tile, split, diag);
-              ok = ok && tile >= 0 && tile < p.n_ktiles && split >= 0 && split < (diag ? p.n_splits_diag : p.n_splits);
+            for (int u = 0; u < (int)units; ++u) {
+              int tile, split, mp, np;
+              decode_unit(u, p, tile, split, mp, np);
+              ok = ok && np >= 0 && np <= mp && mp < p.n_panels && split >= 0 && split < splits_of(p, mp, np);
               ok = ok && got.insert({tile, split}).second;
             }
-            const int expect = p.n_panels * p.n_splits_diag + (p.n_ktiles - p.n_panels) * p.n_splits;
-            CHECK(ok && (int)got.size() == expect && units == expect, "unit decode (n=%d o=%d q=%d): %d units, %d distinct, %d expected",
+            long long expect = 0;
+            for (int mp = 0; mp < p.n_panels; ++mp)
+              for (int np = 0; np <= mp; ++np) expect += splits_of(p, mp, np);
+            CHECK(ok && (long long)got.size() == expect && units == expect, "unit decode (n=%d o=%d q=%d): %lld units, %d distinct, %lld expected",
                   n, o, q, units, (int)got.size(), expect);
           }
         }
@@ -135,6 +131,7 @@ static void check_plan_rank2() {
         CHECK(p.ks_last >= 1 && p.ks_last <= 4 && 16 * (p.npairs - 1) + 4 * p.ks_last >= o, "ks_last=%d o=%d", p.ks_last, o);
         CHECK(!p.trim_last || 16 * (p.pair_off + p.npairs) <= p.nib * 8 - 8, "rank-2 trim_last reaches live columns (o=%d nib=%d)", o, p.nib);
         CHECK(p.n_splits_diag == p.n_splits, "rank-2 diagonal tiles are full tiles: %d vs %d", p.n_splits_diag, p.n_splits);
+        CHECK(p.n_splits_edge == p.n_splits, "rank-2 plans keep the two-class schedule: %d vs %d", p.n_splits_edge, p.n_splits);
         CHECK(p.kpart_elems == (size_t)p.n_splits * p.n_ktiles * p.ktile * p.ktile, "kpart size");
       }
     }

@@ -60,6 +60,32 @@ def test_half_transform_schedule_does_not_change_the_bits(engine, monkeypatch, n
         monkeypatch.delenv(switch)
 
 
+@pytest.mark.parametrize("n,n_occ,naux", [(130, 33, 97), (160, 81, 40), (300, 120, 80), (688, 80, 30), (100, 17, 50)])
+@pytest.mark.parametrize("splits", [None, "8", "3"])
+def test_accumulation_split_classes(engine, monkeypatch, n, n_occ, naux, splits):
+    """The accumulation's units come in up to three classes with their own split of the auxiliary range
+    (off-diagonal tiles, diagonal tiles at 9/16, tiles of a partly filled last panel row at LB/8:
+    csrc/common.cuh k_unit_decode, csrc/k_kernels.cu plan_k).  Forced on and off, with the planner's and with
+    forced split counts: every schedule must give F within the tolerance (a different, fixed summation order
+    each), and each one reproducibly."""
+    b, h, density, coeff = synth.synth_problem(300 + n, n, n_occ, naux)
+    engine.set_tensor(b)
+    ref = oracle.build_fock_df(h, b, density, coeff, n_occ)
+    if splits:
+        monkeypatch.setenv("MQCB200_KSPLITS", splits)
+    monkeypatch.setenv("MQCB200_EDGE_SPLITS", "1")
+    f_edge = engine.build_fock_df(h, density, coeff, n_occ)
+    assert _maxabs(f_edge, ref) <= TOL
+    assert np.array_equal(f_edge, engine.build_fock_df(h, density, coeff, n_occ))
+    monkeypatch.setenv("MQCB200_NO_EDGE_TILES", "1")      # same plan, the per-warp row-block skip instead of the even deal
+    assert np.array_equal(f_edge, engine.build_fock_df(h, density, coeff, n_occ))
+    monkeypatch.delenv("MQCB200_NO_EDGE_TILES")
+    monkeypatch.delenv("MQCB200_EDGE_SPLITS")
+    monkeypatch.setenv("MQCB200_NO_EDGE_SPLITS", "1")
+    f_two = engine.build_fock_df(h, density, coeff, n_occ)
+    assert _maxabs(f_two, ref) <= TOL and _maxabs(f_two, f_edge) <= 1e-11
+
+
 @pytest.mark.parametrize("n,n_occ,naux", [(24, 5, 116), (72, 15, 340), (130, 33, 64), (200, 50, 96)])
 def test_jk_match_oracle(engine, n, n_occ, naux):
     b, h, density, coeff = synth.synth_problem(7, n, n_occ, naux)

@@ -111,7 +111,8 @@ int mqcb200_build_df_tensor(void *handle, int slot, int n, int naux, const doubl
  * collective in the sense that every rank makes them, but each rank pushes only ITS share of the
  * nu blocks: a rank whitens its blocks for ALL auxiliary rows and the GEMM's epilogue stores every
  * row directly into the packed tensor of the rank that owns it, over NVLink peer memory -- the
- * all-to-all from mu-nu slabs to Q slabs costs no separate pass. */
+ * all-to-all from mu-nu slabs to Q slabs costs no separate pass.  A rank whose push failed must still
+ * call mqcb200_whiten_end: the call fails on EVERY rank then, and no rank's tensor becomes usable. */
 int mqcb200_whiten_begin(void *handle, int slot, int n, int naux_total, int q_begin, int q_count,
                          const double *half);
 int mqcb200_whiten_push(void *handle, int slot, int nu_begin, int nu_count,

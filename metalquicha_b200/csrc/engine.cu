@@ -182,6 +182,7 @@ struct Engine {
     WhitenDst dst{};
     void *mapped[WHITEN_MAX_RANKS] = {};
     bool multi = false;
+    bool failed = false;           // a push failed on this rank of a sharded whitening: whiten_end tells the others
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     double gemm_ms = 0.0, flops = 0.0;
   } wh;
@@ -1843,6 +1844,7 @@ static void whiten_abort(Engine *e) {
   w.t0 = w.t1 = nullptr;
   w.active = false;
   w.multi = false;
+  w.failed = false;
 }
 
 // `half` is on the HOST unless half_on_device.  Collective when a communicator is active: every rank
@@ -2000,7 +2002,7 @@ static void whiten_end(Engine *e, int slot) {
   e->bind();
   CUDA_CHECK(cudaStreamSynchronize(e->stream));
   bool ok = true;
-  if (w.multi) ok = ranks_agree(e, true);                // every rank's stores into my rows have landed
+  if (w.multi) ok = ranks_agree(e, !w.failed);           // every rank's stores into my rows have landed, and none gave up
   e->whiten_ms = w.gemm_ms;
   e->whiten_flops = w.flops;
   whiten_abort(e);                                       // releases the scratch and unmaps the peers
@@ -2228,7 +2230,10 @@ int mqcb200_whiten_push(void *handle, int slot, int nu_begin, int nu_count, cons
   try {
     whiten_push(e, slot, nu_begin, nu_count, three_cols, ld_aux);
   } catch (...) {
+    // a lone rank gives the whitening up at once; a rank of a sharded one must still meet the others in
+    // whiten_end (collective), where its failure becomes everyone's
     if (e->wh.active && !e->wh.multi) whiten_abort(e);
+    else if (e->wh.active) e->wh.failed = true;
     throw;
   }
   API_END

@@ -259,6 +259,9 @@ class B200FockEngine:
             raise ValueError("h and density must both be n x n")
         self._check_operand(n, slot)
         coeff, ldc = self._coeff(coeff, n, n_occ)
+        if out is not None and not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == (n, n)
+                                    and out.flags.f_contiguous and out.flags.writeable):
+            raise ValueError("out must be a writeable column-major float64 n x n array (the library writes n*n doubles into it)")
         fock = out if out is not None else np.empty((n, n), dtype=np.float64, order="F")
         _check(self._lib.mqcb200_build_fock(
             self._h, slot, _ptr(h), _ptr(density), _ptr(coeff), ldc, int(n_occ),

@@ -10,7 +10,10 @@
 !  transposes anywhere.
 !
 !  NOT COMPILED IN THIS REPOSITORY: the build image has no Fortran compiler.  The
-!  C header it mirrors IS compiled and tested (tests/test_abi.py checks every symbol).
+!  C header it mirrors IS compiled and tested (tests/test_abi.py checks every symbol),
+!  and tests/test_fortran_binding.py reads this file against the header prototype by
+!  prototype: every symbol present, argument count, order and names, VALUE on every C
+!  scalar and on no array, kinds (c_int / c_double / c_size_t / c_int64_t), constants.
 !
 !  Build:  gfortran -c mqc_b200_iface.f90        Link:  ... -lmqcb200
 ! ============================================================================
@@ -32,7 +35,10 @@ module mqc_b200_iface
    public :: mqcb200_scf, mqcb200_scf_fragment, mqcb200_scf_fragment_batch, mqcb200_df_gradient_densities
    public :: mqcb200_metric_inverse_sqrt, mqcb200_build_df_tensor
    public :: mqcb200_whiten_begin, mqcb200_whiten_push, mqcb200_whiten_end
-   public :: MQCB200_OK, MQCB200_FAIL, MQCB200_BAD_HANDLE
+   public :: mqcb200_set_fuse_threshold, mqcb200_set_overlap, mqcb200_set_profiling, mqcb200_set_scf_check_every
+   public :: mqcb200_last_timings, mqcb200_last_launches, mqcb200_last_gamma_fused, mqcb200_last_set_tensor
+   public :: mqcb200_last_whiten, mqcb200_last_metric, mqcb200_synth_tensor
+   public :: MQCB200_OK, MQCB200_FAIL, MQCB200_BAD_HANDLE, MQCB200_NUM_TIMERS
    public :: MQCB200_SLOT_FULL_RANGE, MQCB200_SLOT_ATTENUATED
 
    integer(c_int), parameter :: MQCB200_OK = 0          !! same values as MQC_OK/MQC_FAIL/MQC_BAD_HANDLE,
@@ -40,6 +46,7 @@ module mqc_b200_iface
    integer(c_int), parameter :: MQCB200_BAD_HANDLE = 2
    integer(c_int), parameter :: MQCB200_SLOT_FULL_RANGE = 0   !! bmat
    integer(c_int), parameter :: MQCB200_SLOT_ATTENUATED = 1   !! bmat_lr
+   integer(c_int), parameter :: MQCB200_NUM_TIMERS = 8        !! length of mqcb200_last_timings' array
 
    interface
       function mqcb200_create(device_rank, handle) bind(C, name="mqcb200_create") result(status)
@@ -354,6 +361,77 @@ module mqc_b200_iface
          real(c_double), intent(out) :: e_electronic
          integer(c_int), intent(out) :: iterations, converged, n_mo
          real(c_double), intent(out) :: coeff(*), orbital_energies(*), density(*), e_history(*)
+         integer(c_int) :: status
+      end function
+      ! ---- tuning and diagnostics (mqcb200.h: the "instrumentation" block and the setters) ----
+      function mqcb200_set_fuse_threshold(handle, bytes) bind(C, name="mqcb200_set_fuse_threshold") result(status)
+         import :: c_int, c_ptr, c_size_t
+         type(c_ptr), value :: handle
+         integer(c_size_t), value :: bytes
+         integer(c_int) :: status
+      end function
+      function mqcb200_set_overlap(handle, on) bind(C, name="mqcb200_set_overlap") result(status)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: on
+         integer(c_int) :: status
+      end function
+      function mqcb200_set_profiling(handle, on) bind(C, name="mqcb200_set_profiling") result(status)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: on
+         integer(c_int) :: status
+      end function
+      function mqcb200_set_scf_check_every(handle, iterations) bind(C, name="mqcb200_set_scf_check_every") result(status)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: iterations
+         integer(c_int) :: status
+      end function
+      function mqcb200_last_timings(handle, ms) bind(C, name="mqcb200_last_timings") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         real(c_double), intent(out) :: ms(*)        !! MQCB200_NUM_TIMERS phase sums in milliseconds
+         integer(c_int) :: status
+      end function
+      function mqcb200_last_launches(handle, n_kernels) bind(C, name="mqcb200_last_launches") result(status)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), intent(out) :: n_kernels
+         integer(c_int) :: status
+      end function
+      function mqcb200_last_gamma_fused(handle, fused) bind(C, name="mqcb200_last_gamma_fused") result(status)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), intent(out) :: fused
+         integer(c_int) :: status
+      end function
+      function mqcb200_last_set_tensor(handle, ms, h2d_bytes) bind(C, name="mqcb200_last_set_tensor") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         real(c_double), intent(out) :: ms, h2d_bytes
+         integer(c_int) :: status
+      end function
+      function mqcb200_last_whiten(handle, ms, flops) bind(C, name="mqcb200_last_whiten") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         real(c_double), intent(out) :: ms, flops
+         integer(c_int) :: status
+      end function
+      function mqcb200_last_metric(handle, ms, sweeps) bind(C, name="mqcb200_last_metric") result(status)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: handle
+         real(c_double), intent(out) :: ms
+         integer(c_int), intent(out) :: sweeps
+         integer(c_int) :: status
+      end function
+      function mqcb200_synth_tensor(handle, slot, n, naux_total, q_begin, q_count, seed, scale) &
+         bind(C, name="mqcb200_synth_tensor") result(status)
+         import :: c_int, c_ptr, c_double, c_int64_t
+         type(c_ptr), value :: handle
+         integer(c_int), value :: slot, n, naux_total, q_begin, q_count
+         integer(c_int64_t), value :: seed           !! uint64_t on the C side: the bit pattern is what counts
+         real(c_double), value :: scale
          integer(c_int) :: status
       end function
    end interface

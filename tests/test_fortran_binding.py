@@ -211,3 +211,40 @@ def test_constants_agree_with_the_header():
         assert defines[name] == value, f"{name}: header {defines[name]}, Fortran {value}"
     for must in ("MQCB200_OK", "MQCB200_FAIL", "MQCB200_BAD_HANDLE", "MQCB200_NUM_TIMERS"):
         assert must in params
+
+
+def _call_argument_counts(text):
+    """Every ``mqcb200_xxx( ... )`` reference in joined Fortran source -> (name, number of actual arguments)."""
+    found = []
+    for m in re.finditer(r"\b(mqcb200_\w+)\s*\(", text):
+        depth, i, args, cur = 1, m.end(), 0, False
+        while i < len(text) and depth:
+            ch = text[i]
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                args += 1
+            elif not ch.isspace():
+                cur = True
+            i += 1
+        found.append((m.group(1), args + 1 if cur else 0))
+    return found
+
+
+def test_wrapper_calls_pass_as_many_arguments_as_the_prototypes_take():
+    """The wrapper module (mqc_b200_fock.f90: the routines a maintainer calls in place of build_fock_df,
+    build_df_tensor, response_operator_df ...) must hand every entry point exactly the arguments the header
+    lists -- with explicit interfaces a compiler would refuse anything else; here the test does."""
+    protos = c_prototypes()
+    n_calls = 0
+    for fn in sorted(os.listdir(FDIR)):
+        if not fn.endswith(".f90") or fn == os.path.basename(IFACE):
+            continue
+        text = "\n".join(_join_continuations(open(os.path.join(FDIR, fn)).read()))
+        for name, n_args in _call_argument_counts(text):
+            assert name in protos, f"{fn} calls {name}, which the header does not declare"
+            assert n_args == len(protos[name][1]), f"{fn}: {name} called with {n_args} arguments, the header takes {len(protos[name][1])}"
+            n_calls += 1
+    assert n_calls >= 15            # the wrapper really goes through the interface module

@@ -1278,7 +1278,7 @@ static void scf_fragment(Engine *e, const ScfArgs &a) {
 // a one-sided Jacobi iteration on the (shifted, hence positive definite) F' = Y^T F Y with Y the
 // previous orbitals: nearly diagonal, three or four sweeps.  Per iteration the host sees the DIIS
 // overlaps of the newest error vector, the Jacobi "rotated anything?" flags and three scalars.
-static bool diis_solve_host(const double *overlap /*[8][8] slot coords*/, int newest, int n_stored, int dmax, double *coef,
+bool diis_solve_host(const double *overlap /*[8][8] slot coords*/, int newest, int n_stored, int dmax, double *coef,
                             int *slots) {
   // diis_coefficients + solve_diis (src/methods/mqc_diis.f90:146-273): ages oldest -> newest
   if (n_stored < 2) return false;

@@ -210,6 +210,12 @@ void launch_k_accumulate(const double *d_x, int q_count, const KPlan &plan, doub
 // slabs, src_slab_stride doubles apart, gathered back to back into dst (n(n+1)/2 doubles per slab).  Reads
 // nothing outside the q_count slabs and writes nothing outside dst's q_count triangles (tests/native).
 void gather_lower(const double *src, int n, size_t q_count, size_t src_slab_stride, double *dst);
+// Host side of the any-size device SCF: diis_coefficients + solve_diis of src/methods/mqc_diis.f90:146-273 on
+// the ring's cached overlaps.  overlap[8][8] is indexed by ring slot, `newest` is the 1-based slot of the newest
+// vector (as in diis_state_t), n_stored <= dmax <= 8.  On success coef[i] / slots[i] (i = 0 oldest .. n_stored-1
+// newest) are the extrapolation weights and the 0-based slots they belong to.  false: fewer than two vectors,
+// or a pivot below 1e-14 (the caller then uses the plain Fock matrix).
+bool diis_solve_host(const double *overlap, int newest, int n_stored, int dmax, double *coef, int *slots);
 // One-time (per process and device) opt-in to large dynamic shared memory.
 void configure_kernels();            // K kernels; calls the two below
 void configure_fragment_kernels();

@@ -25,7 +25,7 @@ import numpy as np
 
 LINEAR_DEPENDENCE_TOL = 1.0e-7      # mqc_scf_common.f90:27
 GWH_K = 1.75                        # mqc_scf_common.f90:33
-PIVOT_FLOOR = 1.0e-14               # mqc_diis.f90:35
+PIVOT_FLOOR = 1.0e-14               # mqc_diis.f90:32
 
 
 def build_orthogonalizer(overlap):

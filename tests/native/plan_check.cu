@@ -4,6 +4,7 @@
 #include <sys/mman.h>
 #include <unistd.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <set>
@@ -237,8 +238,137 @@ static void check_gather_lower() {
   }
 }
 
+// ---- diis_solve_host against the reference's own DIIS test -------------------------------------------
+// test/test_mqc_diis.f90 of the reference compares diis_state_t, step by step, with the shift-the-history,
+// rebuild-B algorithm it replaced (reference_extrapolate, :256-312) on vectors from its own LCG filler
+// (:314-332), to 1e-12 * max(1, |F|) (:10).  The same case, same sizes and seeds (:157-223), is run here
+// on the engine's host-side solve; the ring bookkeeping around it is what scf_general does.
+static void fill_pseudorandom(std::vector<double> &a, int rows, int cols, int seed) {
+  a.assign((size_t)rows * cols, 0.0);
+  long long state = seed;
+  for (int j = 0; j < cols; ++j)
+    for (int i = 0; i < rows; ++i) {
+      state = (1103515245LL * state + 12345LL) % 2147483648LL;
+      a[(size_t)j * rows + i] = (double)state / 2147483648.0 - 0.5;
+    }
+}
+
+static bool reference_extrapolate(const std::vector<double> &hist_f, const std::vector<double> &hist_e, int nf, int ne,
+                                  int n_stored, std::vector<double> &fock) {
+  fock.assign(nf, 0.0);
+  if (n_stored < 2) return false;
+  const int n = n_stored + 1;
+  std::vector<double> aug((size_t)n * (n + 1), 0.0);
+  auto A = [&](int r, int c) -> double & { return aug[(size_t)r * (n + 1) + c]; };
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) A(i, j) = -1.0;
+  A(n - 1, n - 1) = 0.0;
+  for (int i = 0; i < n_stored; ++i)
+    for (int j = 0; j < n_stored; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < ne; ++k) s += hist_e[(size_t)i * ne + k] * hist_e[(size_t)j * ne + k];
+      A(i, j) = s;
+    }
+  A(n - 1, n) = -1.0;
+  for (int i = 0; i < n; ++i) {
+    int piv = i;
+    for (int j = i + 1; j < n; ++j)
+      if (std::fabs(A(j, i)) > std::fabs(A(piv, i))) piv = j;
+    if (piv != i)
+      for (int c = 0; c <= n; ++c) std::swap(A(i, c), A(piv, c));
+    const double pivot = A(i, i);
+    if (std::fabs(pivot) < 1.0e-14) return false;
+    for (int j = i + 1; j < n; ++j) {
+      const double factor = A(j, i) / pivot;
+      for (int c = i; c <= n; ++c) A(j, c) -= factor * A(i, c);
+    }
+  }
+  std::vector<double> coef(n, 0.0);
+  for (int i = n - 1; i >= 0; --i) {
+    double s = 0.0;
+    for (int c = i + 1; c < n; ++c) s += A(i, c) * coef[c];
+    coef[i] = (A(i, n) - s) / A(i, i);
+  }
+  for (int i = 0; i < n_stored; ++i)
+    for (int k = 0; k < nf; ++k) fock[k] += coef[i] * hist_f[(size_t)i * nf + k];
+  return true;
+}
+
+static void check_diis_solve() {
+  struct Case { int nf, ne, nmax, npush, seed_f, seed_e; };
+  const Case cases[] = {{12, 12, 4, 9, 11, 29},      // test_vs_reference
+                        {6, 6, 3, 10, 17, 23},       // test_ring_evicts' data
+                        {7, 7, 3, 8, 13, 5},         // test_overlap_cache's data
+                        {20, 20, 8, 20, 3, 31}};     // the ring size the SCF uses
+  for (const Case &c : cases) {
+    std::vector<double> f_in, e_in;
+    fill_pseudorandom(f_in, c.nf, c.npush, c.seed_f);
+    fill_pseudorandom(e_in, c.ne, c.npush, c.seed_e);
+    std::vector<double> ring_f((size_t)c.nmax * c.nf), ring_e((size_t)c.nmax * c.ne);     // by slot
+    std::vector<double> hist_f((size_t)c.nmax * c.nf), hist_e((size_t)c.nmax * c.ne);     // by age (the reference's)
+    double overlap[64] = {0.0};
+    int n_stored = 0, newest = 0, n_hist = 0;
+    for (int step = 0; step < c.npush; ++step) {
+      // the ring push of scf_general (diis_push, mqc_diis.f90:94-119): overlaps of the newest vector only
+      newest = newest % c.nmax + 1;
+      if (n_stored < c.nmax) ++n_stored;
+      const int slot = newest - 1;
+      for (int k = 0; k < c.nf; ++k) ring_f[(size_t)slot * c.nf + k] = f_in[(size_t)step * c.nf + k];
+      for (int k = 0; k < c.ne; ++k) ring_e[(size_t)slot * c.ne + k] = e_in[(size_t)step * c.ne + k];
+      for (int age = 0; age < n_stored; ++age) {
+        const int other = ((newest - n_stored + age) % c.nmax + c.nmax) % c.nmax;
+        double s = 0.0;
+        for (int k = 0; k < c.ne; ++k) s += ring_e[(size_t)slot * c.ne + k] * ring_e[(size_t)other * c.ne + k];
+        overlap[slot * 8 + other] = s;
+        overlap[other * 8 + slot] = s;
+      }
+      // the reference's history: shift down when full, append at the end
+      if (n_hist < c.nmax) ++n_hist;
+      else {
+        for (int i = 0; i + 1 < c.nmax; ++i) {
+          for (int k = 0; k < c.nf; ++k) hist_f[(size_t)i * c.nf + k] = hist_f[(size_t)(i + 1) * c.nf + k];
+          for (int k = 0; k < c.ne; ++k) hist_e[(size_t)i * c.ne + k] = hist_e[(size_t)(i + 1) * c.ne + k];
+        }
+      }
+      for (int k = 0; k < c.nf; ++k) hist_f[(size_t)(n_hist - 1) * c.nf + k] = f_in[(size_t)step * c.nf + k];
+      for (int k = 0; k < c.ne; ++k) hist_e[(size_t)(n_hist - 1) * c.ne + k] = e_in[(size_t)step * c.ne + k];
+
+      double coef[8];
+      int slots[8];
+      const bool ok = diis_solve_host(overlap, newest, n_stored, c.nmax, coef, slots);
+      std::vector<double> ref;
+      const bool ok_ref = reference_extrapolate(hist_f, hist_e, c.nf, c.ne, n_hist, ref);
+      CHECK(ok == ok_ref, "DIIS solvability disagrees at step %d (nmax=%d)", step + 1, c.nmax);
+      if (!ok || !ok_ref) continue;
+      std::vector<double> fock(c.nf, 0.0);
+      double sum = 0.0;
+      for (int i = 0; i < n_stored; ++i) {
+        sum += coef[i];
+        for (int k = 0; k < c.nf; ++k) fock[k] += coef[i] * ring_f[(size_t)slots[i] * c.nf + k];
+        // oldest first: age i of the ring is entry i of the shifted history
+        for (int k = 0; k < c.ne; ++k)
+          CHECK(ring_e[(size_t)slots[i] * c.ne + k] == hist_e[(size_t)i * c.ne + k], "slot order at step %d", step + 1);
+      }
+      double dev = 0.0, scale = 1.0;
+      for (int k = 0; k < c.nf; ++k) {
+        dev = std::fmax(dev, std::fabs(fock[k] - ref[k]));
+        scale = std::fmax(scale, std::fabs(ref[k]));
+      }
+      CHECK(dev <= 1.0e-12 * scale, "extrapolated Fock differs from the reference algorithm at step %d by %.3e (nmax=%d)", step + 1, dev, c.nmax);
+      CHECK(std::fabs(sum - 1.0) <= 1.0e-10, "DIIS weights sum to %.15f", sum);
+    }
+  }
+  {  // below two vectors nothing is extrapolated (test_below_two)
+    double overlap[64] = {0.0}, coef[8];
+    int slots[8];
+    overlap[0] = 1.0;
+    CHECK(!diis_solve_host(overlap, 1, 0, 4, coef, slots) && !diis_solve_host(overlap, 1, 1, 4, coef, slots), "extrapolated below two vectors");
+  }
+}
+
 int main() {
   check_gather_lower();
+  check_diis_solve();
   check_layout();
   check_half_tail();
   check_plan_k();

@@ -1,5 +1,8 @@
-"""Host-side invariants of the launch planners and the packed layout (tests/native/plan_check.cu):
-compiled with nvcc as a host program, linked against libmqcb200.so, run on the CPU."""
+"""Host-side code of the library checked on the CPU (tests/native/plan_check.cu, compiled with nvcc as a
+host program and linked against libmqcb200.so): invariants of the launch planners and the packed layout,
+the unit decode the accumulation kernel shares with its planner, the lower-triangle gather of set_tensor
+between guard pages, and the DIIS solve of the any-size device SCF against the reference's own DIIS test
+(test/test_mqc_diis.f90: its filler, sizes, seeds and comparison algorithm)."""
 import os
 import shutil
 import subprocess

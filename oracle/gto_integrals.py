@@ -8,6 +8,13 @@ programs write their basis out inline and assert total energies against PySCF to
     validation/check_rhf.f90:94-153   H2O / STO-3G, standard geometry   E = -74.9658162796
     (basis data: hydrogen_sto3g :148-159, oxygen_sto3g :161-178 of the same file)
 
+and its validation manifest holds density-fitted energies in a basis whose data is published and (for H and O)
+also present in the tree in another form:
+
+    validation/validation_tests_cpu.json:899-904  H2O / 6-31G* fitted with 6-31G*    E = -76.188111755038
+    validation/validation_tests_cpu.json:905-910  CH4 / 6-31G** fitted with 6-31G**  E = -40.381603512964
+    validation/validation_tests_cpu.json:719-723  H2O / 6-31G*, exact integrals      E = -76.010317945971
+
 libcint (third party, absent: JorgeG94/libfint v0.1.1) supplies the integrals there.  This
 module restates the PUBLISHED McMurchie-Davidson scheme (J. Comput. Phys. 26, 218 (1978);
 Helgaker, Jorgensen, Olsen, "Molecular Electronic-Structure Theory", ch. 9) for exactly those
@@ -222,7 +229,7 @@ STO3G = {
           (0, [5.0331513, 1.1695961, 0.3803890], [-0.09996723, 0.39951283, 0.70011547]),
           (1, [5.0331513, 1.1695961, 0.3803890], [0.15591627, 0.60768372, 0.39195739])],
 }
-CHARGE = {"H": 1, "O": 8}
+CHARGE = {"H": 1, "C": 6, "O": 8}
 
 
 def build_basis(symbols, coords, table=STO3G):
@@ -238,6 +245,103 @@ def build_basis(symbols, coords, table=STO3G):
 H2_STO3G = (["H", "H"], [[0.0, 0.0, 0.0], [0.0, 0.0, 1.4]], 2, -1.1167143251)
 H2O_STO3G = (["O", "H", "H"], [[0.0, 0.0, -0.1364652], [0.0, 1.4304924, 1.0826636], [0.0, -1.4304924, 1.0826636]],
              10, -74.9658162796)
+
+
+# ---- 6-31G* (Pople): published data, restated ---------------------------------------------------
+# The reference reads its named basis sets from the Basis Set Exchange bundle (basis_sets/PROVENANCE.md),
+# which is not in the tree.  6-31G* is published data: W. J. Hehre, R. Ditchfield, J. A. Pople, J. Chem.
+# Phys. 56, 2257 (1972) (H, O valence/core), P. C. Hariharan, J. A. Pople, Theor. Chim. Acta 28, 213 (1973)
+# (the d polarisation function, exponent 0.8 on O), in the ten digits the Basis Set Exchange distributes.
+# The same numbers are held by the reference tree itself, in GAMESS form (coefficient x primitive norm, eight
+# digits), in the PROJECTION BASIS SET block of tools/efp_validation/reference/water_6-31gs_cmo.efp:1711-1743:
+# tests/test_reference_golden_energies.py checks this table against that block.
+# "SP" shells are written out as an s and a p shell over the same exponents; d shells are CARTESIAN (6d),
+# as the reference routes them (test/test_mqc_libcint_cartesian.f90: water is 19 functions in 6-31G*).
+POPLE_631GS = {
+    "H": [(0, [18.73113696, 2.825394365, 0.6401216923], [0.03349460434, 0.2347269535, 0.8137573261]),
+          (0, [0.1612777588], [1.0])],
+    "O": [(0, [5484.671660, 825.2349460, 188.0469580, 52.96450000, 16.89757040, 5.799635340],
+              [0.001831074430, 0.01395017220, 0.06844507810, 0.2327143360, 0.4701928980, 0.3585208530]),
+          (0, [15.53961625, 3.599933586, 1.013761750], [-0.1107775495, -0.1480262627, 1.130767015]),
+          (1, [15.53961625, 3.599933586, 1.013761750], [0.07087426823, 0.3397528391, 0.7271585773]),
+          (0, [0.2700058226], [1.0]),
+          (1, [0.2700058226], [1.0]),
+          (2, [0.8000000000], [1.0])],
+}
+# 6-31G**: the same plus a p shell (exponent 1.1) on H; carbon from the same papers.  No file of the reference
+# tree holds the carbon numbers: what confirms them is that the CH4 energy below comes out to 2e-12.
+POPLE_631GSS = {
+    "H": POPLE_631GS["H"] + [(1, [1.1000000000], [1.0])],
+    "O": POPLE_631GS["O"],
+    "C": [(0, [3047.524880, 457.3695180, 103.9486850, 29.21015530, 9.286662960, 3.163926960],
+              [0.001834737132, 0.01403732281, 0.06884262226, 0.2321844432, 0.4679413484, 0.3623119853]),
+          (0, [7.868272350, 1.881288540, 0.5442492580], [-0.1193324198, -0.1608541517, 1.143456438]),
+          (1, [7.868272350, 1.881288540, 0.5442492580], [0.06899906659, 0.3164239610, 0.7443082909]),
+          (0, [0.1687144782], [1.0]),
+          (1, [0.1687144782], [1.0]),
+          (2, [0.8000000000], [1.0])],
+}
+BOHR_TO_ANGSTROM = 0.529177210903           # src/core/mqc_physical_constants.F90:35 (CODATA 2018, the default)
+# validation/inputs/sample_inputs/w1.xyz (Angstrom), the geometry of validation_tests_cpu.json:899-904:
+# "RHF H2O 6-31g* density fitted with 6-31g*", expected_energy -76.188111755038 (manifest tolerance 1e-9)
+W1_ANGSTROM = [[0.00000000000000, 0.00000000009155, 0.10077199490609],
+               [0.00000000000000, 0.77250895271063, -0.46780199741728],
+               [0.00000000000000, -0.77250895280218, -0.46780199748881]]
+H2O_631GS_DF = (["O", "H", "H"], [[x / BOHR_TO_ANGSTROM for x in row] for row in W1_ANGSTROM], 10, -76.188111755038)
+# the same molecule and basis WITHOUT density fitting: validation_tests_cpu.json:719-723 "RHF H2O 6-31g* (CPU)"
+H2O_631GS_EXACT_ENERGY = -76.010317945971
+# validation/inputs/sample_inputs/ch4.xyz (Angstrom); validation_tests_cpu.json:905-910
+# "RHF CH4 6-31g** density fitted with 6-31g**", expected_energy -40.381603512964
+_CH4_A = 0.62757974260912
+CH4_ANGSTROM = [[0.0, 0.0, 0.0], [_CH4_A, _CH4_A, _CH4_A], [_CH4_A, -_CH4_A, -_CH4_A], [-_CH4_A, _CH4_A, -_CH4_A],
+                [-_CH4_A, -_CH4_A, _CH4_A]]
+CH4_631GSS_DF = (["C", "H", "H", "H", "H"], [[x / BOHR_TO_ANGSTROM for x in row] for row in CH4_ANGSTROM], 10,
+                 -40.381603512964)
+DF_CASES = {"h2o_631gs": (H2O_631GS_DF, POPLE_631GS), "ch4_631gss": (CH4_631GSS_DF, POPLE_631GSS)}
+
+
+def _single(f: BasisFunction):
+    """An auxiliary function as a 'pair' with a unit s function of exponent 0 on the same centre."""
+    return [_Pair(a, f.lmn, f.center, ca, 0.0, (0, 0, 0), f.center, 1.0) for ca, a in zip(f.coefs, f.exps)]
+
+
+def three_centre(basis, aux) -> np.ndarray:
+    """(mu nu|P), shape (n, n, naux): what `three_centre` of the reference hands to build_df_tensor
+    (mqc_libcint_integrals.F90:913-990), flattened there as three(mu + n*nu, P)."""
+    n, naux = len(basis), len(aux)
+    singles = [_single(f) for f in aux]
+    out = np.zeros((n, n, naux))
+    for i in range(n):
+        for j in range(i + 1):
+            pr = _pairs(basis[i], basis[j])
+            for k in range(naux):
+                out[i, j, k] = out[j, i, k] = _eri_pairs(pr, singles[k])
+    return out
+
+
+def two_centre(aux) -> np.ndarray:
+    """(P|Q), the Coulomb metric of the auxiliary basis."""
+    naux = len(aux)
+    singles = [_single(f) for f in aux]
+    out = np.zeros((naux, naux))
+    for i in range(naux):
+        for j in range(i + 1):
+            out[i, j] = out[j, i] = _eri_pairs(singles[i], singles[j])
+    return out
+
+
+def df_case_integrals(name: str):
+    """(S, H, three(n*n, naux) column-major flattened, metric(naux, naux), E_nuc, n_electrons, E_reference) of one
+    of the reference's density-fitted validation cases: the inputs of build_df_tensor + run_libcint_rhf(aux=...).
+    The auxiliary basis is the orbital basis itself, as the validation inputs ask (aux_basis == basis)."""
+    (symbols, coords, n_electrons, e_ref), table = DF_CASES[name]
+    basis = build_basis(symbols, coords, table)
+    aux = build_basis(symbols, coords, table)
+    charges = [CHARGE[s] for s in symbols]
+    s, t, v = one_electron(basis, charges, coords)
+    n, naux = len(basis), len(aux)
+    three = np.asfortranarray(three_centre(basis, aux).reshape(n * n, naux, order="F"))   # (mu + n*nu, P), integrals.F90:985
+    return s, t + v, three, two_centre(aux), nuclear_repulsion(charges, coords), n_electrons, e_ref
 
 
 def molecule_integrals(symbols, coords):

@@ -10,6 +10,17 @@ oracle holds: the exact-integral restatement, and the density-fitted restatement
 plain C, C on BLAS) on a tensor that fits the four-index integrals exactly.  That ties the
 factor 2 of K, the 1/2 of the Fock matrix, the energy expression and the (mu,nu) flattening of
 the fitted path to numbers the reference itself holds.
+
+Second half of the file -- the DENSITY-FITTED path proper.  The reference's validation manifest
+(validation/validation_tests_cpu.json, tolerance 1e-9 Eh: validation/run_validation.py:398) holds
+    H2O / 6-31G*  fitted with 6-31G*    E = -76.188111755038   (:899-904)   [exact integrals: -76.010317945971, :719-723]
+    CH4 / 6-31G** fitted with 6-31G**   E = -40.381603512964   (:905-910)
+through ``build_df_tensor`` (three_centre -> metric_inverse_sqrt -> whitening GEMM) and ``build_fock_df``
+inside ``run_libcint_rhf``.  6-31G* / 6-31G** are published data (oracle/gto_integrals.py cites the papers;
+the H and O numbers are cross-checked below against the copy the reference tree holds in GAMESS form), so
+the whole fitted path of the oracle -- (mu nu|P), (P|Q), metric^(-1/2) with its 1e-10 threshold, the
+(mu + n*nu, P) flattening, J, K with its factor 2, the energy -- is run on real integrals and must land on
+those numbers.  The fitting error here is 0.18 Eh: an agreement to 1e-9 leaves no room for a wrong convention.
 """
 import numpy as np
 import pytest
@@ -86,3 +97,115 @@ def test_fitted_scf_on_an_exactly_fitting_tensor_reproduces_it_too(molecule, bui
         return f, oracle.electronic_energy(h_, f, density)
     res = scf.run_rhf(h, s, n_electrons, fock_builder, e_nuc=e_nuc)
     assert res["converged"] and abs(res["energy"] - e_ref) < TOL_E
+
+
+# =====================================================================================================
+# The density-fitted validation energies of the reference (see the module docstring)
+# =====================================================================================================
+@pytest.fixture(scope="module", params=list(gto.DF_CASES))
+def df_case(request):
+    s, h, three, metric, e_nuc, n_electrons, e_ref = gto.df_case_integrals(request.param)
+    return request.param, s, h, three, metric, e_nuc, n_electrons, e_ref
+
+
+def _plain_c_builder(n):
+    import ctypes
+    import os
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(oracle.__file__), "_build", "libdf_fock_ref.so"))
+    dp = ctypes.c_void_p
+    lib.df_ref_build_fock.restype = ctypes.c_int
+    lib.df_ref_build_fock.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_int,
+                                      ctypes.c_double, ctypes.c_double, dp]
+
+    def build(h_, b_, density, coeff, n_occ):
+        out = np.empty((n, n), order="F")
+        hh, bb, dd, cc = (np.asfortranarray(x, dtype=np.float64) for x in (h_, b_, density, coeff))
+        assert lib.df_ref_build_fock(n, b_.shape[1], n_occ, hh.ctypes.data, bb.ctypes.data, dd.ctypes.data,
+                                     cc.ctypes.data, cc.shape[0], 1.0, 1.0, out.ctypes.data) == 0
+        return out
+    return build
+
+
+@pytest.mark.parametrize("builder", ["numpy_loops", "plain_c", "c_on_blas"])
+def test_density_fitted_scf_reproduces_the_reference_held_df_energy(df_case, builder):
+    name, s, h, three, metric, e_nuc, n_electrons, e_ref = df_case
+    n, naux = h.shape[0], metric.shape[0]
+    assert (n, naux) == {"h2o_631gs": (19, 19), "ch4_631gss": (35, 35)}[name]     # test_mqc_libcint_cartesian.f90:265-274: B is (361, 19)
+    b = oracle.whiten(three, metric)                                                 # integrals.F90:981-987
+    assert b.shape == (n * n, naux)
+    if builder == "numpy_loops":
+        build = oracle.build_fock_df
+    elif builder == "c_on_blas":
+        from oracle import df_fock_blas
+        build = df_fock_blas.build_fock_df
+    else:
+        build = _plain_c_builder(n)
+
+    def fock_builder(h_, density, coeff, n_occ):
+        f = build(h_, b, density, coeff, n_occ)
+        return f, oracle.electronic_energy(h_, f, density)
+    res = scf.run_rhf(h, s, n_electrons, fock_builder, e_nuc=e_nuc, energy_tol=1e-12, density_tol=1e-10, max_iter=100)
+    assert res["converged"] and abs(res["energy"] - e_ref) < TOL_E, res["energy"]
+    if builder == "numpy_loops":
+        plain = scf.run_rhf(h, s, n_electrons, fock_builder, e_nuc=e_nuc, energy_tol=1e-12, density_tol=1e-10,
+                            diis_vectors=0, max_iter=300)
+        assert plain["converged"] and abs(plain["energy"] - e_ref) < TOL_E
+
+
+def test_the_fitting_error_itself_matches():
+    """check_df.f90:60-63 asserts the gap between the fitted and the exact energy, "the sharper one": a fitted
+    energy could come out right with a wrong metric if errors cancelled, the error itself could not.  Same here on
+    the pair of numbers the manifest holds for water / 6-31G*: exact integrals through build_fock (rhf.f90:1491-1574)."""
+    (symbols, coords, n_electrons, e_df), table = gto.DF_CASES["h2o_631gs"]
+    basis = gto.build_basis(symbols, coords, table)
+    charges = [gto.CHARGE[x] for x in symbols]
+    s, t, v = gto.one_electron(basis, charges, coords)
+    eri = gto.electron_repulsion(basis)
+    h = t + v
+
+    def fock_builder(h_, density, coeff, n_occ):
+        f = oracle.build_fock_eri(h_, eri, density)
+        return f, oracle.electronic_energy(h_, f, density)
+    exact = scf.run_rhf(h, s, n_electrons, fock_builder, e_nuc=gto.nuclear_repulsion(charges, coords),
+                        energy_tol=1e-12, density_tol=1e-10)
+    assert exact["converged"] and abs(exact["energy"] - gto.H2O_631GS_EXACT_ENERGY) < TOL_E
+    _, _, three, metric, e_nuc, _, _ = gto.df_case_integrals("h2o_631gs")
+    b = oracle.whiten(three, metric)
+
+    def df_builder(h_, density, coeff, n_occ):
+        f = oracle.build_fock_df(h_, b, density, coeff, n_occ)
+        return f, oracle.electronic_energy(h_, f, density)
+    fitted = scf.run_rhf(h, s, n_electrons, df_builder, e_nuc=e_nuc, energy_tol=1e-12, density_tol=1e-10)
+    gap_ref = e_df - gto.H2O_631GS_EXACT_ENERGY                    # -0.177793809067
+    assert abs((fitted["energy"] - exact["energy"]) - gap_ref) < TOL_E
+    assert abs(gap_ref) > 0.1                                      # a coarse fit on purpose: nothing cancels by accident
+
+
+def test_basis_table_agrees_with_the_copy_the_reference_tree_holds():
+    """tools/efp_validation/reference/water_6-31gs_cmo.efp:1711-1743 (PROJECTION BASIS SET, written by GAMESS from
+    the same 6-31G* water): exponents, and contraction coefficients multiplied by the primitive norms, to eight
+    digits.  The numbers below are that block; the table of oracle/gto_integrals.py must reproduce them."""
+    import math
+    held = {
+        ("O", 0, 0): ([5484.6716600000, 825.2349460000, 188.0469580000, 52.9645000000, 16.8975704000, 5.7996353400],
+                      [0.83172368, 1.53081556, 2.47714854, 3.25628110, 2.79289337, 0.95493768]),
+        ("O", 1, 0): ([15.5396162453, 3.5999335863, 1.0137617501], [-0.61793396, -0.27572093, 0.81420760]),
+        ("O", 2, 1): ([15.5396162453, 3.5999335863, 1.0137617501], [3.11694427, 2.40143753, 1.05436042]),
+        ("O", 3, 0): ([0.2700058226], [0.26695616]),
+        ("O", 4, 1): ([0.2700058226], [0.27743197]),
+        ("O", 5, 2): ([0.8000000000], [1.11382493]),
+        ("H", 0, 0): ([18.7311369600, 2.8253943648, 0.6401216923], [0.21493545, 0.36457120, 0.41505143]),
+        ("H", 1, 0): ([0.1612777588], [0.18138065]),
+    }
+
+    def double_factorial(k):
+        return 1 if k <= 0 else k * double_factorial(k - 2)
+    for (sym, idx, l), (exps, gamess) in held.items():
+        shell_l, t_exps, t_coefs = gto.POPLE_631GS[sym][idx]
+        assert shell_l == l and len(t_exps) == len(exps)
+        for a_held, a_table in zip(exps, t_exps):
+            assert abs(a_held - a_table) <= 1e-9 * a_held + 5e-10            # the table carries BSE's ten digits
+        # GAMESS prints coefficient * norm of the primitive x^l exp(-a r^2)
+        for a, c, g in zip(t_exps, t_coefs, gamess):
+            norm = (2.0 * a / math.pi) ** 0.75 * (4.0 * a) ** (l / 2.0) / math.sqrt(double_factorial(2 * l - 1))
+            assert abs(c * norm - g) <= 2e-8 * max(1.0, abs(g)), (sym, idx, a)

@@ -10,19 +10,28 @@ does (``tests/test_no_oracle_in_product.py`` enforces that).
 PARITY PIN.  The reference (JorgeG94/metalquicha) is Fortran; this image has no Fortran
 compiler, no libcint/libfint, no pic-blas and no basis-set bundle, so the reference cannot
 be compiled or run here, and none of its tests asserts a J, K, F or c_P element (SURVEY.md
-section 8c).  What it DOES hold are total energies -- and two of them come with their basis
-written out inline: H2 and H2O in STO-3G (validation/check_rhf.f90:54-153, 1e-9 Eh against
-PySCF).  With the integrals restated (oracle/gto_integrals.py) the SCF restatement
-(oracle/scf_oracle.py) reproduces both to 3e-11 Eh through ``build_fock_eri`` AND through
-``build_fock_df`` on a tensor that fits the four-index integrals exactly
-(tests/test_reference_golden_energies.py) -- which pins the factor 2 of K, the 1/2 of F, the
-energy expression and the flattening of the fitted path to reference-held numbers.  The CUDA
-engine runs the same SCF to the same energies (tests/test_gpu_golden_scf.py).  The energies
-that need the named basis sets (cc-pVDZ/JKFIT, def2, 6-31G*) stay unasserted
-(tests/golden/reference_energies.json).  Beyond that pin the restatement follows the
-reference *loop for loop* with file:line citations, is cross-checked against two independent
-C restatements (``oracle/df_fock_ref.c``, ``oracle/df_fock_blas.c``), and satisfies the
-reference's own algebraic identities (tests/test_oracle.py).
+section 8c).  What it DOES hold are total energies, and this oracle is pinned to them
+(tests/test_reference_golden_energies.py, with the integrals restated in oracle/gto_integrals.py):
+
+* the reference's own DENSITY-FITTED validation energies -- water/6-31G* fitted with 6-31G*
+  (-76.188111755038) and CH4/6-31G** fitted with 6-31G** (-40.381603512964),
+  validation/validation_tests_cpu.json:899-910, tolerance 1e-9 Eh -- are reproduced to 2e-12 Eh
+  through ``metric_inverse_sqrt`` -> ``whiten`` -> ``build_fock_df`` inside the restated SCF loop
+  (oracle/scf_oracle.py), and so is the fitting error against the exact-integral energy
+  (-0.178 Eh: nothing cancels by accident).  6-31G* is published data; the H and O numbers are
+  cross-checked against the copy the reference tree holds in GAMESS form;
+* H2 and H2O in STO-3G (validation/check_rhf.f90:54-153, basis written out inline there) to 3e-11 Eh
+  through ``build_fock_eri`` AND through ``build_fock_df`` on a tensor that fits the four-index
+  integrals exactly.
+
+That pins the metric threshold and inverse square root, the whitening and its (mu + n*nu, P)
+flattening, the Coulomb contraction, the factor 2 of K, the 1/2 of F and the energy expression to
+reference-held numbers.  The CUDA engine runs the same cases (tests/test_gpu_reference_df_energies.py,
+tests/test_gpu_golden_scf.py).  The energies that need the other named basis sets (cc-pVDZ with
+JKFIT/RIFIT, def2) or the XC quadrature stay unasserted (tests/golden/reference_energies.json).
+Beyond the pin the restatement follows the reference *loop for loop* with file:line citations, is
+cross-checked against two independent C restatements (``oracle/df_fock_ref.c``,
+``oracle/df_fock_blas.c``), and satisfies the reference's own algebraic identities (tests/test_oracle.py).
 
 All arrays are float64.  Matrices use the reference's layout: ``b`` is
 ``(n*n, naux)`` with slab ``b[:, p]`` holding the symmetric ``n x n`` matrix of

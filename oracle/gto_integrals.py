@@ -229,6 +229,17 @@ STO3G = {
           (0, [5.0331513, 1.1695961, 0.3803890], [-0.09996723, 0.39951283, 0.70011547]),
           (1, [5.0331513, 1.1695961, 0.3803890], [0.15591627, 0.60768372, 0.39195739])],
 }
+# STO-3G in the ten digits the Basis Set Exchange distributes (the reference's named "sto-3g").  The inline table
+# above is an older tabulation of the same set with seven to eight significant digits (the two agree to 3e-7
+# relative: tests/test_reference_golden_energies.py); it is what check_rhf.f90 itself uses, but the twelve-digit
+# energies of the validation manifest were computed with the named set and need these digits (with the inline
+# table the UHF energy below comes out 2.7e-8 off, with this one 4e-12).
+STO3G_BSE = {
+    "H": [(0, [3.425250914, 0.6239137298, 0.1688554040], [0.1543289673, 0.5353281423, 0.4446345422])],
+    "O": [(0, [130.7093214, 23.80886605, 6.443608313], [0.1543289673, 0.5353281423, 0.4446345422]),
+          (0, [5.033151319, 1.169596125, 0.3803889600], [-0.09996722919, 0.3995128261, 0.7001154689]),
+          (1, [5.033151319, 1.169596125, 0.3803889600], [0.1559162750, 0.6076837186, 0.3919573931])],
+}
 CHARGE = {"H": 1, "C": 6, "O": 8}
 
 
@@ -297,6 +308,9 @@ CH4_ANGSTROM = [[0.0, 0.0, 0.0], [_CH4_A, _CH4_A, _CH4_A], [_CH4_A, -_CH4_A, -_C
                 [-_CH4_A, -_CH4_A, _CH4_A]]
 CH4_631GSS_DF = (["C", "H", "H", "H", "H"], [[x / BOHR_TO_ANGSTROM for x in row] for row in CH4_ANGSTROM], 10,
                  -40.381603512964)
+# validation/inputs/sample_inputs/oh.xyz (Angstrom); validation_tests_cpu.json:1844-1849
+# "UHF OH sto-3g multiplicity 2 (CPU)", expected_energy -74.362637545612: the reference-held two-spin energy
+OH_STO3G_UHF = (["O", "H"], [[0.0, 0.0, 0.0], [0.0, 0.0, 0.9697 / BOHR_TO_ANGSTROM]], 9, 2, -74.362637545612)
 DF_CASES = {"h2o_631gs": (H2O_631GS_DF, POPLE_631GS), "ch4_631gss": (CH4_631GSS_DF, POPLE_631GSS)}
 
 
@@ -344,9 +358,9 @@ def df_case_integrals(name: str):
     return s, t + v, three, two_centre(aux), nuclear_repulsion(charges, coords), n_electrons, e_ref
 
 
-def molecule_integrals(symbols, coords):
-    """(S, H = T + V, eri, E_nuc) of a molecule in the inline STO-3G basis."""
-    basis = build_basis(symbols, coords)
+def molecule_integrals(symbols, coords, table=STO3G):
+    """(S, H = T + V, eri, E_nuc) of a molecule (default: the inline STO-3G basis of check_rhf.f90)."""
+    basis = build_basis(symbols, coords, table)
     charges = [CHARGE[s] for s in symbols]
     s, t, v = one_electron(basis, charges, coords)
     return s, t + v, electron_repulsion(basis), nuclear_repulsion(charges, coords)

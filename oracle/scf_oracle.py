@@ -18,6 +18,7 @@ Pieces and their sources:
   DIIS                   src/methods/mqc_diis.f90:94-275       ring of 8, scaled B matrix, pivoted elimination
   loop / convergence     mqc_libcint_rhf.f90:566-636           iter > 1 and |dE| < e_tol and rms(dD) < d_tol
   final rebuild          mqc_libcint_rhf.f90:646-649
+  run_uhf                mqc_libcint_rhf.f90:682-974           the two-spin loop: one DIIS subspace over both spins
 """
 from __future__ import annotations
 
@@ -156,6 +157,71 @@ def run_rhf(h, s, n_electrons, fock_builder, e_nuc=0.0, max_iter=100, energy_tol
     return {"energy": electronic + e_nuc, "electronic": electronic, "nuclear_repulsion": e_nuc,
             "iterations": iterations, "converged": converged, "orbitals": coeff,
             "orbital_energies": eigenvalues, "density": density, "n_occupied": n_occ}
+
+
+UHF_DIIS_START = 4                  # DEFAULT_UHF_DIIS_START, mqc_libcint_rhf.f90:51
+
+
+def spin_contamination(c_alpha, c_beta, overlap, n_alpha, n_beta):
+    """<S^2> = S_z(S_z+1) + n_beta - sum_ij |<phi_i^a|phi_j^b>|^2      src/scf/mqc_scf_common.f90:111-138"""
+    sz = 0.5 * (n_alpha - n_beta)
+    s2 = sz * (sz + 1.0) + n_beta
+    if n_alpha == 0 or n_beta == 0:
+        return s2
+    mo = c_alpha[:, :n_alpha].T @ (overlap @ c_beta[:, :n_beta])
+    return s2 - float(np.sum(mo ** 2))
+
+
+def run_uhf(h, s, n_electrons, multiplicity, fock_builder, e_nuc=0.0, max_iter=100, energy_tol=1e-10,
+            density_tol=1e-8, diis_vectors=8, guess="gwh"):
+    """``run_libcint_uhf`` (mqc_libcint_rhf.f90:682-974) around
+    ``fock_builder(h, d_alpha, d_beta, c_alpha, n_alpha, c_beta, n_beta) -> (fock_a, fock_b, e_elec)``:
+    occupations from the multiplicity (:767-789), the same symmetric guess for both spins (:846-852), ONE DIIS
+    subspace over both spins -- the two Fock matrices laid end to end, the two commutators likewise, extrapolating
+    from cycle 4 (:835-838, :900-912) -- the convergence test on |dE| and the rms over both densities (:927-935),
+    and the final rebuild (:939-943)."""
+    if multiplicity < 1 or (n_electrons + multiplicity - 1) % 2:
+        raise ValueError("UHF: an electron count and multiplicity that cannot be paired -- their parities disagree")
+    n_alpha = (n_electrons + multiplicity - 1) // 2
+    n_beta = n_electrons - n_alpha
+    n = h.shape[0]
+    x = build_orthogonalizer(s)
+    fock_a = guess_fock_gwh(s, h) if guess == "gwh" else np.array(h, copy=True)
+    fock_b = fock_a.copy()
+    c_a, eig_a = diagonalize(fock_a, x)
+    c_b, eig_b = diagonalize(fock_b, x)
+    d_a = c_a[:, :n_alpha] @ c_a[:, :n_alpha].T
+    d_b = c_b[:, :n_beta] @ c_b[:, :n_beta].T
+    diis = Diis(diis_vectors)
+    e_old, converged, iterations = 0.0, False, 0
+    for it in range(1, max_iter + 1):
+        d_a_old, d_b_old = d_a, d_b
+        fock_a, fock_b, e_elec = fock_builder(h, d_a, d_b, c_a, n_alpha, c_b, n_beta)
+        if diis_vectors > 0:
+            err = np.concatenate([commutator(fock_a, d_a, s, x).reshape(-1, order="F"),
+                                  commutator(fock_b, d_b, s, x).reshape(-1, order="F")])
+            flat = np.concatenate([fock_a.reshape(-1, order="F"), fock_b.reshape(-1, order="F")])
+            diis.push(flat, err)
+            if it >= UHF_DIIS_START:
+                flat, ok = diis.extrapolate(flat)
+                if ok:
+                    fock_a = flat[:n * n].reshape(n, n, order="F")
+                    fock_b = flat[n * n:].reshape(n, n, order="F")
+        c_a, eig_a = diagonalize(fock_a, x)
+        c_b, eig_b = diagonalize(fock_b, x)
+        d_a = c_a[:, :n_alpha] @ c_a[:, :n_alpha].T
+        d_b = c_b[:, :n_beta] @ c_b[:, :n_beta].T
+        de = abs(e_elec - e_old)
+        drms = float(np.sqrt((np.sum((d_a - d_a_old) ** 2) + np.sum((d_b - d_b_old) ** 2)) / (2 * n * n)))
+        e_old, iterations = e_elec, it
+        if it > 1 and de < energy_tol and drms < density_tol:
+            converged = True
+            break
+    _, _, electronic = fock_builder(h, d_a, d_b, c_a, n_alpha, c_b, n_beta)
+    return {"energy": electronic + e_nuc, "electronic": electronic, "iterations": iterations, "converged": converged,
+            "orbitals": c_a, "orbitals_beta": c_b, "density": d_a, "density_beta": d_b,
+            "n_occupied": n_alpha, "n_occupied_beta": n_beta,
+            "spin_squared": spin_contamination(c_a, c_b, s, n_alpha, n_beta)}
 
 
 def exact_fit_tensor(eri, tol=1e-13):

@@ -209,3 +209,41 @@ def test_basis_table_agrees_with_the_copy_the_reference_tree_holds():
         for a, c, g in zip(t_exps, t_coefs, gamess):
             norm = (2.0 * a / math.pi) ** 0.75 * (4.0 * a) ** (l / 2.0) / math.sqrt(double_factorial(2 * l - 1))
             assert abs(c * norm - g) <= 2e-8 * max(1.0, abs(g)), (sym, idx, a)
+
+
+# =====================================================================================================
+# The two-spin build against a reference-held unrestricted energy
+# =====================================================================================================
+def test_two_spin_fitted_build_reproduces_the_reference_held_uhf_energy():
+    """validation_tests_cpu.json:1844-1849: UHF OH / STO-3G, doublet, E = -74.362637545612 (1e-9), computed by
+    run_libcint_uhf with build_fock_uhf (mqc_libcint_rhf.f90:682-974, :1648-1681).  The reference's CPU path has no
+    fitted two-spin build; the engine's (and the oracle's jk_df_uhf) takes its conventions from the cuEST loop --
+    J from the TOTAL density, K_sigma = sum_P (B_P C_sigma)(B_P C_sigma)^T with no factor 2, the energy
+    1/2 [sum (Da+Db) H + sum Da Fa + sum Db Fb].  On a tensor that fits the four-index integrals exactly the
+    fitted two-spin build IS build_fock_uhf, so the restated loop must land on the reference's number."""
+    symbols, coords, n_electrons, multiplicity, e_ref = gto.OH_STO3G_UHF
+    s, h, eri, e_nuc = gto.molecule_integrals(symbols, coords, gto.STO3G_BSE)
+    b = scf.exact_fit_tensor(eri)
+    n = h.shape[0]
+    assert np.max(np.abs((b @ b.T).reshape(n, n, n, n, order="F") - eri)) < 1e-12
+
+    def fock_builder(h_, d_a, d_b, c_a, n_a, c_b, n_b):
+        f_a, f_b = oracle.build_fock_df_uhf(h_, b, d_a, d_b, c_a, n_a, c_b, n_b)
+        return f_a, f_b, oracle.uhf_electronic_energy(h_, f_a, f_b, d_a, d_b)
+    res = scf.run_uhf(h, s, n_electrons, multiplicity, fock_builder, e_nuc=e_nuc, energy_tol=1e-12, density_tol=1e-10)
+    assert res["converged"] and (res["n_occupied"], res["n_occupied_beta"]) == (5, 4)
+    assert abs(res["energy"] - e_ref) < TOL_E, res["energy"]
+    assert 0.75 <= res["spin_squared"] < 0.76                       # a doublet with next to no contamination
+    plain = scf.run_uhf(h, s, n_electrons, multiplicity, fock_builder, e_nuc=e_nuc, energy_tol=1e-12, density_tol=1e-10,
+                        diis_vectors=0, max_iter=300)
+    assert plain["converged"] and abs(plain["energy"] - e_ref) < TOL_E
+
+
+def test_bse_sto3g_table_agrees_with_the_inline_one():
+    """The ten-digit STO-3G table against the inline table of check_rhf.f90:148-178 (an older tabulation with
+    seven to eight significant digits): the same basis set to 3e-7 relative in every exponent and coefficient."""
+    for sym in ("H", "O"):
+        for (l8, e8, c8), (l10, e10, c10) in zip(gto.STO3G[sym], gto.STO3G_BSE[sym]):
+            assert l8 == l10
+            for a, b_ in zip(list(e8) + list(c8), list(e10) + list(c10)):
+                assert abs(a - b_) <= 3e-7 * abs(b_)

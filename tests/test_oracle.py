@@ -111,6 +111,41 @@ def test_identity_v_fitted_build_equals_exact_build_on_fitted_integrals():
         assert np.max(np.abs(f_df - f_eri)) <= 1e-12
 
 
+def test_identity_vi_fitted_response_operators_equal_the_exact_one_on_fitted_integrals():
+    """validation/check_df_cphf.f90 of the reference: "form the fitted integrals in four-index form,
+    (uv|ls)_RI = sum_P B(uv,P) B(ls,P), hand those to the ordinary exact-ERI [operator], and require the two
+    responses to agree to rounding" (:11-16, algebra tolerance 1e-9 at :158).  Here at the operator level, for
+    ``response_operator_df`` (the factorised form, cphf.F90:499-566) and ``fitted_potential_general`` (:568-616),
+    on the REAL water / 6-31G* fitted with 6-31G* tensor (the case whose energy pins the oracle), with an
+    asymmetric trial rotation so that a transposed factor cannot hide behind symmetry (:43)."""
+    from oracle import gto_integrals as gto, scf_oracle as scf
+    s, h, three, metric, e_nuc, n_electrons, _ = gto.df_case_integrals("h2o_631gs")
+    b = oracle.whiten(three, metric)
+    n, naux = h.shape[0], metric.shape[0]
+    slabs = b.T.reshape(naux, n, n)
+    eri_ri = np.einsum("pab,pcd->abcd", slabs, slabs)
+    x_orth = scf.build_orthogonalizer(s)
+    coeff, _ = scf.diagonalize(scf.guess_fock_gwh(s, h), x_orth)
+    n_occ = n_electrons // 2
+    c_occ, c_vir = coeff[:, :n_occ], coeff[:, n_occ:]
+    u = np.array([[1.0 / (a + 2 * i + 3) for i in range(n_occ)] for a in range(n - n_occ)])    # the rhs pattern of :111
+    x = c_vir @ u
+    dtilde = x @ c_occ.T + c_occ @ x.T
+    for ks in (None, 0.25, 0.0):
+        exact = oracle.build_fock_eri(np.zeros((n, n)), eri_ri, dtilde, k_scale=ks)            # J[Dt] - kf/2 K[Dt]
+        g = oracle.response_operator_df(b, x, c_occ, dtilde, k_scale=ks)
+        assert np.max(np.abs(g - exact)) <= 1e-11 * max(1.0, float(np.max(np.abs(exact))))
+        g2 = oracle.fitted_potential_general(b, dtilde, k_scale=ks)
+        assert np.max(np.abs(g2 - exact)) <= 1e-11 * max(1.0, float(np.max(np.abs(exact))))
+    # an unstructured symmetric, indefinite, traceless density (check_fitted_reference_gradient.f90:27-33)
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((n, n))
+    d = a + a.T
+    d -= np.trace(d) / n * np.eye(n)
+    exact = oracle.build_fock_eri(np.zeros((n, n)), eri_ri, d, k_scale=0.5)
+    assert np.max(np.abs(oracle.fitted_potential_general(b, d, k_scale=0.5) - exact)) <= 1e-11 * float(np.max(np.abs(exact)))
+
+
 def test_metric_inverse_sqrt_drops_null_modes():
     """Eigenvalues <= 1e-10 are zeroed, not errored (integrals.F90:1002,1027-1033)."""
     _, metric = synth.synth_physical_like_tensor(7, 4, 12, n_null=3)

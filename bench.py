@@ -997,6 +997,39 @@ def run_farm_scf_batched(ctx, problems, k):
 
 
 # ------------------------------------------------------------------------------------------
+def run_reference_pin(make_plain_engine):
+    """Parity against a number the REFERENCE holds, inside the bench line: the reference's own density-fitted
+    validation case -- water / 6-31G* fitted with 6-31G*, validation/validation_tests_cpu.json:899-904,
+    E = -76.188111755038, manifest tolerance 1e-9 Eh -- with every Fock build of the SCF loop done by the engine
+    (bmat from the restated integrals, oracle/gto_integrals.py; the loop is the oracle's restatement of
+    run_libcint_rhf: checker code, as in the parity block), then the whole loop device-resident on the same tensor.
+    Not timed, rank 0 only, on its own engine handle (no communicator)."""
+    import numpy as np
+    from oracle import df_fock_oracle as oracle
+    from oracle import gto_integrals as gto
+    from oracle import scf_oracle as scf
+    t0 = time.perf_counter()
+    s_mat, h_mat, three, metric, e_nuc, n_electrons, e_ref = gto.df_case_integrals("h2o_631gs")
+    eng = make_plain_engine()
+    try:
+        eng.set_tensor(np.asfortranarray(oracle.whiten(three, metric)))
+
+        def fock_builder(h_, density, coeff, n_occ):
+            f = eng.build_fock_df(np.asfortranarray(h_), np.asfortranarray(density), np.asfortranarray(coeff), n_occ)
+            return f, eng.last_energy()
+        res = scf.run_rhf(h_mat, s_mat, n_electrons, fock_builder, e_nuc=e_nuc)
+        dev = eng.run_scf(np.asfortranarray(h_mat), np.asfortranarray(s_mat), n_electrons, e_nuc=e_nuc)
+    finally:
+        eng.close()
+    err, err_dev = float(abs(res["energy"] - e_ref)), float(abs(dev["energy"] - e_ref))
+    return {"case": "H2O RHF/6-31G* density-fitted with 6-31G* (validation/validation_tests_cpu.json:899-904 of the reference)",
+            "reference_held_energy": float(e_ref), "tolerance": 1e-9,
+            "energy_fock_builds_on_gpu": float(res["energy"]), "abs_err": err, "iterations": int(res["iterations"]),
+            "energy_whole_loop_on_gpu": float(dev["energy"]), "abs_err_whole_loop_on_gpu": err_dev,
+            "ok": bool(res["converged"] and err <= 1e-9 and dev["converged"] and err_dev <= 1e-7),
+            "wall_s": time.perf_counter() - t0}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1009,6 +1042,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-setup-timings", action="store_true")
+    ap.add_argument("--no-reference-pin", action="store_true")
     ap.add_argument("--k-scale", type=float, default=None)
     ap.add_argument("--workers-per-gpu", type=int, default=4, help="fragment farm: host workers (engine handles) per GPU")
     ap.add_argument("--farm-pop", type=int, default=4, help="fragment farm: ids taken per round trip to the shared queue")
@@ -1093,6 +1127,13 @@ def main():
             if key not in ("value", "unit", "ms_per_step", "steps"):
                 line[key] = val
         line["workloads"] = {k: v for k, v in results.items() if k != args.workload}
+        if not args.no_reference_pin and not args.no_parity:
+            try:
+                line["reference_pin"] = run_reference_pin(lambda: B200FockEngine(ctx.local_rank))
+                log(f"reference-held DF energy: |dE| = {line['reference_pin']['abs_err']:.2e} (Fock builds on the GPU), "
+                    f"{line['reference_pin']['abs_err_whole_loop_on_gpu']:.2e} (whole loop on the GPU)")
+            except Exception as ex:              # a check beside the headline never sinks it
+                line["reference_pin"] = {"error": str(ex)[:300]}
         line["bench_wall_s"] = time.perf_counter() - t_start
         emit(line)
     if world > 1:

@@ -31,39 +31,42 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
-def test_reference_pin_block_is_serialisable_and_lands_on_the_reference_energy():
+def test_reference_pin_block_is_serialisable_and_lands_on_the_reference_energy(tmp_path):
     """bench.run_reference_pin with a stand-in engine backed by the oracle (the real one needs a GPU; the same
     calls run on a B200 in tests/test_gpu_reference_df_energies.py): the block must be plain JSON and must
-    reproduce the reference-held density-fitted energy."""
-    import importlib.util
-    import numpy as np
-    from oracle import df_fock_oracle as oracle, scf_oracle as scf
-    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bench)
+    reproduce the reference-held density-fitted energy.  Run in a child process: importing bench.py claims
+    file descriptor 1 for its one JSON line, which must not happen to the test runner."""
+    out_file = tmp_path / "pin.json"
+    code = f"""
+import importlib.util, json, os, sys
+import numpy as np
+sys.path.insert(0, {ROOT!r})
+from oracle import df_fock_oracle as oracle, scf_oracle as scf
+spec = importlib.util.spec_from_file_location("bench_module", os.path.join({ROOT!r}, "bench.py"))
+bench = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(bench)
 
-    class StandIn:
-        def set_tensor(self, b):
-            self.b = np.asarray(b)
+class StandIn:
+    def set_tensor(self, b):
+        self.b = np.asarray(b)
+    def build_fock_df(self, h, density, coeff, n_occ):
+        assert h.flags.f_contiguous and density.flags.f_contiguous and coeff.flags.f_contiguous
+        self.f = oracle.build_fock_df(h, self.b, density, coeff, n_occ)
+        self.e = oracle.electronic_energy(h, self.f, density)
+        return self.f
+    def last_energy(self):
+        return self.e
+    def run_scf(self, h, s, n_electrons, e_nuc=0.0):
+        def builder(h_, density, coeff, n_occ):
+            f = oracle.build_fock_df(h_, self.b, density, coeff, n_occ)
+            return f, oracle.electronic_energy(h_, f, density)
+        return scf.run_rhf(h, s, n_electrons, builder, e_nuc=e_nuc)
+    def close(self):
+        pass
 
-        def build_fock_df(self, h, density, coeff, n_occ):
-            assert h.flags.f_contiguous and density.flags.f_contiguous and coeff.flags.f_contiguous
-            self.f = oracle.build_fock_df(h, self.b, density, coeff, n_occ)
-            self.e = oracle.electronic_energy(h, self.f, density)
-            return self.f
-
-        def last_energy(self):
-            return self.e
-
-        def run_scf(self, h, s, n_electrons, e_nuc=0.0):
-            def builder(h_, density, coeff, n_occ):
-                f = oracle.build_fock_df(h_, self.b, density, coeff, n_occ)
-                return f, oracle.electronic_energy(h_, f, density)
-            return scf.run_rhf(h, s, n_electrons, builder, e_nuc=e_nuc)
-
-        def close(self):
-            self.closed = True
-
-    block = bench.run_reference_pin(StandIn)
-    json.loads(json.dumps(block))
+open({str(out_file)!r}, "w").write(json.dumps(bench.run_reference_pin(StandIn)))
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    block = json.loads(out_file.read_text())
     assert block["ok"] and block["abs_err"] <= 1e-9 and block["reference_held_energy"] == -76.188111755038

@@ -17,7 +17,8 @@ module mqc_b200_fock
    !!
    !! NOT COMPILED IN THIS REPOSITORY (no Fortran compiler in the build image); the
    !! twin `mqc_b200_fock_stub.f90` is what a build without the engine compiles.
-   use, intrinsic :: iso_c_binding, only: c_ptr, c_null_ptr, c_associated, c_int, c_double, c_char, c_null_char
+   use, intrinsic :: iso_c_binding, only: c_ptr, c_null_ptr, c_associated, c_int, c_double, c_char, c_null_char, &
+                                          c_int64_t
    use pic_types, only: dp
    use mqc_error, only: error_t, ERROR_VALIDATION
    use mqc_b200_iface
@@ -29,6 +30,7 @@ module mqc_b200_fock
    public :: b200_build_fock_df, b200_electronic_energy
    public :: b200_build_fock_df_uhf
    public :: b200_build_df_tensor
+   public :: b200_metric_inverse_sqrt, b200_whiten_begin, b200_whiten_push, b200_whiten_end
    public :: b200_set_tensor_shard, b200_comm_init, b200_comm_unique_id
    public :: b200_response_operator_df, b200_fitted_potential_general
    public :: b200_df_gradient_densities
@@ -219,6 +221,102 @@ contains
       if (mqcb200_build_df_tensor(handle, slot, int(n_ao, c_int), int(size(three, 2), c_int), three, metric, &
                                   1.0e-10_c_double, half) /= MQCB200_OK) call engine_failure("b200: build_df_tensor", error)
    end subroutine b200_build_df_tensor
+
+   subroutine b200_metric_inverse_sqrt(device_rank, metric, half, n_kept, error)
+      !! metric_inverse_sqrt(metric, half, error) (mqc_libcint_integrals.F90:992-1038) on the device: same
+      !! 1e-10 threshold, same zeroed modes, same refusal of a singular metric
+      integer, intent(in) :: device_rank
+      real(dp), intent(in), contiguous :: metric(:, :)
+      real(dp), intent(out), contiguous :: half(:, :)
+      integer, intent(out) :: n_kept
+      type(error_t), intent(inout) :: error
+      type(c_ptr) :: handle
+      integer(c_int) :: kept
+
+      n_kept = 0
+      call get_engine(device_rank, handle, error)
+      if (error%has_error()) return
+      if (size(metric, 1) /= size(metric, 2) .or. size(half, 1) /= size(metric, 1) .or. &
+          size(half, 2) /= size(metric, 2)) then
+         call error%set(ERROR_VALIDATION, "b200: the metric and its inverse square root are (naux, naux)")
+         return
+      end if
+      if (mqcb200_metric_inverse_sqrt(handle, int(size(metric, 1), c_int), metric, 1.0e-10_c_double, half, kept) &
+          /= MQCB200_OK) then
+         call engine_failure("b200: metric_inverse_sqrt", error)
+         return
+      end if
+      n_kept = int(kept)
+   end subroutine b200_metric_inverse_sqrt
+
+   subroutine b200_whiten_begin(device_rank, n_ao, naux_total, q_begin, q_count, half, error, attenuated)
+      !! Start of the slab-streamed b = three . half (mqc_libcint_integrals.F90:981-987) for this rank's
+      !! auxiliary slab [q_begin, q_begin + q_count) (0-based): three(nao*nao, naux) -- 115 GB for the 200-atom
+      !! case -- never has to exist.  Collective over the ranks when b200_comm_init has been called.
+      integer, intent(in) :: device_rank, n_ao, naux_total, q_begin, q_count
+      real(dp), intent(in), contiguous :: half(:, :)
+      type(error_t), intent(inout) :: error
+      logical, intent(in), optional :: attenuated
+      type(c_ptr) :: handle
+      integer(c_int) :: slot
+
+      call get_engine(device_rank, handle, error)
+      if (error%has_error()) return
+      slot = MQCB200_SLOT_FULL_RANGE
+      if (present(attenuated)) then
+         if (attenuated) slot = MQCB200_SLOT_ATTENUATED
+      end if
+      if (size(half, 1) /= naux_total .or. size(half, 2) /= naux_total) then
+         call error%set(ERROR_VALIDATION, "b200: half is (naux, naux)")
+         return
+      end if
+      if (mqcb200_whiten_begin(handle, slot, int(n_ao, c_int), int(naux_total, c_int), int(q_begin, c_int), &
+                               int(q_count, c_int), half) /= MQCB200_OK) call engine_failure("b200: whiten_begin", error)
+   end subroutine b200_whiten_begin
+
+   subroutine b200_whiten_push(nu_begin, three_block, n_ao, error, attenuated)
+      !! One block of (mu nu|P): three_block(nao*nu_count, naux) holds all mu and all P for the orbital
+      !! columns nu in [nu_begin, nu_begin + nu_count) (0-based; whole 16-wide column tiles unless the
+      !! block ends at nao) -- what three_centre produces for a range of shells
+      integer, intent(in) :: nu_begin, n_ao
+      real(dp), intent(in), contiguous :: three_block(:, :)
+      type(error_t), intent(inout) :: error
+      logical, intent(in), optional :: attenuated
+      integer(c_int) :: slot
+
+      if (.not. c_associated(shared_handle)) then
+         call error%set(ERROR_VALIDATION, "b200: whiten_push called before b200_whiten_begin")
+         return
+      end if
+      slot = MQCB200_SLOT_FULL_RANGE
+      if (present(attenuated)) then
+         if (attenuated) slot = MQCB200_SLOT_ATTENUATED
+      end if
+      if (n_ao <= 0 .or. mod(size(three_block, 1), max(n_ao, 1)) /= 0) then
+         call error%set(ERROR_VALIDATION, "b200: a block of the three-centre tensor is (nao*nu_count, naux)")
+         return
+      end if
+      if (mqcb200_whiten_push(shared_handle, slot, int(nu_begin, c_int), int(size(three_block, 1)/n_ao, c_int), &
+                              three_block, int(size(three_block, 1), c_int64_t)) /= MQCB200_OK) &
+         call engine_failure("b200: whiten_push", error)
+   end subroutine b200_whiten_push
+
+   subroutine b200_whiten_end(error, attenuated)
+      !! The tensor becomes usable (collective when sharded: a rank whose push failed fails everyone here)
+      type(error_t), intent(inout) :: error
+      logical, intent(in), optional :: attenuated
+      integer(c_int) :: slot
+
+      if (.not. c_associated(shared_handle)) then
+         call error%set(ERROR_VALIDATION, "b200: whiten_end called before b200_whiten_begin")
+         return
+      end if
+      slot = MQCB200_SLOT_FULL_RANGE
+      if (present(attenuated)) then
+         if (attenuated) slot = MQCB200_SLOT_ATTENUATED
+      end if
+      if (mqcb200_whiten_end(shared_handle, slot) /= MQCB200_OK) call engine_failure("b200: whiten_end", error)
+   end subroutine b200_whiten_end
 
    subroutine b200_set_tensor_shard(device_rank, bmat_shard, n_ao, naux_total, q_begin, error)
       !! This rank's auxiliary slab [q_begin, q_begin + size(bmat_shard, 2)) of a whole-molecule tensor

@@ -16,6 +16,7 @@ module mqc_b200_fock
    public :: b200_build_fock_df, b200_electronic_energy
    public :: b200_build_fock_df_uhf
    public :: b200_build_df_tensor
+   public :: b200_metric_inverse_sqrt, b200_whiten_begin, b200_whiten_push, b200_whiten_end
    public :: b200_set_tensor_shard, b200_comm_init, b200_comm_unique_id
    public :: b200_response_operator_df, b200_fitted_potential_general
    public :: b200_df_gradient_densities
@@ -41,6 +42,43 @@ contains
       call error%set(ERROR_VALIDATION, REFUSAL)
       if (device_rank < 0 .or. n_ao < 0 .or. size(bmat) < 0 .or. present(attenuated)) return
    end subroutine b200_set_tensor
+
+   subroutine b200_metric_inverse_sqrt(device_rank, metric, half, n_kept, error)
+      integer, intent(in) :: device_rank
+      real(dp), intent(in) :: metric(:, :)
+      real(dp), intent(out) :: half(:, :)
+      integer, intent(out) :: n_kept
+      type(error_t), intent(inout) :: error
+      half = 0.0_dp
+      n_kept = 0
+      call error%set(ERROR_VALIDATION, REFUSAL)
+      if (device_rank < 0 .or. size(metric) < 0) return
+   end subroutine b200_metric_inverse_sqrt
+
+   subroutine b200_whiten_begin(device_rank, n_ao, naux_total, q_begin, q_count, half, error, attenuated)
+      integer, intent(in) :: device_rank, n_ao, naux_total, q_begin, q_count
+      real(dp), intent(in) :: half(:, :)
+      type(error_t), intent(inout) :: error
+      logical, intent(in), optional :: attenuated
+      call error%set(ERROR_VALIDATION, REFUSAL)
+      if (device_rank + n_ao + naux_total + q_begin + q_count + size(half) < 0 .or. present(attenuated)) return
+   end subroutine b200_whiten_begin
+
+   subroutine b200_whiten_push(nu_begin, three_block, n_ao, error, attenuated)
+      integer, intent(in) :: nu_begin, n_ao
+      real(dp), intent(in) :: three_block(:, :)
+      type(error_t), intent(inout) :: error
+      logical, intent(in), optional :: attenuated
+      call error%set(ERROR_VALIDATION, REFUSAL)
+      if (nu_begin + n_ao + size(three_block) < 0 .or. present(attenuated)) return
+   end subroutine b200_whiten_push
+
+   subroutine b200_whiten_end(error, attenuated)
+      type(error_t), intent(inout) :: error
+      logical, intent(in), optional :: attenuated
+      call error%set(ERROR_VALIDATION, REFUSAL)
+      if (present(attenuated)) return
+   end subroutine b200_whiten_end
 
    subroutine b200_clear_tensors(error)
       type(error_t), intent(inout) :: error

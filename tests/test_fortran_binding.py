@@ -248,3 +248,36 @@ def test_wrapper_calls_pass_as_many_arguments_as_the_prototypes_take():
             assert n_args == len(protos[name][1]), f"{fn}: {name} called with {n_args} arguments, the header takes {len(protos[name][1])}"
             n_calls += 1
     assert n_calls >= 15            # the wrapper really goes through the interface module
+
+
+def _module_procedures(path):
+    """name -> dummy-argument list of every subroutine/function of a module file (joined source)."""
+    text = _join_continuations(open(path).read())
+    procs = {}
+    for line in text:
+        m = re.match(r"^\s*(?:pure\s+)?(subroutine|function)\s+(\w+)\s*\(([^)]*)\)", line, re.I)
+        if m:
+            procs[m.group(2).lower()] = [a.strip().lower() for a in m.group(3).split(",") if a.strip()]
+    return procs
+
+
+def test_stub_module_offers_the_same_entry_points_with_the_same_arguments():
+    """The refusing stub (what a build without the engine compiles, the reference's own arrangement:
+    src/methods/mqc_libcint_bridge_stub.f90) must be call-compatible with the real module: same public names,
+    same dummy arguments in the same order -- otherwise a call site compiles against one and not the other."""
+    real = os.path.join(FDIR, "mqc_b200_fock.f90")
+    stub = os.path.join(FDIR, "mqc_b200_fock_stub.f90")
+
+    def public_names(path):
+        names = set()
+        for line in _join_continuations(open(path).read()):
+            m = re.match(r"^\s*public\s*::\s*(.*)$", line, re.I)
+            if m:
+                names.update(x.strip().lower() for x in m.group(1).split(","))
+        return names
+    pub_real, pub_stub = public_names(real), public_names(stub)
+    assert pub_real == pub_stub, (sorted(pub_real - pub_stub), sorted(pub_stub - pub_real))
+    procs_real, procs_stub = _module_procedures(real), _module_procedures(stub)
+    for name in sorted(pub_real):
+        assert name in procs_real and name in procs_stub, name
+        assert procs_real[name] == procs_stub[name], f"{name}: {procs_real[name]} vs {procs_stub[name]}"

@@ -1019,6 +1019,24 @@ def run_reference_pin(make_plain_engine):
             return f, eng.last_energy()
         res = scf.run_rhf(h_mat, s_mat, n_electrons, fock_builder, e_nuc=e_nuc)
         dev = eng.run_scf(np.asfortranarray(h_mat), np.asfortranarray(s_mat), n_electrons, e_nuc=e_nuc)
+        # the two-spin build against the reference-held unrestricted energy (UHF OH/STO-3G doublet,
+        # validation_tests_cpu.json:1844-1849) on a tensor that fits the four-index integrals exactly
+        try:
+            symbols, coords, n_el_u, mult, e_ref_u = gto.OH_STO3G_UHF
+            s_u, h_u, eri_u, e_nuc_u = gto.molecule_integrals(symbols, coords, gto.STO3G_BSE)
+            eng.set_tensor(np.asfortranarray(scf.exact_fit_tensor(eri_u)))
+
+            def uhf_builder(h_, d_a, d_b, c_a, n_a, c_b, n_b):
+                f_a, f_b = eng.build_fock_df_uhf(np.asfortranarray(h_), np.asfortranarray(d_a), np.asfortranarray(d_b),
+                                                 np.asfortranarray(c_a), n_a, np.asfortranarray(c_b), n_b)
+                return f_a, f_b, oracle.uhf_electronic_energy(h_, f_a, f_b, d_a, d_b)
+            uhf = scf.run_uhf(h_u, s_u, n_el_u, mult, uhf_builder, e_nuc=e_nuc_u)
+            err_u = float(abs(uhf["energy"] - e_ref_u))
+            two_spin = {"case": "UHF OH/STO-3G doublet (validation/validation_tests_cpu.json:1844-1849), two-spin Fock builds on the GPU",
+                        "reference_held_energy": float(e_ref_u), "energy": float(uhf["energy"]), "abs_err": err_u,
+                        "spin_squared": float(uhf["spin_squared"]), "ok": bool(uhf["converged"] and err_u <= 1e-9)}
+        except Exception as ex:
+            two_spin = {"error": str(ex)[:300]}
     finally:
         eng.close()
     err, err_dev = float(abs(res["energy"] - e_ref)), float(abs(dev["energy"] - e_ref))
@@ -1027,6 +1045,7 @@ def run_reference_pin(make_plain_engine):
             "energy_fock_builds_on_gpu": float(res["energy"]), "abs_err": err, "iterations": int(res["iterations"]),
             "energy_whole_loop_on_gpu": float(dev["energy"]), "abs_err_whole_loop_on_gpu": err_dev,
             "ok": bool(res["converged"] and err <= 1e-9 and dev["converged"] and err_dev <= 1e-7),
+            "two_spin": two_spin,
             "wall_s": time.perf_counter() - t0}
 
 

@@ -56,6 +56,8 @@ class StandIn:
         return self.f
     def last_energy(self):
         return self.e
+    def build_fock_df_uhf(self, h, d_a, d_b, c_a, n_a, c_b, n_b):
+        return oracle.build_fock_df_uhf(h, self.b, d_a, d_b, c_a, n_a, c_b, n_b)
     def run_scf(self, h, s, n_electrons, e_nuc=0.0):
         def builder(h_, density, coeff, n_occ):
             f = oracle.build_fock_df(h_, self.b, density, coeff, n_occ)
@@ -70,3 +72,4 @@ open({str(out_file)!r}, "w").write(json.dumps(bench.run_reference_pin(StandIn)))
     assert out.returncode == 0, out.stderr[-2000:]
     block = json.loads(out_file.read_text())
     assert block["ok"] and block["abs_err"] <= 1e-9 and block["reference_held_energy"] == -76.188111755038
+    assert block["two_spin"]["ok"] and block["two_spin"]["reference_held_energy"] == -74.362637545612

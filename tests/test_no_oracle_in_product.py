@@ -6,17 +6,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_package_and_csrc_do_not_reference_the_oracle():
-    pkg = os.path.join(ROOT, "metalquicha_b200")
+    """The package (kernels, C ABI, Python mirror, Fortran sources) and the public headers (C and C++)."""
     offenders = []
-    for dirpath, _, files in os.walk(pkg):
-        if os.path.basename(dirpath) == "build":
-            continue
-        for f in files:
-            if not f.endswith((".py", ".cu", ".cuh", ".h", ".f90", "Makefile")):
+    for top in (os.path.join(ROOT, "metalquicha_b200"), os.path.join(ROOT, "include")):
+        for dirpath, _, files in os.walk(top):
+            if os.path.basename(dirpath) == "build":
                 continue
-            text = open(os.path.join(dirpath, f), errors="replace").read()
-            if re.search(r"^\s*(from|import)\s+oracle\b|df_fock_oracle|df_fock_ref|oracle/", text, re.M):
-                offenders.append(os.path.join(dirpath, f))
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".f90", "Makefile")):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|df_fock_oracle|df_fock_ref|gto_integrals|scf_oracle|oracle/", text, re.M):
+                    offenders.append(os.path.join(dirpath, f))
     assert offenders == []
 
 

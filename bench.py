@@ -1132,6 +1132,14 @@ def main():
             torch.cuda.empty_cache()
         log(f"{name} done at {time.perf_counter() - t_start:.1f} s")
 
+    reference_pin = None
+    if ctx.rank == 0 and not args.no_reference_pin and not args.no_parity:
+        try:                                     # before the barrier: the other ranks wait there meanwhile
+            reference_pin = run_reference_pin(lambda: B200FockEngine(ctx.local_rank))
+            log(f"reference-held DF energy: |dE| = {reference_pin['abs_err']:.2e} (Fock builds on the GPU), "
+                f"{reference_pin['abs_err_whole_loop_on_gpu']:.2e} (whole loop on the GPU)")
+        except Exception as ex:                  # a check beside the headline never sinks it
+            reference_pin = {"error": str(ex)[:300]}
     if world > 1:
         dist.barrier()
     if ctx.rank == 0:
@@ -1146,13 +1154,8 @@ def main():
             if key not in ("value", "unit", "ms_per_step", "steps"):
                 line[key] = val
         line["workloads"] = {k: v for k, v in results.items() if k != args.workload}
-        if not args.no_reference_pin and not args.no_parity:
-            try:
-                line["reference_pin"] = run_reference_pin(lambda: B200FockEngine(ctx.local_rank))
-                log(f"reference-held DF energy: |dE| = {line['reference_pin']['abs_err']:.2e} (Fock builds on the GPU), "
-                    f"{line['reference_pin']['abs_err_whole_loop_on_gpu']:.2e} (whole loop on the GPU)")
-            except Exception as ex:              # a check beside the headline never sinks it
-                line["reference_pin"] = {"error": str(ex)[:300]}
+        if reference_pin is not None:
+            line["reference_pin"] = reference_pin
         line["bench_wall_s"] = time.perf_counter() - t_start
         emit(line)
     if world > 1:

@@ -126,12 +126,18 @@ class Diis:
 
 
 def run_rhf(h, s, n_electrons, fock_builder, e_nuc=0.0, max_iter=100, energy_tol=1e-10, density_tol=1e-8,
-            diis_vectors=8, guess="gwh", record=None):
+            diis_vectors=8, guess="gwh", record=None, guess_density=None, guess_fock=None):
     """``run_libcint_rhf`` around ``fock_builder(h, density, coeff, n_occ) -> (fock, e_elec)``.
-    Returns a dict with energy, electronic, iterations, converged, orbitals, density."""
+    Returns a dict with energy, electronic, iterations, converged, orbitals, density.
+    ``guess_density`` + ``guess_fock(h, density) -> fock``: the atomic guesses of the reference enter the loop as
+    ONE Fock build from the guess density (``atomic_guess_fock``, mqc_libcint_rhf.f90:1382-1411, call site :546);
+    on the fitted path that build goes through the density's pseudo-orbitals."""
     n_occ = n_electrons // 2
     x = build_orthogonalizer(s)
-    fock = guess_fock_gwh(s, h) if guess == "gwh" else np.array(h, copy=True)
+    if guess_density is not None:
+        fock = guess_fock(h, guess_density)
+    else:
+        fock = guess_fock_gwh(s, h) if guess == "gwh" else np.array(h, copy=True)
     coeff, eigenvalues = diagonalize(fock, x)
     density = build_density_closed_shell(coeff, n_occ)
     diis = Diis(diis_vectors)

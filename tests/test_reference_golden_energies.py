@@ -152,6 +152,38 @@ def test_density_fitted_scf_reproduces_the_reference_held_df_energy(df_case, bui
         assert plain["converged"] and abs(plain["energy"] - e_ref) < TOL_E
 
 
+def test_atomic_guess_through_pseudo_orbitals_lands_on_the_same_reference_energy():
+    """test/test_mqc_libcint_guess.f90:49 "guess_choice_does_not_change_the_energy", on the fitted path: an atomic
+    guess enters run_libcint_rhf as ONE build_fock_df from the guess density through ``density_pseudo_orbitals``
+    (atomic_guess_fock, rhf.f90:1382-1411; the factorisation :1413-1462) -- SURVEY 8 row a3.  From a crude
+    superposition-of-atoms density (block diagonal over the atoms, not idempotent, 10 electrons) the loop must
+    converge onto the reference-held fitted energy, and the pseudo-orbitals must rebuild their density to 1e-11
+    (test_mqc_libcint_guess.f90:332)."""
+    s, h, three, metric, e_nuc, n_electrons, e_ref = gto.df_case_integrals("h2o_631gs")
+    b = oracle.whiten(three, metric)
+    n = h.shape[0]
+    # free-atom-like occupations on the diagonal blocks: O 1s2 2s2 2p4 spread over its functions, H 1s1 each
+    occ = np.zeros(n)
+    occ[0], occ[1], occ[2:5], occ[5], occ[6:9] = 2.0, 1.4, 1.0, 0.6, 1.0 / 3.0        # oxygen s, sp inner, sp outer
+    occ[15], occ[16], occ[17], occ[18] = 0.7, 0.3, 0.7, 0.3                              # the two hydrogens
+    guess = np.diag(occ)
+    guess *= n_electrons / float(np.sum(guess * s))                                       # tr(D S) = N
+    pseudo, n_modes = oracle.density_pseudo_orbitals(guess)
+    assert np.max(np.abs(2.0 * pseudo @ pseudo.T - guess)) < 1e-11
+    assert n_modes > n_electrons // 2                                                     # not an idempotent density
+
+    def fock_builder(h_, density, coeff, n_occ):
+        f = oracle.build_fock_df(h_, b, density, coeff, n_occ)
+        return f, oracle.electronic_energy(h_, f, density)
+
+    def guess_fock(h_, density):
+        c, m = oracle.density_pseudo_orbitals(density)
+        return oracle.build_fock_df(h_, b, density, c, m)
+    res = scf.run_rhf(h, s, n_electrons, fock_builder, e_nuc=e_nuc, energy_tol=1e-12, density_tol=1e-10,
+                      guess_density=guess, guess_fock=guess_fock)
+    assert res["converged"] and abs(res["energy"] - e_ref) < TOL_E, res["energy"]
+
+
 def test_the_fitting_error_itself_matches():
     """check_df.f90:60-63 asserts the gap between the fitted and the exact energy, "the sharper one": a fitted
     energy could come out right with a wrong metric if errors cancelled, the error itself could not.  Same here on
